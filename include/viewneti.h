@@ -1,0 +1,176 @@
+/* viewneti.h — C-ABI of libviewneti_sm100a.so (hand-written sm_100a CUDA for the ViewNeTI hot path).
+ *
+ * The reference (jmhb0/view_neti) is pure Python and has NO FFI: every entry point below is new and
+ * replaces a library call the reference makes through torch/diffusers on the path
+ *     training/coach.py:197-214          unet(noisy_latents, timesteps, _hs).sample ; mse ; backward
+ *     models/xti_attention_processor.py  XTIAttenProc.__call__ (32x per UNet forward)
+ *     sd_pipeline_call.py:71-101         two-pass CFG denoise loop
+ * Each declaration cites the reference/diffusers operation it stands in for.  INTEGRATION.md shows the
+ * ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the caller
+ *     (PyTorch caching allocator); the library allocates nothing on the device.
+ *   - activations are NHWC / token-major [rows, C] bf16 with an explicit row stride `ld*` in ELEMENTS
+ *     (so channel-slices of a concat buffer are first-class); norm/bias parameters are fp32.
+ *   - all launches are asynchronous on the passed stream, no hidden syncs, CUDA-graph capturable.
+ *   - return 0 on success, negative on error (message: vn_last_error()); never throws, never exits.
+ *   - a process drives one device/stream at a time through this library (not thread-safe).
+ */
+#ifndef VIEWNETI_H_
+#define VIEWNETI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vn_stream_t;          /* cudaStream_t */
+
+#define VN_ABI_VERSION 1
+
+int         vn_version(void);
+const char* vn_last_error(void);
+/* number of kernels launched by this library since load / since last reset (bench `gpu_launches`). */
+int64_t     vn_launch_count(void);
+void        vn_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * tcgen05 / TMA GEMM and implicit-GEMM 3x3 convolution.
+ *   D[M,N] = A[M,K] * B[N,K]^T  (+ bias[N]) (+ rowbias[row / rows_per_batch, N]) (+ R[M,N])
+ * mode 0: A is [M,K] row-major bf16 (lda).          replaces torch Linear / 1x1 conv (cuBLAS) on
+ *         xti_attention_processor.py:30,38-42,53 (to_q/to_k/to_v/to_out), diffusers proj_in/proj_out,
+ *         FeedForward linears, conv_shortcut; with B = W^T it is the dgrad of the same op.
+ * mode 1: A is NHWC [nb,H,W,C] bf16 (pixel stride lda), 3x3 stride 1 pad 1, K = 9*C with
+ *         k = tap*C + c; M = nb*H*W.                 replaces cuDNN Conv2d in diffusers ResnetBlock2D /
+ *         Upsample2D; with flipped+transposed weights it is the conv dgrad.
+ * B is always [N,K] bf16 K-major (ldb).  D is bf16 (or fp32 when out_fp32) with row stride ldd.
+ * Constraints: K % 64 == 0 (mode 1: C % 64 == 0), N % 8 == 0, lda/ldb/ldd/ldr % 8 == 0, 16-byte aligned bases.
+ * Split-K: `workspace` must hold >= vn_gemm_workspace_bytes() bytes, be all-zero before the first call
+ * and is left all-zero by every call (self-cleaning), so one buffer serves a whole stream.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct vn_gemm_desc {
+  int32_t mode;
+  int32_t M, N, K;
+  int32_t nb, H, W, C;              /* mode 1 only */
+  const void* A;  int64_t lda;
+  const void* B;  int64_t ldb;
+  void*       D;  int64_t ldd;
+  const float* bias;                /* [N] or NULL */
+  const float* rowbias; int64_t ld_rowbias; int32_t rows_per_batch;   /* [nbatch,N] fp32 or NULL */
+  const void* R;  int64_t ldr;      /* residual [M,N] bf16 or NULL (may alias D) */
+  int32_t out_fp32;
+  void*   workspace; size_t workspace_bytes;
+  int32_t force_bn, force_split;    /* tuning/test overrides; 0 = auto */
+} vn_gemm_desc;
+
+size_t vn_gemm_workspace_bytes(int max_M, int max_N);
+int    vn_gemm(const vn_gemm_desc* d, vn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm (+ optional SiLU) over NHWC bf16 [nb, hw, C] — diffusers ResnetBlock2D.norm1/norm2,
+ * Transformer2DModel.norm, conv_norm_out (torch native_group_norm + silu).
+ * stats/red: fp32 [nb, groups, 2]; must be zero on entry of *_stats (they accumulate with atomics).
+ *   fwd stats = (sum x, sum x^2);  bwd red = (sum dxhat, sum dxhat*xhat)
+ * ------------------------------------------------------------------------------------------------ */
+int vn_groupnorm_stats(const void* x, int64_t ldx, int nb, int hw, int C, int groups, float* stats, vn_stream_t s);
+int vn_groupnorm_apply(const void* x, int64_t ldx, const float* stats, const float* gamma, const float* beta,
+                       float eps, int silu, void* y, int64_t ldy, int nb, int hw, int C, int groups, vn_stream_t s);
+int vn_groupnorm_bwd_stats(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* stats,
+                           const float* gamma, const float* beta, float eps, int silu, float* red,
+                           int nb, int hw, int C, int groups, vn_stream_t s);
+/* dx = GN^T(dy) (+ add1) (+ add2) */
+int vn_groupnorm_bwd_apply(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* stats,
+                           const float* red, const float* gamma, const float* beta, float eps, int silu,
+                           const void* add1, int64_t ldadd1, const void* add2, int64_t ldadd2,
+                           void* dx, int64_t lddx, int nb, int hw, int C, int groups, vn_stream_t s);
+
+/* LayerNorm over rows of [rows, C] bf16 — diffusers BasicTransformerBlock.norm1/2/3.
+ * stats: fp32 [rows,2] = (mean, rstd), written by fwd, read by bwd.  bwd: dx = LN^T(dy) (+ add). */
+int vn_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, float eps,
+                     void* y, int64_t ldy, float* stats, int rows, int C, vn_stream_t s);
+int vn_layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* gamma,
+                     const float* stats, const void* add, int64_t ldadd, void* dx, int64_t lddx,
+                     int rows, int C, vn_stream_t s);
+
+/* GEGLU — diffusers GEGLU: h = [a | g] ([rows, 2F]);  y = a * gelu_erf(g). */
+int vn_geglu_fwd(const void* h, int64_t ldh, void* y, int64_t ldy, int rows, int F, vn_stream_t s);
+int vn_geglu_bwd(const void* h, int64_t ldh, const void* dy, int64_t lddy, void* dh, int64_t lddh,
+                 int rows, int F, vn_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention core, head_dim 64 — xti_attention_processor.py:44-50:
+ *   head_to_batch_dim, get_attention_scores (fp32 logits: baddbmm alpha=scale, softmax), bmm, batch_to_head_dim.
+ * q/k/v/o are token-major with heads side by side: element (b, n, h, d) at  base + b*bs + n*ld + h*64 + d
+ * so head split/merge copies disappear.  K and V come from DIFFERENT tensors (XTI: K from
+ * CONTEXT_TENSOR_i, V from CONTEXT_TENSOR_BYPASS_i).  lse: fp32 [nb, heads, nq] (natural log), delta same shape.
+ * fwd: one flash kernel (logits never leave the SM).
+ * bwd: dq, dk, dv.  dk/dv may be accumulated in fp32 scratch `dkv_acc` ([2, nb, nk, heads*64] fp32, zero on
+ * entry, left zero) when nk is too small to parallelise over keys (cross-attention, nk = 77).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct vn_attn_desc {
+  int32_t nb, heads, nq, nk;
+  float   scale;
+  const void* q; int64_t ldq, bsq;
+  const void* k; int64_t ldk, bsk;
+  const void* v; int64_t ldv, bsv;
+  void*       o; int64_t ldo, bso;        /* fwd: out; bwd: in */
+  float*      lse;                        /* fwd: out; bwd: in */
+  /* backward only */
+  const void* d_o; int64_t lddo, bsdo;
+  float*      delta;                      /* scratch [nb, heads, nq] */
+  void* dq; int64_t lddq, bsdq;           /* may be NULL (pruned) */
+  void* dk; int64_t lddk, bsdk;
+  void* dv; int64_t lddv, bsdv;
+  float* dkv_acc;                         /* NULL or zeroed scratch, see above */
+} vn_attn_desc;
+int vn_attention_fwd(const vn_attn_desc* d, vn_stream_t s);
+int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------
+ * Resampling / small convolutions / glue
+ * ------------------------------------------------------------------------------------------------ */
+/* diffusers Upsample2D: nearest x2.  y [nb,2H,2W,C];  bwd: dx = 2x2 sum of dy (+ nothing) */
+int vn_upsample2x_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, int nb, int H, int W, int C, vn_stream_t s);
+int vn_upsample2x_bwd(const void* dy, int64_t lddy, void* dx, int64_t lddx, int nb, int H, int W, int C, vn_stream_t s);
+/* diffusers Downsample2D (Conv 3x3 stride 2 pad 1) = im2col + vn_gemm.  col [nb*Ho*Wo, 9*C], k = tap*C + c */
+int vn_im2col_s2(const void* x, int64_t ldx, void* col, int nb, int H, int W, int C, vn_stream_t s);
+/* dgrad: dx[nb,H,W,C] = col2im(dcol) (+ add) */
+int vn_col2im_s2(const void* dcol, const void* add, int64_t ldadd, void* dx, int64_t lddx,
+                 int nb, int H, int W, int C, vn_stream_t s);
+/* conv_in: NCHW fp32 latents [nb,Cin,H,W] -> NHWC bf16 [nb,H,W,Cout]; w fp32 [Cout,Cin,3,3] */
+int vn_conv_in_fwd(const float* x, const float* w, const float* bias, void* y, int64_t ldy,
+                   int nb, int Cin, int H, int W, int Cout, vn_stream_t s);
+/* conv_out: NHWC bf16 [nb,H,W,Cin] -> NCHW fp32 [nb,Cout,H,W]; w fp32 [Cout,Cin,3,3] */
+int vn_conv_out_fwd(const void* x, int64_t ldx, const float* w, const float* bias, float* y,
+                    int nb, int Cin, int H, int W, int Cout, vn_stream_t s);
+/* dgrad of conv_out: dy NCHW fp32 -> dx NHWC bf16 */
+int vn_conv_out_bwd(const float* dy, const float* w, void* dx, int64_t lddx,
+                    int nb, int Cin, int H, int W, int Cout, vn_stream_t s);
+/* diffusers Timesteps(flip_sin_to_cos=True, freq_shift=0): out fp32 [nb, dim] = [cos | sin] */
+int vn_timestep_sinusoid(const int64_t* t, float* out, int nb, int dim, vn_stream_t s);
+/* small-M linear for the time-embedding MLP and the 22 per-ResBlock time_emb_proj layers (one launch):
+ * y[b,n] = bias[n] + sum_k act(x[b,k]) * W[n,k];  W bf16 [N,K]; x,y fp32; silu_in applies SiLU to x. */
+int vn_gemv(const float* x, int64_t ldx, const void* W, const float* bias, float* y, int64_t ldy,
+            int nb, int N, int K, int silu_in, vn_stream_t s);
+/* fp32 -> bf16 cast of context tensors etc. (n elements) and bf16 -> fp32 */
+int vn_cast_f32_bf16(const float* x, void* y, int64_t n, vn_stream_t s);
+int vn_cast_bf16_f32(const void* x, float* y, int64_t n, vn_stream_t s);
+/* strided 2-D bf16 copy, dst[r, 0:cols] = src[r, 0:cols] (+ add[r, 0:cols]): torch.cat of the UNet skip
+ * connections (diffusers up blocks) and the gradient fan-in of the residual stream in the backward pass. */
+int vn_copy2d(const void* src, int64_t lds, const void* add, int64_t ldadd, void* dst, int64_t ldd,
+              int64_t rows, int cols, vn_stream_t s);
+/* coach.py:211-213  loss = mean((pred-target)^2) in fp32; also dpred = 2*(pred-target)/n * loss_scale */
+int vn_mse_loss(const float* pred, const float* target, int64_t n, float loss_scale, float* loss, float* dpred, vn_stream_t s);
+/* sd_pipeline_call.py:98,101 fused: eps = u + g*(c-u); DDIM (eta=0) step for epsilon / v prediction.
+ * latents fp32 [n] updated in place.  acp_t / acp_prev = alphas_cumprod at t / t_prev; vpred: 0 eps, 1 v. */
+int vn_cfg_ddim_step(float* latents, const float* eps_uncond, const float* eps_cond, int64_t n,
+                     float guidance, float acp_t, float acp_prev, int vpred, vn_stream_t s);
+int vn_memset_zero(void* p, size_t bytes, vn_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIEWNETI_H_ */

@@ -1,0 +1,246 @@
+"""Tensor-level wrappers over the C-ABI (include/viewneti.h): torch tensors in, raw pointers across.
+
+Activations are bf16, channel-last, possibly channel-slices of a wider buffer: every wrapper takes
+"rows x C" views whose last dim is contiguous and passes the row stride as `ld`.  Nothing here
+computes: each function is exactly one library call (there is no CPU / eager fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _abi
+from ._abi import AttnDesc, GemmDesc, check, ptr, stream
+
+BF16 = torch.bfloat16
+
+
+def _ld(t: torch.Tensor) -> int:
+    """Row stride (elements) of a [..., rows, C] view with contiguous last dim and collapsible leading dims."""
+    assert t.stride(-1) == 1, "last dim must be contiguous"
+    ld = t.stride(-2)
+    exp = ld * t.shape[-2]
+    for i in range(t.dim() - 3, -1, -1):          # leading dims must collapse onto the row dim
+        if t.shape[i] != 1:
+            assert t.stride(i) == exp, f"view does not collapse to rows: shape {tuple(t.shape)} stride {t.stride()}"
+            exp *= t.shape[i]
+    return ld
+
+
+class Workspace:
+    """Split-K scratch for vn_gemm (zero on entry, left zero by every call) + fp32 dK/dV accumulator."""
+
+    def __init__(self, max_m: int, max_n: int, device, dkv_elems: int = 0):
+        lib = _abi.load()
+        self.bytes = int(lib.vn_gemm_workspace_bytes(max_m, max_n))
+        self.buf = torch.zeros(self.bytes, dtype=torch.uint8, device=device)
+        self.dkv = torch.zeros(max(dkv_elems, 1), dtype=torch.float32, device=device)
+
+
+def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, bias=None, rowbias=None, rows_per_batch: int = 0,
+         R=None, ws: Optional[Workspace] = None, force_bn: int = 0, force_split: int = 0) -> torch.Tensor:
+    """D[M,N] = A[M,K] @ B[N,K]^T (+bias[N]) (+rowbias[row // rows_per_batch, N]) (+R[M,N])."""
+    lib = _abi.load()
+    M, K = A.shape[-2] * (A.numel() // (A.shape[-1] * A.shape[-2])), A.shape[-1]
+    N = B.shape[0]
+    assert B.shape[1] == K and A.dtype == BF16 and B.dtype == BF16
+    d = GemmDesc()
+    d.mode = 0
+    d.M, d.N, d.K = M, N, K
+    d.A, d.lda = ptr(A), _ld(A)
+    d.B, d.ldb = ptr(B), B.stride(0)
+    d.D, d.ldd = ptr(D), _ld(D)
+    d.out_fp32 = 1 if D.dtype == torch.float32 else 0
+    d.bias = ptr(bias)
+    if rowbias is not None:
+        d.rowbias, d.ld_rowbias, d.rows_per_batch = ptr(rowbias), rowbias.stride(0), rows_per_batch
+    if R is not None:
+        d.R, d.ldr = ptr(R), _ld(R)
+    if ws is not None:
+        d.workspace, d.workspace_bytes = ptr(ws.buf), ws.bytes
+    d.force_bn, d.force_split = force_bn, force_split
+    check(lib.vn_gemm(C.byref(d), stream()), "vn_gemm")
+    return D
+
+
+def conv3x3(x: torch.Tensor, Wk: torch.Tensor, D: torch.Tensor, *, bias=None, rowbias=None, R=None,
+            ws: Optional[Workspace] = None, force_bn: int = 0, force_split: int = 0) -> torch.Tensor:
+    """Implicit-GEMM 3x3 / stride 1 / pad 1 conv.  x [nb,H,W,C] NHWC view, Wk [N, 9*C] (k = tap*C + c), D [nb,H,W,N]."""
+    lib = _abi.load()
+    nb, H, W, Cc = x.shape
+    N = Wk.shape[0]
+    assert Wk.shape[1] == 9 * Cc and x.stride(3) == 1
+    assert x.stride(1) == W * x.stride(2) and (nb == 1 or x.stride(0) == H * x.stride(1))
+    d = GemmDesc()
+    d.mode = 1
+    d.M, d.N, d.K = nb * H * W, N, 9 * Cc
+    d.nb, d.H, d.W, d.C = nb, H, W, Cc
+    d.A, d.lda = ptr(x), x.stride(2)
+    d.B, d.ldb = ptr(Wk), Wk.stride(0)
+    d.D, d.ldd = ptr(D), D.stride(-2)
+    d.out_fp32 = 1 if D.dtype == torch.float32 else 0
+    d.bias = ptr(bias)
+    if rowbias is not None:
+        d.rowbias, d.ld_rowbias, d.rows_per_batch = ptr(rowbias), rowbias.stride(0), H * W
+    if R is not None:
+        d.R, d.ldr = ptr(R), R.stride(-2)
+    if ws is not None:
+        d.workspace, d.workspace_bytes = ptr(ws.buf), ws.bytes
+    d.force_bn, d.force_split = force_bn, force_split
+    check(lib.vn_gemm(C.byref(d), stream()), "vn_gemm(conv)")
+    return D
+
+
+# ---- GroupNorm / LayerNorm / GEGLU -------------------------------------------------------------
+def groupnorm_stats(x, nb, hw, groups, stats):
+    check(_abi.load().vn_groupnorm_stats(ptr(x), _ld(x), nb, hw, x.shape[-1], groups, ptr(stats), stream()), "gn_stats")
+
+
+def groupnorm_apply(x, stats, gamma, beta, eps, silu, y, nb, hw, groups):
+    check(_abi.load().vn_groupnorm_apply(ptr(x), _ld(x), ptr(stats), ptr(gamma), ptr(beta), eps, int(silu), ptr(y),
+                                         _ld(y), nb, hw, x.shape[-1], groups, stream()), "gn_apply")
+
+
+def groupnorm_bwd(x, dy, stats, red, gamma, beta, eps, silu, dx, nb, hw, groups, add1=None, add2=None):
+    lib = _abi.load()
+    Cc = x.shape[-1]
+    check(lib.vn_groupnorm_bwd_stats(ptr(x), _ld(x), ptr(dy), _ld(dy), ptr(stats), ptr(gamma), ptr(beta), eps, int(silu),
+                                     ptr(red), nb, hw, Cc, groups, stream()), "gn_bwd_stats")
+    check(lib.vn_groupnorm_bwd_apply(ptr(x), _ld(x), ptr(dy), _ld(dy), ptr(stats), ptr(red), ptr(gamma), ptr(beta), eps,
+                                     int(silu), ptr(add1), _ld(add1) if add1 is not None else 0, ptr(add2),
+                                     _ld(add2) if add2 is not None else 0, ptr(dx), _ld(dx), nb, hw, Cc, groups,
+                                     stream()), "gn_bwd_apply")
+
+
+def layernorm_fwd(x, gamma, beta, eps, y, stats, rows):
+    check(_abi.load().vn_layernorm_fwd(ptr(x), _ld(x), ptr(gamma), ptr(beta), eps, ptr(y), _ld(y), ptr(stats), rows,
+                                       x.shape[-1], stream()), "ln_fwd")
+
+
+def layernorm_bwd(x, dy, gamma, stats, dx, rows, add=None):
+    check(_abi.load().vn_layernorm_bwd(ptr(x), _ld(x), ptr(dy), _ld(dy), ptr(gamma), ptr(stats), ptr(add),
+                                       _ld(add) if add is not None else 0, ptr(dx), _ld(dx), rows, x.shape[-1],
+                                       stream()), "ln_bwd")
+
+
+def geglu_fwd(h, y, rows):
+    check(_abi.load().vn_geglu_fwd(ptr(h), _ld(h), ptr(y), _ld(y), rows, y.shape[-1], stream()), "geglu_fwd")
+
+
+def geglu_bwd(h, dy, dh, rows):
+    check(_abi.load().vn_geglu_bwd(ptr(h), _ld(h), ptr(dy), _ld(dy), ptr(dh), _ld(dh), rows, dy.shape[-1], stream()),
+          "geglu_bwd")
+
+
+# ---- attention ----------------------------------------------------------------------------------
+def _attn_desc(q, k, v, o, lse, heads, scale) -> AttnDesc:
+    """q,o: [nb, nq, heads*64] views; k,v: [nb, nk, heads*64] views (last dim contiguous)."""
+    d = AttnDesc()
+    d.nb, d.nq, d.nk, d.heads, d.scale = q.shape[0], q.shape[1], k.shape[1], heads, scale
+    d.q, d.ldq, d.bsq = ptr(q), q.stride(1), q.stride(0)
+    d.k, d.ldk, d.bsk = ptr(k), k.stride(1), k.stride(0)
+    d.v, d.ldv, d.bsv = ptr(v), v.stride(1), v.stride(0)
+    d.o, d.ldo, d.bso = ptr(o), o.stride(1), o.stride(0)
+    d.lse = ptr(lse)
+    return d
+
+
+def attention_fwd(q, k, v, o, lse, heads, scale=0.125):
+    d = _attn_desc(q, k, v, o, lse, heads, scale)
+    check(_abi.load().vn_attention_fwd(C.byref(d), stream()), "attention_fwd")
+
+
+def attention_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, heads, scale=0.125, dkv_acc=None):
+    d = _attn_desc(q, k, v, o, lse, heads, scale)
+    d.d_o, d.lddo, d.bsdo = ptr(d_o), d_o.stride(1), d_o.stride(0)
+    d.delta = ptr(delta)
+    if dq is not None:
+        d.dq, d.lddq, d.bsdq = ptr(dq), dq.stride(1), dq.stride(0)
+    d.dk, d.lddk, d.bsdk = ptr(dk), dk.stride(1), dk.stride(0)
+    d.dv, d.lddv, d.bsdv = ptr(dv), dv.stride(1), dv.stride(0)
+    d.dkv_acc = ptr(dkv_acc)
+    check(_abi.load().vn_attention_bwd(C.byref(d), stream()), "attention_bwd")
+
+
+# ---- resampling / edge convs / glue -------------------------------------------------------------
+def upsample2x_fwd(x, y):
+    nb, H, W, Cc = x.shape
+    check(_abi.load().vn_upsample2x_fwd(ptr(x), x.stride(2), ptr(y), y.stride(2), nb, H, W, Cc, stream()), "upsample")
+
+
+def upsample2x_bwd(dy, dx):
+    nb, H, W, Cc = dx.shape
+    check(_abi.load().vn_upsample2x_bwd(ptr(dy), dy.stride(2), ptr(dx), dx.stride(2), nb, H, W, Cc, stream()),
+          "upsample_bwd")
+
+
+def im2col_s2(x, col):
+    nb, H, W, Cc = x.shape
+    check(_abi.load().vn_im2col_s2(ptr(x), x.stride(2), ptr(col), nb, H, W, Cc, stream()), "im2col_s2")
+
+
+def col2im_s2(dcol, dx, add=None):
+    nb, H, W, Cc = dx.shape
+    check(_abi.load().vn_col2im_s2(ptr(dcol), ptr(add), add.stride(2) if add is not None else 0, ptr(dx), dx.stride(2),
+                                   nb, H, W, Cc, stream()), "col2im_s2")
+
+
+def conv_in_fwd(x, w, bias, y):
+    nb, Cin, H, W = x.shape
+    check(_abi.load().vn_conv_in_fwd(ptr(x), ptr(w), ptr(bias), ptr(y), y.stride(2), nb, Cin, H, W, y.shape[-1],
+                                     stream()), "conv_in")
+
+
+def conv_out_fwd(x, w, bias, y):
+    nb, H, W, Cin = x.shape
+    check(_abi.load().vn_conv_out_fwd(ptr(x), x.stride(2), ptr(w), ptr(bias), ptr(y), nb, Cin, H, W, y.shape[1],
+                                      stream()), "conv_out")
+
+
+def conv_out_bwd(dy, w, dx):
+    nb, Cout, H, W = dy.shape
+    check(_abi.load().vn_conv_out_bwd(ptr(dy), ptr(w), ptr(dx), dx.stride(2), nb, dx.shape[-1], H, W, Cout, stream()),
+          "conv_out_bwd")
+
+
+def timestep_sinusoid(t, out):
+    check(_abi.load().vn_timestep_sinusoid(ptr(t), ptr(out), out.shape[0], out.shape[1], stream()), "timestep")
+
+
+def gemv(x, W, bias, y, silu_in=False):
+    check(_abi.load().vn_gemv(ptr(x), x.stride(0), ptr(W), ptr(bias), ptr(y), y.stride(0), x.shape[0], W.shape[0],
+                              W.shape[1], int(silu_in), stream()), "gemv")
+
+
+def cast_f32_bf16(x, y):
+    check(_abi.load().vn_cast_f32_bf16(ptr(x), ptr(y), x.numel(), stream()), "cast")
+
+
+def cast_bf16_f32(x, y):
+    check(_abi.load().vn_cast_bf16_f32(ptr(x), ptr(y), x.numel(), stream()), "cast")
+
+
+def copy2d(src, dst, add=None):
+    rows = src.numel() // src.shape[-1]
+    check(_abi.load().vn_copy2d(ptr(src), _ld(src), ptr(add), _ld(add) if add is not None else 0, ptr(dst), _ld(dst),
+                                rows, src.shape[-1], stream()), "copy2d")
+
+
+def mse_loss(pred, target, loss, dpred=None, loss_scale=1.0):
+    check(_abi.load().vn_mse_loss(ptr(pred), ptr(target), pred.numel(), loss_scale, ptr(loss), ptr(dpred), stream()),
+          "mse")
+
+
+def cfg_ddim_step(latents, eps_u, eps_c, guidance, acp_t, acp_prev, vpred):
+    check(_abi.load().vn_cfg_ddim_step(ptr(latents), ptr(eps_u), ptr(eps_c), latents.numel(), guidance, acp_t, acp_prev,
+                                       int(vpred), stream()), "cfg_ddim")
+
+
+def launch_count() -> int:
+    return int(_abi.load().vn_launch_count())
+
+
+def launch_count_reset() -> None:
+    _abi.load().vn_launch_count_reset()
