@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — TI train images/s of the ViewNeTI hot path (SD-2.1, 512^2 => 64x64x4 latents, 77x1024 contexts).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--latent 64]
+    N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+One "step" = one train image per GPU: frozen UNet forward + fp32 MSE + dgrad-only backward to the 32 XTI context
+tensors (reference training/coach.py:197-214), batch-parallel over ranks (per-GPU batch 1, BASELINE config 2/3),
+plus — for N > 1 — the single NCCL all-reduce of the flat mapper-gradient buffer.
+Prints ONE JSON line (rank 0).  `value` = whole-job images/s with inputs resident in HBM (CUDA-graph replay);
+`e2e` = the same metric through the drop-in Python API (UNet2DConditionModel.__call__ + mse_loss + backward) with
+pinned-host inputs copied in every step and the loss read back.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic work per train image (SURVEY.md 8d / BASELINE.md 3): 2*MAC of every conv / linear / attention GEMM
+GFLOP_TRAIN = {64: 1671.3, 32: 362.9}
+GFLOP_FWD = {64: 804.3, 32: 181.1}
+MAPPER_GRAD_ELEMS = 2 * 141696          # M_v + active M_o
+METRIC = "TI train images/sec (SD2.1, 512^2)"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def oracle_train_step_time(latent: int, steps: int, warmup: int, budget_s: float):
+    """Times the fp32 CPU oracle (our restatement of the reference's diffusers path; the reference itself cannot be
+    installed here) on the same workload.  Returns (seconds per image, images timed, threads)."""
+    from oracle.unet_sd21 import UNetOracle, train_step_oracle
+    from tests.unet_parity import ctx_to, make_inputs
+    from view_neti_b200.sd21 import SD21, init_state_dict
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    unet = UNetOracle(SD21)
+    unet.load_state_dict(init_state_dict(SD21, 0))
+    lat, t, tgt, ctx = make_inputs(SD21, 1, latent, latent, seed=1)
+    t_start = time.time()
+    done_w, times = 0, []
+    while done_w < warmup and (time.time() - t_start) < budget_s * 0.4:
+        train_step_oracle(unet, lat, t, tgt, ctx_to(ctx, "cpu"))
+        done_w += 1
+    while len(times) < steps:
+        t0 = time.time()
+        train_step_oracle(unet, lat, t, tgt, ctx_to(ctx, "cpu"))
+        times.append(time.time() - t0)
+        if time.time() - t_start > budget_s:
+            break
+    return sum(times) / len(times), len(times), threads, done_w
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    per, n, threads, done_w = oracle_train_step_time(args.latent, max(1, args.steps), args.warmup, budget_s=200.0)
+    v = 1.0 / per
+    sample = (f"{n} timed + {done_w} warm-up train images (fwd + fp32 MSE + autograd backward to the 32 contexts) at "
+              f"{args.latent}x{args.latent} latents, B=1, fp32 PyTorch eager on the host CPU; wall budget 200 s "
+              f"(requested steps={args.steps}, warmup={args.warmup})")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": n,
+        "warmup": done_w, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": f"mode 2 single-scene TI step, SD2.1 {args.latent * 8}x{args.latent * 8}, bs=1 "
+                               f"({args.latent}x{args.latent}x4 latents, 16+16 contexts 77x1024)",
+                   "note": "reference arm = oracle port of the reference's diffusers CPU path (diffusers/accelerate "
+                           "are not installable offline; see DESIGN.md)"},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+def profile_categories(plan):
+    """One instrumented eager train step: CUDA events around every library call, summed per kernel family."""
+    from view_neti_b200 import ops
+    cats = {}
+    names = {"gemm": "gemm", "conv3x3": "conv", "attention_fwd": "attn", "attention_bwd": "attn"}
+    orig = {}
+    flops = {"gemm": 0.0, "conv": 0.0}
+
+    def wrap(fname, cat):
+        f = getattr(ops, fname)
+        orig[fname] = f
+
+        def g(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = f(*a, **k)
+            e1.record()
+            cats.setdefault(cat, []).append((e0, e1))
+            if fname == "gemm":
+                A, B = a[0], a[1]
+                flops["gemm"] += 2.0 * (A.numel() // A.shape[-1]) * B.shape[0] * B.shape[1]
+            elif fname == "conv3x3":
+                x, Wk = a[0], a[1]
+                flops["conv"] += 2.0 * (x.numel() // x.shape[-1]) * Wk.shape[0] * Wk.shape[1]
+            return r
+        setattr(ops, fname, g)
+
+    for fname in dir(ops):
+        f = getattr(ops, fname)
+        if callable(f) and f.__module__ == ops.__name__ and not fname.startswith("_") and fname not in (
+                "launch_count", "launch_count_reset", "check", "ptr", "stream") and not isinstance(f, type):
+            wrap(fname, names.get(fname, "other"))
+    try:
+        plan.train_step()
+        torch.cuda.synchronize()
+    finally:
+        for fname, f in orig.items():
+            setattr(ops, fname, f)
+    ms = {c: sum(a.elapsed_time(b) for a, b in ev) for c, ev in cats.items()}
+    n = {c: len(ev) for c, ev in cats.items()}
+    return ms, n, flops
+
+
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from view_neti_b200 import ops
+    from view_neti_b200.sd21 import SD21, init_state_dict
+    from view_neti_b200.unet import UNet2DConditionModel
+    from tests.unet_parity import make_inputs
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = args.latent
+    cfg = SD21
+    model = UNet2DConditionModel(init_state_dict(cfg, 0), cfg, dev)
+    plan = model.engine.plan(1, L, L)
+    lat, t, tgt, ctx = make_inputs(cfg, 1, L, L, seed=1 + rank)       # per-rank samples (weak scaling)
+    plan.latents.copy_(lat); plan.timesteps.copy_(t); plan.target.copy_(tgt)
+    for i in range(cfg.num_cross_layers):
+        plan.ctx[0, i].copy_(ctx[f"CONTEXT_TENSOR_{i}"]); plan.ctx[1, i].copy_(ctx[f"CONTEXT_TENSOR_BYPASS_{i}"])
+    flat = torch.zeros(MAPPER_GRAD_ELEMS, device=dev)               # flat mapper-gradient buffer (M_v + M_o)
+
+    graph = plan.capture("train")
+    launches_per_step = plan.launches["train"]
+
+    def step():
+        graph.replay()
+        if world > 1:
+            # stand-in for the CLIP/mapper backward ("next"): the buffer depends on this step's d_ctx
+            flat.copy_(plan.d_ctx.view(-1)[:MAPPER_GRAD_ELEMS])
+            dist.all_reduce(flat)
+            flat.mul_(1.0 / world)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    ms_per_step = ms_total / args.steps
+    value = world * args.steps / (ms_total / 1e3)
+    loss_dev = float(plan.loss)
+
+    # ---- end to end through the drop-in API, host-resident inputs ------------------------------------------
+    pin = lambda x: x.clone().pin_memory()      # noqa: E731
+    h_lat, h_t, h_tgt = pin(lat), pin(t), pin(tgt)
+    h_ctx = {k: pin(v) for k, v in ctx.items() if torch.is_tensor(v)}
+    h2d = sum(x.numel() * x.element_size() for x in [h_lat, h_t, h_tgt, *h_ctx.values()])
+
+    def e2e_step():
+        d_lat = h_lat.to(dev, non_blocking=True)
+        d_t = h_t.to(dev, non_blocking=True)
+        d_tgt = h_tgt.to(dev, non_blocking=True)
+        d_ctx = {"this_idx": 0}
+        for k, v in h_ctx.items():
+            d_ctx[k] = v.to(dev, non_blocking=True).requires_grad_(True)
+        pred = model(d_lat, d_t, d_ctx).sample                       # coach.py:197-198
+        loss = F.mse_loss(pred.float(), d_tgt.float(), reduction="mean")   # :211-213
+        loss.backward()                                                    # :214
+        if world > 1:
+            flat.copy_(torch.cat([d_ctx["CONTEXT_TENSOR_0"].grad.view(-1)[:MAPPER_GRAD_ELEMS // 2],
+                                  d_ctx["CONTEXT_TENSOR_BYPASS_0"].grad.view(-1)[:MAPPER_GRAD_ELEMS // 2]]))
+            dist.all_reduce(flat)
+        return float(loss.detach().cpu())                                 # D2H read of the step's result (:257)
+
+    ops.launch_count_reset()
+    for _ in range(3):
+        e2e_loss = e2e_step()
+    e2e_launches_eager = ops.launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    k2 = max(3, min(args.steps, 20))
+    e0.record()
+    for _ in range(k2):
+        e2e_loss = e2e_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * k2 / (float(ms2) / 1e3)
+    api_plan = model.engine.plan(1, L, L)
+    e2e_launches = api_plan.launches.get("fwd", 0) + api_plan.launches.get("bwd", 0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (vn_gemm_kernel: every conv / linear), measured live ----------------
+    peaks, peak_src = measured_peaks()
+    cat_ms, cat_n, flops = profile_categories(plan)
+    tot_ms = sum(cat_ms.values())
+    gemm_ms = cat_ms.get("gemm", 0.0) + cat_ms.get("conv", 0.0)
+    gemm_flops = flops["gemm"] + flops["conv"]
+    gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    step_tflops = GFLOP_TRAIN.get(L, 0.0) * 1e9 / (ms_per_step * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("vn_gemm_kernel_dram_bytes_per_launch")
+    roofline = {
+        "bound": "tensor", "kernel": "vn_gemm_kernel (tcgen05 GEMM + implicit-GEMM conv; all Linear/Conv fwd + dgrad)",
+        "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak if peak else None,
+        "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
+        "traffic": traffic,
+        "launches_per_step": cat_n.get("gemm", 0) + cat_n.get("conv", 0),
+        "flops_per_step": gemm_flops, "avg_launch_us": 1e3 * gemm_ms / max(1, cat_n.get("gemm", 0) + cat_n.get("conv", 0)),
+        "share_of_step": gemm_ms / tot_ms if tot_ms else None,
+        "category_ms_eager": {k: round(v, 4) for k, v in cat_ms.items()},
+        "category_launches": cat_n,
+        "whole_step": {"gflop_per_image": GFLOP_TRAIN.get(L), "achieved": step_tflops,
+                       "frac": step_tflops / peak if peak else None},
+    }
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample --------------------------------
+    per, n, threads, done_w = oracle_train_step_time(L, steps=1, warmup=0, budget_s=60.0)
+    cpu = {"value": 1.0 / per, "unit": "images/s", "cores": threads, "kind": "port",
+           "sample": f"{n} train image(s) (fwd + MSE + backward to 32 contexts) at {L}x{L} latents, fp32 PyTorch eager, "
+                     f"{threads} threads, no warm-up"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"mode 2 single-scene TI step, SD2.1 {L * 8}x{L * 8}, bs=1 per GPU "
+                               f"({L}x{L}x4 latents, 16+16 contexts 77x1024), UNet fwd + fp32 MSE + dgrad backward "
+                               f"to the 32 contexts" + (", + all-reduce of the flat mapper-grad buffer" if world > 1 else ""),
+                   "global_batch": world, "parallelism": f"dp{world}", "weights": "seeded random, SD-2.1 shapes (865.9M)",
+                   "l2": "weights streamed per step (2 x 1.73 GB fwd + dgrad copies) exceed the 126 MB L2",
+                   "graph": "one CUDA graph per step"},
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "steps": k2, "api": "UNet2DConditionModel.__call__ + F.mse_loss + backward (CUDA-graph replay inside)"},
+        "gpu_launches": launches_per_step * args.steps + e2e_launches * k2 + e2e_launches_eager,
+        "launches_per_step": launches_per_step,
+        "clocks": clocks.summary(),
+        "loss": loss_dev, "e2e_loss": e2e_loss,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--latent", type=int, default=64)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    if world != args.gpus:
+        print(f"bench.py: WORLD_SIZE={world} but --gpus {args.gpus}; using WORLD_SIZE", file=sys.stderr)
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

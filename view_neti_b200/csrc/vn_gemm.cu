@@ -6,18 +6,23 @@
 // (xti_attention_processor.py:30,38-42,53; ResnetBlock2D conv1/conv2/conv_shortcut; Transformer2DModel
 // proj_in/out; FeedForward) and, with pre-transposed weights, their dgrads (coach.py:214).
 //
-// Kernel shape (one 128 x BN output tile per CTA, optional split-K over gridDim.z):
-//   warp 0      : TMA producer   — one elected lane; A tile [128 rows x 64 k] + B tile [BN x 64 k] per stage,
-//                                  128B-swizzled, completion on the stage's `full` mbarrier.
-//                                  conv mode: A comes from a 4-D NHWC tensor map, one (tap, 64-channel) slab per
-//                                  k-block at coordinates (c0, w0+dx-1, h0+dy-1, b); TMA zero-fills the halo,
-//                                  so padding costs nothing and no im2col buffer exists.
-//   warp 1      : MMA issuer     — allocates TMEM, one lane issues 4 x tcgen05.mma (K=16) per stage,
-//                                  tcgen05.commit releases the stage / signals the epilogue.
-//   warps 2..5  : epilogue       — tcgen05.ld 32 lanes x 32 columns at a time; fused bias / time-embedding
-//                                  row-bias / residual; 16-byte stores.  Split-K: fp32 red.add into a
-//                                  self-cleaning workspace, last-arriving CTA of a tile runs the epilogue.
+// One kernel template, two schedules:
+//   PERSISTENT (SPLIT = false): grid = min(tiles, #SMs), one CTA per SM walks 128 x BN output tiles.
+//     warp 0    : TMA producer — A tile [128 x 64] + B tile [BN x 64] per stage (128B swizzle); conv mode takes A from a
+//                 4-D NHWC tensor map, one (tap, 64-channel) slab per k-block at (c0, w0+dx-1, h0+dy-1, img): TMA
+//                 zero-fills the halo, so padding is free and no im2col buffer exists.  It also prefetches the
+//                 residual tile into the output staging buffer.
+//     warp 1    : MMA issuer — one lane issues 4 x tcgen05.mma (K=16) per stage into one of TWO TMEM accumulator
+//                 stages, so the epilogue of tile i overlaps the main loop of tile i+1.
+//     warps 2-5 : epilogue — tcgen05.ld, + bias / time-embedding row-bias / residual (read from smem), bf16 pack into
+//                 the swizzled staging tile, TMA store (clips the M / N tails).
+//   SPLIT-K (SPLIT = true): for few-tile / long-K problems (deep UNet levels, M = 64..1024).  A thread-block CLUSTER of
+//     S in {2,4,8} CTAs shares one output tile, each CTA accumulates K/S in its own TMEM; partials are exchanged
+//     through DISTRIBUTED SHARED MEMORY (st.shared::cluster), CTA r reduces rows [r*128/S, (r+1)*128/S) and runs
+//     the epilogue for them.  No global atomics, no workspace, deterministic.
 #include "vn_common.cuh"
+
+#include <string.h>
 
 namespace {
 
@@ -29,108 +34,168 @@ struct GemmParams {
   int M, N;
   int kb_total, kb_per_split, splits;
   int mode;
+  int m_tiles, n_tiles;
   int H, W, cblocks, tw, th, tiles_w, tiles_h, rows_a;
   void* D; long long ldd;
   const float* bias;
   const float* rowbias; long long ld_rowbias; int rows_per_batch;
   const bf16* R; long long ldr;
   int out_fp32;
-  float* ws; int* counters;
+  int use_tma_epilogue;
 };
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// Finish one 32-column chunk of one output row: v[] holds fp32 sums.
-__device__ __forceinline__ void epilogue_store(const GemmParams& p, float (&v)[32], long long gm, int bidx, int n_base) {
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int n = n_base + g * 8;
-    if (n >= p.N) break;
-    float o[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = v[g * 8 + j];
-    if (p.bias) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-      o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
-      o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
-    }
-    if (p.rowbias) {
-      const float* rb = p.rowbias + (long long)bidx * p.ld_rowbias + n;
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(rb + 4));
-      o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
-      o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
-    }
-    if (p.R) {
-      const uint4 r = *reinterpret_cast<const uint4*>(p.R + gm * p.ldr + n);
-      float2 t;
-      t = unpack_bf162(r.x); o[0] += t.x; o[1] += t.y;
-      t = unpack_bf162(r.y); o[2] += t.x; o[3] += t.y;
-      t = unpack_bf162(r.z); o[4] += t.x; o[5] += t.y;
-      t = unpack_bf162(r.w); o[6] += t.x; o[7] += t.y;
-    }
-    if (p.out_fp32) {
-      float* dst = reinterpret_cast<float*>(p.D) + gm * p.ldd + n;
-      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
-    } else {
-      uint4 w;
-      w.x = pack_bf162(o[0], o[1]); w.y = pack_bf162(o[2], o[3]);
-      w.z = pack_bf162(o[4], o[5]); w.w = pack_bf162(o[6], o[7]);
-      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.D) + gm * p.ldd + n) = w;
-    }
+// Direct (register -> global) finish of 8 consecutive columns of one output row; used by the fp32 and split-K paths.
+__device__ __forceinline__ void store8(const GemmParams& p, float (&o)[8], long long gm, int bidx, int n) {
+  if (p.bias) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+    o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+    o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+  }
+  if (p.rowbias) {
+    const float* rb = p.rowbias + (long long)bidx * p.ld_rowbias + n;
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(rb + 4));
+    o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+    o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+  }
+  if (p.R) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p.R + gm * p.ldr + n);
+    float2 t;
+    t = unpack_bf162(r.x); o[0] += t.x; o[1] += t.y;
+    t = unpack_bf162(r.y); o[2] += t.x; o[3] += t.y;
+    t = unpack_bf162(r.z); o[4] += t.x; o[5] += t.y;
+    t = unpack_bf162(r.w); o[6] += t.x; o[7] += t.y;
+  }
+  if (p.out_fp32) {
+    float* dst = reinterpret_cast<float*>(p.D) + gm * p.ldd + n;
+    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  } else {
+    uint4 w;
+    w.x = pack_bf162(o[0], o[1]); w.y = pack_bf162(o[2], o[3]);
+    w.z = pack_bf162(o[4], o[5]); w.w = pack_bf162(o[6], o[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.D) + gm * p.ldd + n) = w;
   }
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads) vn_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                            const __grid_constant__ CUtensorMap tmB,
-                                                            const GemmParams p) {
+struct TileCoord {
+  int m0, n0, img, h0, w0;
+};
+__device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int tile, int bn) {
+  TileCoord c;
+  const int mt = tile % p.m_tiles;
+  c.n0 = (tile / p.m_tiles) * bn;
+  c.m0 = 0; c.img = 0; c.h0 = 0; c.w0 = 0;
+  if (p.mode == 0) {
+    c.m0 = mt * BM;
+  } else {
+    const int tpi = p.tiles_w * p.tiles_h;
+    c.img = mt / tpi;
+    const int r = mt - c.img * tpi;
+    c.h0 = (r / p.tiles_w) * p.th;
+    c.w0 = (r % p.tiles_w) * p.tw;
+  }
+  return c;
+}
+// global row index, batch index and validity of tile row r
+__device__ __forceinline__ bool tile_row(const GemmParams& p, const TileCoord& c, int r, long long* gm, int* bidx) {
+  if (p.mode == 0) {
+    *gm = (long long)c.m0 + r;
+    *bidx = p.rows_per_batch > 0 ? (int)(*gm / p.rows_per_batch) : 0;
+    return *gm < p.M;
+  }
+  const int ty = r / p.tw, tx = r - ty * p.tw;
+  const int h = c.h0 + ty, w = c.w0 + tx;
+  *gm = ((long long)c.img * p.H + h) * p.W + w;
+  *bidx = c.img;
+  return (r < p.rows_a) && (h < p.H) && (w < p.W);
+}
+
+template <int BN, int STAGES, bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               const __grid_constant__ CUtensorMap tmD,
+                                                               const __grid_constant__ CUtensorMap tmR,
+                                                               const GemmParams p) {
   constexpr int A_BYTES = BM * BK * 2;            // 16 KB
   constexpr int B_BYTES = BN * BK * 2;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // multiple of 1024 for BN % 8 == 0
-  constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024-byte alignment");
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGING_BYTES = SPLIT ? 0 : BM * BN * 2;     // BN/64 blocks of [128 rows x 128 B], 128B-swizzled
+  constexpr int ACC_STAGES = SPLIT ? 1 : 2;
+  constexpr int TMEM_COLS = (ACC_STAGES * BN) <= 32 ? 32 : (ACC_STAGES * BN) <= 64 ? 64 : (ACC_STAGES * BN) <= 128 ? 128
+                          : (ACC_STAGES * BN) <= 256 ? 256 : 512;
+  static_assert(STAGE_BYTES % 1024 == 0 && BN % 64 == 0 && ACC_STAGES * BN <= 512, "tile configuration");
+  static_assert(!SPLIT || STAGES * STAGE_BYTES >= BM * BN * 4, "exchange buffer must fit in the pipeline stages");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * STAGE_BYTES;
+  float* sbias = reinterpret_cast<float*>(staging + STAGING_BYTES);      // [BN] bias (+ per-image row-bias) of the tile
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbias + BN);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-  int* flag_slot = reinterpret_cast<int*>(tmem_slot + 1);
+  uint64_t* tfull_bar = empty_bar + STAGES;       // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;           // [2] accumulator drained
+  uint64_t* rfull_bar = tempty_bar + 2;           // residual tile landed in staging
+  uint64_t* sfree_bar = rfull_bar + 1;            // staging buffer reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfree_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // ---- tile coordinates ----
-  const int n0 = blockIdx.y * BN;
-  int m0 = 0, img = 0, h0 = 0, w0 = 0;
-  if (p.mode == 0) {
-    m0 = blockIdx.x * BM;
-  } else {
-    const int tpi = p.tiles_w * p.tiles_h;
-    img = blockIdx.x / tpi;
-    const int r = blockIdx.x - img * tpi;
-    h0 = (r / p.tiles_w) * p.th;
-    w0 = (r % p.tiles_w) * p.tw;
-  }
-  const int kb_begin = blockIdx.z * p.kb_per_split;
-  const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
-  const int nkb = kb_end - kb_begin;   // host guarantees >= 1
 
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (!SPLIT && p.use_tma_epilogue) {
+      tma_prefetch_desc(&tmD);
+      if (p.R) tma_prefetch_desc(&tmR);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    mbar_init(rfull_bar, 1);
+    mbar_init(sfree_bar, 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -139,140 +204,273 @@ __global__ void __launch_bounds__(kThreads) vn_gemm_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // ---- work assignment ----
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  int tile_begin, tile_step, kb_begin, nkb;
+  uint32_t crank = 0;
+  if (SPLIT) {
+    crank = cluster_ctarank();
+    tile_begin = blockIdx.x / p.splits;
+    tile_step = num_tiles;                       // exactly one tile per cluster
+    kb_begin = (int)crank * p.kb_per_split;
+    nkb = min(p.kb_total, kb_begin + p.kb_per_split) - kb_begin;   // host guarantees >= 1
+  } else {
+    tile_begin = blockIdx.x;
+    tile_step = gridDim.x;
+    kb_begin = 0;
+    nkb = p.kb_total;
+  }
+  const bool tma_epi = !SPLIT && p.use_tma_epilogue;
+
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       const uint32_t tx_bytes = (uint32_t)(p.rows_a * BK * 2 + B_BYTES);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        const int round = i / STAGES;
-        mbar_wait(&empty_bar[s], (round & 1) ^ 1);
-        mbar_expect_tx(&full_bar[s], tx_bytes);
-        uint8_t* sa = smem + s * STAGE_BYTES;
-        uint8_t* sb = sa + A_BYTES;
-        const int kb = kb_begin + i;
-        if (p.mode == 0) {
-          tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
-        } else {
-          const int tap = kb / p.cblocks;
-          const int cb = kb - tap * p.cblocks;
-          const int dy = tap / 3, dx = tap - dy * 3;
-          tma_load_4d(sa, &tmA, &full_bar[s], cb * BK, w0 + dx - 1, h0 + dy - 1, img);
+      int it = 0, t = 0;
+      for (int tile = tile_begin; tile < num_tiles; tile += tile_step, ++t) {
+        const TileCoord c = tile_coord(p, tile, BN);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full_bar[s], tx_bytes);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          const int kb = kb_begin + i;
+          if (p.mode == 0) {
+            tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, c.m0);
+          } else {
+            const int tap = kb / p.cblocks;
+            const int cb = kb - tap * p.cblocks;
+            const int dy = tap / 3, dx = tap - dy * 3;
+            tma_load_4d(sa, &tmA, &full_bar[s], cb * BK, c.w0 + dx - 1, c.h0 + dy - 1, c.img);
+          }
+          tma_load_2d(sa + A_BYTES, &tmB, &full_bar[s], kb * BK, c.n0);
         }
-        tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0);
+        if (tma_epi && p.R) {
+          // residual tile -> staging, once the previous tile's store has finished reading it
+          mbar_wait(sfree_bar, (t & 1) ^ 1);
+          const int nblk = min(BN / 64, (p.N - c.n0 + 63) / 64);
+          mbar_expect_tx(rfull_bar, (uint32_t)(nblk * p.rows_a * 128));
+          for (int j = 0; j < nblk; ++j) {
+            if (p.mode == 0) tma_load_2d(staging + j * (BM * 128), &tmR, rfull_bar, c.n0 + j * 64, c.m0);
+            else tma_load_4d(staging + j * (BM * 128), &tmR, rfull_bar, c.n0 + j * 64, c.w0, c.h0, c.img);
+          }
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        const int round = i / STAGES;
-        mbar_wait(&full_bar[s], round & 1);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        const uint64_t adesc = umma_desc_k_sw128(sa);
-        const uint64_t bdesc = umma_desc_k_sw128(sa + A_BYTES);
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) ? 1u : 0u);
+      int it = 0, t = 0;
+      for (int tile = tile_begin; tile < num_tiles; tile += tile_step, ++t) {
+        const int n0 = (tile / p.m_tiles) * BN;
+        int n_eff = min(BN, p.N - n0);
+        n_eff = (n_eff + 15) & ~15;               // UMMA N granularity; B rows beyond N are TMA zero-fill
+        const uint32_t idesc = umma_idesc_bf16(BM, n_eff);
+        const int as = SPLIT ? 0 : (t & 1);
+        if (!SPLIT) {
+          mbar_wait(&tempty_bar[as], ((t >> 1) & 1) ^ 1);
+          tc_fence_after();
         }
-        umma_commit(&empty_bar[s]);          // frees this smem stage when the MMAs above have read it
+        const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);            // frees this smem stage when the MMAs above have read it
+        }
+        umma_commit(&tfull_bar[as]);             // accumulator complete
       }
-      umma_commit(accum_bar);                // accumulator complete
     }
     __syncwarp();
-  } else {
-    // ================= epilogue (warps 2..5) =================
-    const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;             // tile row == TMEM lane
-    long long gm;
-    int bidx;
-    bool row_ok;
-    if (p.mode == 0) {
-      gm = (long long)m0 + r;
-      row_ok = gm < p.M;
-      bidx = p.rows_per_batch > 0 ? (int)(gm / p.rows_per_batch) : 0;
-    } else {
-      const int ty = r / p.tw, tx = r - ty * p.tw;
-      const int h = h0 + ty, w = w0 + tx;
-      row_ok = (r < p.rows_a) && (h < p.H) && (w < p.W);
-      gm = ((long long)img * p.H + h) * p.W + w;
-      bidx = img;
-    }
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-
-    if (p.splits == 1) {
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(taddr + c * 32, raw);
-        tmem_ld_wait();
-        if (row_ok) {
-          float v[32];
+  } else if (!SPLIT) {
+    // ================= epilogue (warps 2..5), persistent schedule =================
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                 // tile row == TMEM lane
+    int t = 0;
+    for (int tile = tile_begin; tile < num_tiles; tile += tile_step, ++t) {
+      const TileCoord c = tile_coord(p, tile, BN);
+      const int as = t & 1;
+      long long gm;
+      int bidx;
+      const bool row_ok = tile_row(p, c, r, &gm, &bidx);
+      // bias (+ the per-image time-embedding row-bias in conv mode) of this tile: global loads are issued before
+      // the accumulator wait and parked in shared memory, so no global latency sits on the epilogue's critical path
+      const bool smem_rowbias = p.rowbias && p.mode == 1;
+      float bv[BN / 128 > 0 ? BN / 128 : 1];
+      const int te = threadIdx.x - 64;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          epilogue_store(p, v, gm, bidx, n0 + c * 32);
+      for (int u = 0; u < (BN + 127) / 128; ++u) {
+        const int col = te + u * 128;
+        float v = 0.f;
+        if (col < BN && c.n0 + col < p.N) {
+          if (p.bias) v = __ldg(p.bias + c.n0 + col);
+          if (smem_rowbias) v += __ldg(p.rowbias + (long long)c.img * p.ld_rowbias + c.n0 + col);
         }
+        bv[u] = v;
       }
-    } else {
-      // ---- split-K: accumulate partial tile into the zeroed fp32 workspace ----
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(taddr + c * 32, raw);
-        tmem_ld_wait();
-        if (row_ok) {
-          float* wrow = p.ws + gm * p.N + n0 + c * 32;
+      mbar_wait(&tfull_bar[as], (t >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      if (tma_epi) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (n0 + c * 32 + g * 4 < p.N)
-              red_add_v4(wrow + g * 4, __uint_as_float(raw[g * 4]), __uint_as_float(raw[g * 4 + 1]),
-                         __uint_as_float(raw[g * 4 + 2]), __uint_as_float(raw[g * 4 + 3]));
-          }
-        }
-      }
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) {
-        const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-        const int old = atomicAdd(&p.counters[tile], 1);
-        const int last = (old == p.splits - 1);
-        if (last) p.counters[tile] = 0;      // self-reset for the next launch on this stream
-        *flag_slot = last;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (*flag_slot) {
-        __threadfence();
-        if (row_ok) {
+        for (int u = 0; u < (BN + 127) / 128; ++u)
+          if (te + u * 128 < BN) sbias[te + u * 128] = bv[u];
+        epi_bar_sync();
+        if (p.R) mbar_wait(rfull_bar, t & 1);
 #pragma unroll 1
-          for (int c = 0; c < BN / 32; ++c) {
-            const int nb = n0 + c * 32;
-            if (nb >= p.N) break;
-            float v[32];
-            float* wrow = p.ws + gm * p.N + nb;
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          const int nb0 = c.n0 + cc * 32;
+          if (nb0 >= p.N) break;
+          uint32_t raw[32];
+          tmem_ld32(taddr + cc * 32, raw);
+          tmem_ld_wait();
+          uint8_t* blk = staging + (cc >> 1) * (BM * 128) + r * 128;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (nb + g * 4 < p.N) {
-                t = __ldcg(reinterpret_cast<const float4*>(wrow + g * 4));
-                __stcg(reinterpret_cast<float4*>(wrow + g * 4), make_float4(0.f, 0.f, 0.f, 0.f));   // leave it clean
-              }
-              v[g * 4] = t.x; v[g * 4 + 1] = t.y; v[g * 4 + 2] = t.z; v[g * 4 + 3] = t.w;
+          for (int g = 0; g < 4; ++g) {
+            const int n = nb0 + g * 8;
+            float o[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(sbias + cc * 32 + g * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(sbias + cc * 32 + g * 8 + 4);
+            o[0] = __uint_as_float(raw[g * 8 + 0]) + b0.x; o[1] = __uint_as_float(raw[g * 8 + 1]) + b0.y;
+            o[2] = __uint_as_float(raw[g * 8 + 2]) + b0.z; o[3] = __uint_as_float(raw[g * 8 + 3]) + b0.w;
+            o[4] = __uint_as_float(raw[g * 8 + 4]) + b1.x; o[5] = __uint_as_float(raw[g * 8 + 5]) + b1.y;
+            o[6] = __uint_as_float(raw[g * 8 + 6]) + b1.z; o[7] = __uint_as_float(raw[g * 8 + 7]) + b1.w;
+            if (p.rowbias && !smem_rowbias && n < p.N && row_ok) {
+              const float* rb = p.rowbias + (long long)bidx * p.ld_rowbias + n;
+              const float4 c0 = __ldg(reinterpret_cast<const float4*>(rb));
+              const float4 c1 = __ldg(reinterpret_cast<const float4*>(rb + 4));
+              o[0] += c0.x; o[1] += c0.y; o[2] += c0.z; o[3] += c0.w;
+              o[4] += c1.x; o[5] += c1.y; o[6] += c1.z; o[7] += c1.w;
             }
-            epilogue_store(p, v, gm, bidx, nb);
+            uint4* slot = reinterpret_cast<uint4*>(blk + ((((cc & 1) * 4 + g) ^ (r & 7)) << 4));
+            if (p.R && n < p.N) {
+              const uint4 rr = *slot;
+              float2 f;
+              f = unpack_bf162(rr.x); o[0] += f.x; o[1] += f.y;
+              f = unpack_bf162(rr.y); o[2] += f.x; o[3] += f.y;
+              f = unpack_bf162(rr.z); o[4] += f.x; o[5] += f.y;
+              f = unpack_bf162(rr.w); o[6] += f.x; o[7] += f.y;
+            }
+            uint4 w;
+            w.x = pack_bf162(o[0], o[1]); w.y = pack_bf162(o[2], o[3]);
+            w.z = pack_bf162(o[4], o[5]); w.w = pack_bf162(o[6], o[7]);
+            *slot = w;
           }
         }
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);       // TMEM stage may be overwritten by tile t+2
+        fence_proxy_async();
+        epi_bar_sync();
+        if (threadIdx.x == 64) {
+          const int nblk = min(BN / 64, (p.N - c.n0 + 63) / 64);
+          for (int j = 0; j < nblk; ++j) {
+            if (p.mode == 0) tma_store_2d(&tmD, staging + j * (BM * 128), c.n0 + j * 64, c.m0);
+            else tma_store_4d(&tmD, staging + j * (BM * 128), c.n0 + j * 64, c.w0, c.h0, c.img);
+          }
+          tma_store_commit();
+          tma_store_wait_read();
+          mbar_arrive(sfree_bar);
+        }
+        epi_bar_sync();                                      // staging reusable by all epilogue warps
+      } else {
+        // direct register -> global path (fp32 outputs, odd strides)
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          const int nb0 = c.n0 + cc * 32;
+          if (nb0 >= p.N) break;
+          uint32_t raw[32];
+          tmem_ld32(taddr + cc * 32, raw);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int n = nb0 + g * 8;
+              if (n < p.N) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(raw[g * 8 + j]);
+                store8(p, o, gm, bidx, n);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      }
+    }
+    if (tma_epi && threadIdx.x == 64) tma_store_wait_all();   // global writes complete before the CTA exits
+  }
+
+  if (SPLIT) {
+    // ================= split-K: exchange partial tiles through distributed shared memory =================
+    const int S = p.splits;
+    const int rpo = BM / S;                       // rows reduced (and finished) by each CTA of the cluster
+    const int cpt = BN / S;                       // columns finished per epilogue thread
+    float* exch = reinterpret_cast<float*>(smem); // [S src][BN col][rpo row] fp32, aliases the pipeline stages
+    if (warp >= 2) {
+      mbar_wait(&tfull_bar[0], 0);                // my accumulator is complete => my stages are no longer read
+      tc_fence_after();
+    }
+    __syncwarp();
+    cluster_sync_all();                           // every CTA of the cluster is done with its pipeline stages
+    if (warp >= 2) {
+      const int q = warp & 3;
+      const int r = q * 32 + lane;
+      const uint32_t owner = (uint32_t)(r / rpo);
+      const uint32_t remote = mapa_shared(smem_u32(exch), owner) + (uint32_t)(((int)crank * BN * rpo + (r % rpo)) * 4);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int tile = tile_begin;
+      const int n0 = (tile / p.m_tiles) * BN;
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        if (n0 + cc * 32 >= p.N) break;
+        uint32_t raw[32];
+        tmem_ld32(taddr + cc * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st_cluster_f32(remote + (uint32_t)((cc * 32 + j) * rpo * 4), __uint_as_float(raw[j]));
       }
     }
     tc_fence_before();
+    __syncwarp();
+    cluster_sync_all();                           // all partials have landed (release / acquire at cluster scope)
+    if (warp >= 2) {
+      const int te = threadIdx.x - 64;            // 0..127
+      const int rl = te % rpo;
+      const int cg = te / rpo;
+      const int tile = tile_begin;
+      const TileCoord c = tile_coord(p, tile, BN);
+      long long gm;
+      int bidx;
+      const bool row_ok = tile_row(p, c, (int)crank * rpo + rl, &gm, &bidx);
+      if (row_ok) {
+        for (int g = 0; g < cpt / 8; ++g) {
+          const int col = cg * cpt + g * 8;
+          const int n = c.n0 + col;
+          if (n >= p.N) break;
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = 0.f;
+          for (int src = 0; src < S; ++src) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += exch[((long long)src * BN + col + j) * rpo + rl];
+          }
+          store8(p, o, gm, bidx, n);
+        }
+      }
+    }
   }
 
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -323,49 +521,69 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool SPLIT>
 constexpr int smem_bytes() {
-  return STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  return STAGES * (BM * BK * 2 + BN * BK * 2) + (SPLIT ? 0 : BM * BN * 2) + BN * 4 + (2 * STAGES + 6) * 8 + 16 + 1024;
 }
 
-template <int BN, int STAGES>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid, cudaStream_t st) {
+template <int BN, int STAGES, bool SPLIT>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr,
+           const GemmParams& p, int grid_x, cudaStream_t st) {
   static bool configured = false;
-  constexpr int smem = smem_bytes<BN, STAGES>();
+  constexpr int smem = smem_bytes<BN, STAGES, SPLIT>();
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  auto kern = vn_gemm_kernel<BN, STAGES, SPLIT>;
   if (!configured) {
-    VN_CUDA(cudaFuncSetAttribute(vn_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  vn_gemm_kernel<BN, STAGES><<<grid, kThreads, smem, st>>>(ta, tb, p);
-  VN_LAUNCH_OK();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid_x, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = 0;
+  if (SPLIT) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)p.splits;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.numAttrs = 1;
+  }
+  VN_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tr, p));
+  vn_count_launch();
   return 0;
 }
 
-constexpr size_t kCounterBytes = 64 * 1024;   // 16384 tile counters
-
-// Pick (BN, splits).  Model: a CTA costs  fixed + kblocks * t_kb(BN);  the launch costs waves * that.
+// Pick (BN, splits) with a small cycle model: persistent tiles are processed in rounds over the SMs; a cluster
+// split divides the k-loop of every tile by S but needs all tiles x S CTAs resident at once.
 void choose_tiling(int m_tiles, int N, int kb_total, bool allow_split, int* bn_out, int* split_out) {
   const int sms = num_sms();
-  const int cands[3] = {160, 128, 64};
+  const int cands[3] = {256, 128, 64};
   double best = 1e30;
   int best_bn = 128, best_split = 1;
   for (int ci = 0; ci < 3; ++ci) {
     const int bn = cands[ci];
     const int n_tiles = vn_cdiv(N, bn);
-    const double waste = (double)(n_tiles * bn) / (double)N;
-    const double t_kb = (bn >= 128 ? bn : 96 + bn / 4) * 2.0;       // cycles per 64-deep k-block (MMA floor bn/2*4), small tiles are operand-bound
-    const double t_epi = 600.0 + bn * 6.0;
-    const int max_split = allow_split ? 16 : 1;
-    for (int s = 1; s <= max_split; ++s) {
+    const int tiles = m_tiles * n_tiles;
+    // cycles per 64-deep k-block: tensor floor vs. the L2 -> SM operand stream (~40 B/cycle/SM measured)
+    const double t_mma = bn == 256 ? 512.0 : bn == 128 ? 256.0 : 192.0;
+    const double t_mem = (BM + bn) * 128.0 / 40.0;
+    const double tk = t_mma > t_mem ? t_mma : t_mem;
+    const double t_epi = 300.0 + bn * 8.0;
+    {
+      const int rounds = vn_cdiv(tiles, sms);
+      const double cost = rounds * (kb_total * tk + 300.0) + t_epi + 3000.0;
+      if (cost < best) { best = cost; best_bn = bn; best_split = 1; }
+    }
+    if (!allow_split) continue;
+    for (int s = 2; s <= 8; s *= 2) {
+      if (tiles * s > sms) break;
       const int kps = vn_cdiv(kb_total, s);
-      if (s > 1 && (kps < 4 || vn_cdiv(kb_total, kps) != s)) continue;
-      const long long ctas = (long long)m_tiles * n_tiles * s;
-      const int per_sm = bn == 64 ? 2 : 2;
-      const double waves = (double)vn_cdiv64(ctas, (long long)sms * per_sm);
-      // two co-resident CTAs share one tensor pipe: each wave of 2*sms CTAs takes ~2x the MMA time of one CTA
-      const double t_cta = 2500.0 + kps * t_kb * per_sm + t_epi * (s > 1 ? 2.2 : 1.0);
-      double cost = waves * t_cta * (0.9 + 0.1 * waste);
-      if (ctas < sms) cost *= 1.0;   // under-filled single wave: cost is just t_cta
+      if (kps < 2 || kb_total <= (s - 1) * kps) continue;       // every rank needs at least one k-block
+      const double cost = kps * tk + 2500.0 + t_epi / s + 3500.0;
       if (cost < best) { best = cost; best_bn = bn; best_split = s; }
     }
   }
@@ -376,7 +594,8 @@ void choose_tiling(int m_tiles, int N, int kb_total, bool allow_split, int* bn_o
 }  // namespace
 
 extern "C" size_t vn_gemm_workspace_bytes(int max_M, int max_N) {
-  return kCounterBytes + (size_t)max_M * (size_t)max_N * sizeof(float);
+  (void)max_M; (void)max_N;
+  return 256;       // split-K reduces through distributed shared memory; kept for ABI stability
 }
 
 extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
@@ -389,8 +608,8 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
   VN_CHECK(d->ldb >= d->K, "vn_gemm: ldb < K");
   VN_CHECK(!d->R || d->ldr % 8 == 0, "vn_gemm: ldr must be a multiple of 8");
   VN_CHECK((reinterpret_cast<uintptr_t>(d->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->B) & 15) == 0 &&
-               (reinterpret_cast<uintptr_t>(d->D) & 15) == 0,
-           "vn_gemm: A/B/D must be 16-byte aligned");
+               (reinterpret_cast<uintptr_t>(d->D) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->R) & 15) == 0,
+           "vn_gemm: A/B/D/R must be 16-byte aligned");
 
   GemmParams p{};
   p.M = d->M; p.N = d->N;
@@ -402,15 +621,17 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
   p.R = reinterpret_cast<const bf16*>(d->R); p.ldr = d->ldr;
   p.out_fp32 = d->out_fp32;
 
-  CUtensorMap ta, tb;
-  int m_tiles;
+  CUtensorMap ta, tb, td, tr;
+  memset(&td, 0, sizeof(td));
+  memset(&tr, 0, sizeof(tr));
+  cuuint32_t box_a[4];
   if (d->mode == 0) {
     VN_CHECK(d->lda >= d->K, "vn_gemm: lda < K");
     cuuint64_t dims[2] = {(cuuint64_t)d->K, (cuuint64_t)d->M};
     cuuint64_t str[1] = {(cuuint64_t)d->lda * 2};
-    cuuint32_t box[2] = {BK, BM};
-    if (make_map(&ta, d->A, 2, dims, str, box)) return -1;
-    m_tiles = vn_cdiv(d->M, BM);
+    box_a[0] = BK; box_a[1] = BM;
+    if (make_map(&ta, d->A, 2, dims, str, box_a)) return -1;
+    p.m_tiles = vn_cdiv(d->M, BM);
     p.rows_a = BM;
   } else if (d->mode == 1) {
     VN_CHECK(d->C % BK == 0 && d->K == 9 * d->C, "vn_gemm conv: need C %% 64 == 0 and K == 9*C (C=%d K=%d)", d->C, d->K);
@@ -427,40 +648,64 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
     p.H = d->H; p.W = d->W; p.cblocks = d->C / BK;
     cuuint64_t dims[4] = {(cuuint64_t)d->C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->nb};
     cuuint64_t str[3] = {(cuuint64_t)d->lda * 2, (cuuint64_t)d->lda * 2 * d->W, (cuuint64_t)d->lda * 2 * d->W * d->H};
-    cuuint32_t box[4] = {BK, (cuuint32_t)tw, (cuuint32_t)th, 1};
-    if (make_map(&ta, d->A, 4, dims, str, box)) return -1;
-    m_tiles = d->nb * p.tiles_w * p.tiles_h;
+    box_a[0] = BK; box_a[1] = (cuuint32_t)tw; box_a[2] = (cuuint32_t)th; box_a[3] = 1;
+    if (make_map(&ta, d->A, 4, dims, str, box_a)) return -1;
+    p.m_tiles = d->nb * p.tiles_w * p.tiles_h;
   } else {
     VN_CHECK(false, "vn_gemm: unknown mode %d", d->mode);
   }
 
-  const bool have_ws = d->workspace != nullptr && d->workspace_bytes >= vn_gemm_workspace_bytes(d->M, d->N);
   int bn = 128, splits = 1;
-  choose_tiling(m_tiles, d->N, p.kb_total, have_ws, &bn, &splits);
+  choose_tiling(p.m_tiles, d->N, p.kb_total, true, &bn, &splits);
   if (d->force_bn) bn = d->force_bn;
   if (d->force_split) splits = d->force_split;
-  VN_CHECK(bn == 64 || bn == 128 || bn == 160, "vn_gemm: unsupported BN %d", bn);
-  if (splits > p.kb_total) splits = p.kb_total;
+  VN_CHECK(bn == 64 || bn == 128 || bn == 256, "vn_gemm: unsupported BN %d (64, 128, 256)", bn);
+  VN_CHECK(splits == 1 || splits == 2 || splits == 4 || splits == 8, "vn_gemm: unsupported split %d (1, 2, 4, 8)", splits);
+  while (splits > 1 && (vn_cdiv(p.kb_total, splits) < 1 || p.kb_total <= (splits - 1) * vn_cdiv(p.kb_total, splits)))
+    splits /= 2;
   p.kb_per_split = vn_cdiv(p.kb_total, splits);
-  splits = vn_cdiv(p.kb_total, p.kb_per_split);
   p.splits = splits;
-  const int n_tiles = vn_cdiv(d->N, bn);
-  if (splits > 1) {
-    VN_CHECK(have_ws, "vn_gemm: split-K needs a workspace of %zu bytes", vn_gemm_workspace_bytes(d->M, d->N));
-    VN_CHECK((size_t)m_tiles * n_tiles * sizeof(int) <= kCounterBytes, "vn_gemm: too many tiles for split-K counters");
-    p.counters = reinterpret_cast<int*>(d->workspace);
-    p.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d->workspace) + kCounterBytes);
-  }
+  p.n_tiles = vn_cdiv(d->N, bn);
+  const int tiles = p.m_tiles * p.n_tiles;
   {
     cuuint64_t dims[2] = {(cuuint64_t)d->K, (cuuint64_t)d->N};
     cuuint64_t str[1] = {(cuuint64_t)d->ldb * 2};
     cuuint32_t box[2] = {BK, (cuuint32_t)bn};
     if (make_map(&tb, d->B, 2, dims, str, box)) return -1;
   }
-  dim3 grid(m_tiles, n_tiles, splits);
+  // staged TMA-store epilogue for bf16 outputs of the persistent schedule
+  p.use_tma_epilogue = (splits == 1 && !d->out_fp32) ? 1 : 0;
+  if (p.use_tma_epilogue) {
+    for (int which = 0; which < 2; ++which) {
+      const void* base = which == 0 ? d->D : d->R;
+      const long long ld = which == 0 ? d->ldd : d->ldr;
+      if (!base) continue;
+      CUtensorMap* m = which == 0 ? &td : &tr;
+      if (d->mode == 0) {
+        cuuint64_t dims[2] = {(cuuint64_t)d->N, (cuuint64_t)d->M};
+        cuuint64_t str[1] = {(cuuint64_t)ld * 2};
+        cuuint32_t box[2] = {64, BM};
+        if (make_map(m, base, 2, dims, str, box)) return -1;
+      } else {
+        cuuint64_t dims[4] = {(cuuint64_t)d->N, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->nb};
+        cuuint64_t str[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * d->W, (cuuint64_t)ld * 2 * d->W * d->H};
+        cuuint32_t box[4] = {64, box_a[1], box_a[2], 1};
+        if (make_map(m, base, 4, dims, str, box)) return -1;
+      }
+    }
+  }
+  if (splits == 1) {
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    switch (bn) {
+      case 64: return launch<64, 6, false>(ta, tb, td, tr, p, grid, st);
+      case 128: return launch<128, 5, false>(ta, tb, td, tr, p, grid, st);
+      default: return launch<256, 3, false>(ta, tb, td, tr, p, grid, st);
+    }
+  }
+  const int grid = tiles * splits;
   switch (bn) {
-    case 64: return launch<64, 4>(ta, tb, p, grid, st);
-    case 128: return launch<128, 3>(ta, tb, p, grid, st);
-    default: return launch<160, 3>(ta, tb, p, grid, st);
+    case 64: return launch<64, 6, true>(ta, tb, td, tr, p, grid, st);
+    case 128: return launch<128, 5, true>(ta, tb, td, tr, p, grid, st);
+    default: return launch<256, 4, true>(ta, tb, td, tr, p, grid, st);
   }
 }

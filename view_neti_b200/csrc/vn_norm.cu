@@ -1,72 +1,152 @@
 // vn_norm.cu — GroupNorm(+SiLU), LayerNorm and GEGLU, forward and dgrad, over NHWC / token-major bf16.
-// HBM/L2-bound row-wise kernels: 128-bit or 32-bit coalesced accesses along the channel axis, fp32 statistics,
-// warp-shuffle + shared-memory reductions.  Replaces torch native_group_norm / native_layer_norm / gelu kernels
-// under diffusers ResnetBlock2D, Transformer2DModel, BasicTransformerBlock, GEGLU (all on the coach.py:197 path).
+// HBM/L2-bound streaming kernels: 128-bit coalesced accesses along the channel axis, fp32 statistics, several
+// independent loads in flight per thread, grids sized for >= 2 CTAs per SM.  Replaces torch native_group_norm /
+// native_layer_norm / gelu kernels (and their autograd backward) under diffusers ResnetBlock2D, Transformer2DModel,
+// BasicTransformerBlock, GEGLU — all on the coach.py:197-214 path.
 #include "vn_common.cuh"
 
 namespace {
 
 constexpr int kMaxC = 2560;       // widest GroupNorm input in SD-2.1 (concat 1280+1280)
-constexpr int kGNThreads = 256;
+constexpr int kMaxGroups = 64;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  float2 t;
+  t = unpack_bf162(v.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf162(v.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf162(v.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf162(v.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&a)[8]) {
+  uint4 o;
+  o.x = pack_bf162(a[0], a[1]); o.y = pack_bf162(a[2], a[3]);
+  o.z = pack_bf162(a[4], a[5]); o.w = pack_bf162(a[6], a[7]);
+  return o;
+}
+__device__ __forceinline__ uint4 ld16(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 // ---------------------------------------------------------------------------------------------
-// GroupNorm statistics: grid (chunks, nb); each CTA walks `ppc` pixels over all channels.
-// Threads own fixed bf16x2 channel pairs (pair p -> group (2p)/cpg; cpg is even), so loads are coalesced.
-// MODE 0: (sum x, sum x^2).   MODE 1 (backward): (sum dxhat, sum dxhat*xhat).
+// GroupNorm geometry: a CTA has vecs * k threads (vecs = C/8 16-byte vectors per pixel); thread (slot, v) owns the
+// fixed channel vector v and walks pixels slot, slot + k, ... of the CTA's pixel range, so per-channel constants and
+// partial sums live in registers and every warp access is a contiguous run of one pixel row.
+// grid = (pixel chunks, nb).
 // ---------------------------------------------------------------------------------------------
+struct GNGeom {
+  int threads, k, ppc, chunks;
+};
+GNGeom gn_geom(int nb, int hw, int C) {
+  GNGeom g;
+  const int vecs = C / 8;
+  g.k = 256 / vecs;
+  if (g.k < 1) g.k = 1;
+  if (g.k > hw) g.k = hw;
+  g.threads = vecs * g.k;
+  int target = (148 * 3 + nb - 1) / nb;                 // CTAs per image for ~3 CTAs per SM
+  int ppc = (hw + target - 1) / target;
+  ppc = ((ppc + g.k - 1) / g.k) * g.k;                  // whole slots
+  if (ppc < 2 * g.k && hw >= 2 * g.k) ppc = 2 * g.k;    // at least two pixels per thread to amortise the prologue
+  g.ppc = ppc;
+  g.chunks = (hw + ppc - 1) / ppc;
+  return g;
+}
+
+// MODE 0: stats (sum x, sum x^2) per (image, group).   MODE 1 (backward): (sum dxhat, sum dxhat*xhat).
 template <int MODE>
-__global__ void __launch_bounds__(kGNThreads) gn_reduce_kernel(const bf16* __restrict__ x, long long ldx,
-                                                              const bf16* __restrict__ dy, long long lddy,
-                                                              const float* __restrict__ stats,
-                                                              const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, float eps, int silu,
-                                                              float* __restrict__ out, int hw, int C, int groups,
-                                                              int ppc) {
-  __shared__ float s_acc[64][2];
-  __shared__ float s_mean[64], s_rstd[64];
+__global__ void __launch_bounds__(512) gn_reduce_kernel(const bf16* __restrict__ x, long long ldx,
+                                                         const bf16* __restrict__ dy, long long lddy,
+                                                         const float* __restrict__ stats,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float eps, int silu,
+                                                         float* __restrict__ out, int hw, int C, int groups, int k,
+                                                         int ppc) {
+  __shared__ float s_acc[kMaxGroups][2];
   const int b = blockIdx.y;
   const int cpg = C / groups;
-  const int pairs = C >> 1;
+  const int vecs = C >> 3;
+  const int v = threadIdx.x % vecs, slot = threadIdx.x / vecs;
+  const int c0 = v * 8;
   const int p0 = blockIdx.x * ppc;
   const int p1 = min(hw, p0 + ppc);
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    s_acc[g][0] = 0.f; s_acc[g][1] = 0.f;
-    if (MODE == 1) {
-      const float n = (float)cpg * (float)hw;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) { s_acc[g][0] = 0.f; s_acc[g][1] = 0.f; }
+  float ga[8], be[8], mean[8], rstd[8];
+  if (MODE == 1) {
+    const float n = (float)cpg * (float)hw;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ga[j] = gamma[c0 + j]; be[j] = beta[c0 + j];
+      const int g = (c0 + j) / cpg;
       const float m = stats[(b * groups + g) * 2] / n;
       const float var = fmaxf(stats[(b * groups + g) * 2 + 1] / n - m * m, 0.f);
-      s_mean[g] = m; s_rstd[g] = rsqrtf(var + eps);
+      mean[j] = m; rstd[j] = rsqrtf(var + eps);
     }
   }
   __syncthreads();
-  for (int pr = threadIdx.x; pr < pairs; pr += blockDim.x) {
-    const int c = pr * 2;
-    const int g = c / cpg;
-    float a0 = 0.f, a1 = 0.f;
-    float ga0 = 0.f, ga1 = 0.f, be0 = 0.f, be1 = 0.f, mean = 0.f, rstd = 0.f;
-    if (MODE == 1) {
-      ga0 = gamma[c]; ga1 = gamma[c + 1]; be0 = beta[c]; be1 = beta[c + 1];
-      mean = s_mean[g]; rstd = s_rstd[g];
+  float a0[8], a1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+  const bf16* xb = x + (long long)b * hw * ldx + c0;
+  const bf16* db = MODE == 1 ? dy + (long long)b * hw * lddy + c0 : nullptr;
+  int p = p0 + slot;
+  for (; p + 3 * k < p1; p += 4 * k) {
+    uint4 xv[4], dv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      xv[u] = ld16(xb + (long long)(p + u * k) * ldx);
+      if (MODE == 1) dv[u] = ld16(db + (long long)(p + u * k) * lddy);
     }
-    for (int p = p0; p < p1; ++p) {
-      const long long row = (long long)b * hw + p;
-      const float2 v = __bfloat1622float2(*reinterpret_cast<const bf162*>(x + row * ldx + c));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float xf[8];
+      unpack8(xv[u], xf);
       if (MODE == 0) {
-        a0 += v.x + v.y;
-        a1 += v.x * v.x + v.y * v.y;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a0[j] += xf[j]; a1[j] = fmaf(xf[j], xf[j], a1[j]); }
       } else {
-        const float2 d = __bfloat1622float2(*reinterpret_cast<const bf162*>(dy + row * lddy + c));
-        const float xh0 = (v.x - mean) * rstd, xh1 = (v.y - mean) * rstd;
-        float dz0 = d.x, dz1 = d.y;
-        if (silu) { dz0 *= dsilu_f(xh0 * ga0 + be0); dz1 *= dsilu_f(xh1 * ga1 + be1); }
-        const float dh0 = dz0 * ga0, dh1 = dz1 * ga1;
-        a0 += dh0 + dh1;
-        a1 += dh0 * xh0 + dh1 * xh1;
+        float df[8];
+        unpack8(dv[u], df);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xf[j] - mean[j]) * rstd[j];
+          float dz = df[j];
+          if (silu) dz *= dsilu_f(xh * ga[j] + be[j]);
+          const float dh = dz * ga[j];
+          a0[j] += dh; a1[j] = fmaf(dh, xh, a1[j]);
+        }
       }
     }
-    atomicAdd(&s_acc[g][0], a0);
-    atomicAdd(&s_acc[g][1], a1);
   }
+  for (; p < p1; p += k) {
+    float xf[8];
+    unpack8(ld16(xb + (long long)p * ldx), xf);
+    if (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a0[j] += xf[j]; a1[j] = fmaf(xf[j], xf[j], a1[j]); }
+    } else {
+      float df[8];
+      unpack8(ld16(db + (long long)p * lddy), df);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xf[j] - mean[j]) * rstd[j];
+        float dz = df[j];
+        if (silu) dz *= dsilu_f(xh * ga[j] + be[j]);
+        const float dh = dz * ga[j];
+        a0[j] += dh; a1[j] = fmaf(dh, xh, a1[j]);
+      }
+    }
+  }
+  // channels -> groups (a vector spans at most 1 + 8/cpg groups); merge equal groups before the shared atomics
+  int gprev = c0 / cpg;
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / cpg;
+    if (g != gprev) {
+      atomicAdd(&s_acc[gprev][0], s0); atomicAdd(&s_acc[gprev][1], s1);
+      s0 = 0.f; s1 = 0.f; gprev = g;
+    }
+    s0 += a0[j]; s1 += a1[j];
+  }
+  atomicAdd(&s_acc[gprev][0], s0); atomicAdd(&s_acc[gprev][1], s1);
   __syncthreads();
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     atomicAdd(&out[(b * groups + g) * 2], s_acc[g][0]);
@@ -74,120 +154,133 @@ __global__ void __launch_bounds__(kGNThreads) gn_reduce_kernel(const bf16* __res
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// GroupNorm apply: y = act(x * a[c] + b[c]) with per-(image, channel) a, b staged in shared memory.
-// MODE 0 forward.  MODE 1 backward: dx = rstd*(dxhat - S1/n - xhat*S2/n) (+add1) (+add2).
-// grid (chunks, nb); 8-channel (16 B) vectors.
-// ---------------------------------------------------------------------------------------------
+// MODE 0 forward: y = act(x * a[c] + b[c]).  MODE 1 backward: dx = rstd*(dxhat - S1/n - xhat*S2/n) (+add1) (+add2).
 template <int MODE>
-__global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(const bf16* __restrict__ x, long long ldx,
-                                                             const bf16* __restrict__ dy, long long lddy,
-                                                             const float* __restrict__ stats,
-                                                             const float* __restrict__ red,
-                                                             const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, float eps, int silu,
-                                                             const bf16* __restrict__ add1, long long ld1,
-                                                             const bf16* __restrict__ add2, long long ld2,
-                                                             bf16* __restrict__ y, long long ldy, int hw, int C,
-                                                             int groups, int ppc) {
-  extern __shared__ float s_gn[];
-  float* s_a = s_gn;            // fwd: gamma*rstd          bwd: gamma
-  float* s_b = s_gn + C;        // fwd: beta - mean*a       bwd: beta
-  float* s_m = s_gn + 2 * C;    // bwd only: mean, rstd, S1/n, S2/n per group (4*groups)
+__global__ void __launch_bounds__(512) gn_apply_kernel(const bf16* __restrict__ x, long long ldx,
+                                                        const bf16* __restrict__ dy, long long lddy,
+                                                        const float* __restrict__ stats,
+                                                        const float* __restrict__ red,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, int silu,
+                                                        const bf16* __restrict__ add1, long long ld1,
+                                                        const bf16* __restrict__ add2, long long ld2,
+                                                        bf16* __restrict__ y, long long ldy, int hw, int C,
+                                                        int groups, int k, int ppc) {
   const int b = blockIdx.y;
   const int cpg = C / groups;
-  const float n = (float)cpg * (float)hw;
-  if (MODE == 1) {
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-      const float m = stats[(b * groups + g) * 2] / n;
-      const float var = fmaxf(stats[(b * groups + g) * 2 + 1] / n - m * m, 0.f);
-      s_m[g * 4] = m;
-      s_m[g * 4 + 1] = rsqrtf(var + eps);
-      s_m[g * 4 + 2] = red[(b * groups + g) * 2] / n;
-      s_m[g * 4 + 3] = red[(b * groups + g) * 2 + 1] / n;
-    }
-  }
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    if (MODE == 0) {
-      const int g = c / cpg;
-      const float m = stats[(b * groups + g) * 2] / n;
-      const float var = fmaxf(stats[(b * groups + g) * 2 + 1] / n - m * m, 0.f);
-      const float a = gamma[c] * rsqrtf(var + eps);
-      s_a[c] = a;
-      s_b[c] = beta[c] - m * a;
-    } else {
-      s_a[c] = gamma[c];
-      s_b[c] = beta[c];
-    }
-  }
-  __syncthreads();
   const int vecs = C >> 3;
+  const int v = threadIdx.x % vecs, slot = threadIdx.x / vecs;
+  const int c0 = v * 8;
   const int p0 = blockIdx.x * ppc;
   const int p1 = min(hw, p0 + ppc);
-  const int total = (p1 - p0) * vecs;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int p = p0 + i / vecs;
-    const int c = (i % vecs) * 8;
-    const long long row = (long long)b * hw + p;
-    const uint4 raw = *reinterpret_cast<const uint4*>(x + row * ldx + c);
-    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-    float o[8];
+  const float n = (float)cpg * (float)hw;
+  // per-channel constants:  fwd  y = x*A + B            (A = gamma*rstd, B = beta - mean*A)
+  //                         bwd  xh = x*R + M (R = rstd, M = -mean*rstd), z = xh*G + Bt, dx = R*(dz*G - S1 - xh*S2)
+  float A[8], Bc[8], G[8], S1[8], S2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / cpg;
+    const float m = stats[(b * groups + g) * 2] / n;
+    const float var = fmaxf(stats[(b * groups + g) * 2 + 1] / n - m * m, 0.f);
+    const float rs = rsqrtf(var + eps);
     if (MODE == 0) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 v = unpack_bf162(w[j]);
-        float z0 = v.x * s_a[c + 2 * j] + s_b[c + 2 * j];
-        float z1 = v.y * s_a[c + 2 * j + 1] + s_b[c + 2 * j + 1];
-        if (silu) { z0 = silu_f(z0); z1 = silu_f(z1); }
-        o[2 * j] = z0; o[2 * j + 1] = z1;
-      }
+      A[j] = gamma[c0 + j] * rs;
+      Bc[j] = beta[c0 + j] - m * A[j];
     } else {
-      const uint4 draw = *reinterpret_cast<const uint4*>(dy + row * lddy + c);
-      const uint32_t dw[4] = {draw.x, draw.y, draw.z, draw.w};
+      A[j] = rs; Bc[j] = -m * rs;
+      G[j] = gamma[c0 + j];
+      S1[j] = red[(b * groups + g) * 2] / n;
+      S2[j] = red[(b * groups + g) * 2 + 1] / n;
+    }
+  }
+  float Bt[8];
+  if (MODE == 1) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 v = unpack_bf162(w[j]);
-        const float2 d = unpack_bf162(dw[j]);
-        const float xv[2] = {v.x, v.y};
-        const float dv[2] = {d.x, d.y};
+    for (int j = 0; j < 8; ++j) Bt[j] = beta[c0 + j];
+  }
+  const bf16* xb = x + (long long)b * hw * ldx + c0;
+  const bf16* db = MODE == 1 ? dy + (long long)b * hw * lddy + c0 : nullptr;
+  const bf16* a1b = add1 ? add1 + (long long)b * hw * ld1 + c0 : nullptr;
+  const bf16* a2b = add2 ? add2 + (long long)b * hw * ld2 + c0 : nullptr;
+  bf16* yb = y + (long long)b * hw * ldy + c0;
+  constexpr int U = MODE == 0 ? 4 : 2;
+  int p = p0 + slot;
+  for (; p + (U - 1) * k < p1; p += U * k) {
+    uint4 xv[U], dv[U], r1[U], r2[U];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int cc = c + 2 * j + e;
-          const int g = cc / cpg;
-          const float mean = s_m[g * 4], rstd = s_m[g * 4 + 1];
-          const float xh = (xv[e] - mean) * rstd;
-          float dz = dv[e];
-          if (silu) dz *= dsilu_f(xh * s_a[cc] + s_b[cc]);
-          const float dh = dz * s_a[cc];
-          o[2 * j + e] = rstd * (dh - s_m[g * 4 + 2] - xh * s_m[g * 4 + 3]);
-        }
-      }
-      if (add1) {
-        const uint4 r = *reinterpret_cast<const uint4*>(add1 + row * ld1 + c);
-        const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { const float2 t = unpack_bf162(rw[j]); o[2 * j] += t.x; o[2 * j + 1] += t.y; }
-      }
-      if (add2) {
-        const uint4 r = *reinterpret_cast<const uint4*>(add2 + row * ld2 + c);
-        const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { const float2 t = unpack_bf162(rw[j]); o[2 * j] += t.x; o[2 * j + 1] += t.y; }
+    for (int u = 0; u < U; ++u) {
+      const long long pp = p + u * k;
+      xv[u] = ld16(xb + pp * ldx);
+      if (MODE == 1) {
+        dv[u] = ld16(db + pp * lddy);
+        if (a1b) r1[u] = ld16(a1b + pp * ld1);
+        if (a2b) r2[u] = ld16(a2b + pp * ld2);
       }
     }
-    uint4 out;
-    out.x = pack_bf162(o[0], o[1]); out.y = pack_bf162(o[2], o[3]);
-    out.z = pack_bf162(o[4], o[5]); out.w = pack_bf162(o[6], o[7]);
-    *reinterpret_cast<uint4*>(y + row * ldy + c) = out;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float xf[8], o[8];
+      unpack8(xv[u], xf);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(xf[j], A[j], Bc[j]);
+          o[j] = silu ? silu_f(z) : z;
+        }
+      } else {
+        float df[8];
+        unpack8(dv[u], df);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = fmaf(xf[j], A[j], Bc[j]);
+          float dz = df[j];
+          if (silu) dz *= dsilu_f(fmaf(xh, G[j], Bt[j]));
+          o[j] = A[j] * (dz * G[j] - S1[j] - xh * S2[j]);
+        }
+        if (a1b) { float t[8]; unpack8(r1[u], t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += t[j]; }
+        if (a2b) { float t[8]; unpack8(r2[u], t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += t[j]; }
+      }
+      *reinterpret_cast<uint4*>(yb + (long long)(p + u * k) * ldy) = pack8(o);
+    }
+  }
+  for (; p < p1; p += k) {
+    float xf[8], o[8];
+    unpack8(ld16(xb + (long long)p * ldx), xf);
+    if (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(xf[j], A[j], Bc[j]);
+        o[j] = silu ? silu_f(z) : z;
+      }
+    } else {
+      float df[8];
+      unpack8(ld16(db + (long long)p * lddy), df);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = fmaf(xf[j], A[j], Bc[j]);
+        float dz = df[j];
+        if (silu) dz *= dsilu_f(fmaf(xh, G[j], Bt[j]));
+        o[j] = A[j] * (dz * G[j] - S1[j] - xh * S2[j]);
+      }
+      if (a1b) { float t[8]; unpack8(ld16(a1b + (long long)p * ld1), t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += t[j]; }
+      if (a2b) { float t[8]; unpack8(ld16(a2b + (long long)p * ld2), t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += t[j]; }
+    }
+    *reinterpret_cast<uint4*>(yb + (long long)p * ldy) = pack8(o);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, row held in registers (C <= 2048), two-pass variance in fp32.
+// LayerNorm: one warp per row, the row lives in registers as NV 16-byte vectors per lane (C <= 256*NV).
 // ---------------------------------------------------------------------------------------------
-constexpr int kLNMaxPairs = 32;   // per lane: C/2/32 <= 32  -> C <= 2048
-
-template <int MODE>
+template <int MODE, int NV>
 __global__ void __launch_bounds__(256) ln_kernel(const bf16* __restrict__ x, long long ldx,
                                                  const bf16* __restrict__ dy, long long lddy,
                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -197,69 +290,97 @@ __global__ void __launch_bounds__(256) ln_kernel(const bf16* __restrict__ x, lon
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const int pairs = C >> 1;
+  const int vecs = C >> 3;
   const bf16* xr = x + (long long)row * ldx;
-  float2 v[kLNMaxPairs];
-  float s = 0.f;
+  float xf[NV][8];
+  uint4 raw[NV], draw[NV], araw[NV];
 #pragma unroll
-  for (int i = 0; i < kLNMaxPairs; ++i) {
-    const int p = lane + i * 32;
-    if (p < pairs) {
-      v[i] = __bfloat1622float2(*reinterpret_cast<const bf162*>(xr + 2 * p));
-      s += v[i].x + v[i].y;
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + i * 32;
+    if (v < vecs) {
+      raw[i] = ld16(xr + v * 8);
+      if (MODE == 1) {
+        draw[i] = ld16(dy + (long long)row * lddy + v * 8);
+        if (add) araw[i] = ld16(add + (long long)row * ldadd + v * 8);
+      }
     }
   }
-  float mean, rstd;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (lane + i * 32 < vecs) {
+      unpack8(raw[i], xf[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += xf[i][j];
+    }
+  }
+  bf16* yr = y + (long long)row * ldy;
   if (MODE == 0) {
-    mean = warp_sum(s) / (float)C;
+    const float mean = warp_sum(s) / (float)C;
     float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLNMaxPairs; ++i) {
-      const int p = lane + i * 32;
-      if (p < pairs) { const float a = v[i].x - mean, c = v[i].y - mean; ss += a * a + c * c; }
-    }
-    rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
-    if (lane == 0 && stats) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
-    bf16* yr = y + (long long)row * ldy;
+    for (int i = 0; i < NV; ++i) {
+      if (lane + i * 32 < vecs) {
 #pragma unroll
-    for (int i = 0; i < kLNMaxPairs; ++i) {
-      const int p = lane + i * 32;
-      if (p < pairs) {
-        const float2 g = *reinterpret_cast<const float2*>(gamma + 2 * p);
-        const float2 bb = *reinterpret_cast<const float2*>(beta + 2 * p);
-        *reinterpret_cast<bf162*>(yr + 2 * p) =
-            __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
+        for (int j = 0; j < 8; ++j) { const float a = xf[i][j] - mean; ss = fmaf(a, a, ss); }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+    if (lane == 0 && stats) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + i * 32;
+      if (v < vecs) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (xf[i][j] - mean) * rstd * g[j] + bb[j];
+        *reinterpret_cast<uint4*>(yr + v * 8) = pack8(o);
       }
     }
   } else {
-    mean = stats[row * 2]; rstd = stats[row * 2 + 1];
-    const bf16* dr = dy + (long long)row * lddy;
-    float2 dh[kLNMaxPairs];
+    const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+    float dh[NV][8];
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLNMaxPairs; ++i) {
-      const int p = lane + i * 32;
-      if (p < pairs) {
-        const float2 d = __bfloat1622float2(*reinterpret_cast<const bf162*>(dr + 2 * p));
-        const float2 g = *reinterpret_cast<const float2*>(gamma + 2 * p);
-        dh[i] = make_float2(d.x * g.x, d.y * g.y);
-        v[i].x = (v[i].x - mean) * rstd; v[i].y = (v[i].y - mean) * rstd;
-        c1 += dh[i].x + dh[i].y;
-        c2 += dh[i].x * v[i].x + dh[i].y * v[i].y;
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + i * 32;
+      if (v < vecs) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        float df[8];
+        unpack8(draw[i], df);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dh[i][j] = df[j] * g[j];
+          xf[i][j] = (xf[i][j] - mean) * rstd;
+          c1 += dh[i][j];
+          c2 = fmaf(dh[i][j], xf[i][j], c2);
+        }
       }
     }
     c1 = warp_sum(c1) / (float)C;
     c2 = warp_sum(c2) / (float)C;
-    bf16* yr = y + (long long)row * ldy;
-    const bf16* ar = add ? add + (long long)row * ldadd : nullptr;
 #pragma unroll
-    for (int i = 0; i < kLNMaxPairs; ++i) {
-      const int p = lane + i * 32;
-      if (p < pairs) {
-        float o0 = rstd * (dh[i].x - c1 - v[i].x * c2);
-        float o1 = rstd * (dh[i].y - c1 - v[i].y * c2);
-        if (ar) { const float2 a = __bfloat1622float2(*reinterpret_cast<const bf162*>(ar + 2 * p)); o0 += a.x; o1 += a.y; }
-        *reinterpret_cast<bf162*>(yr + 2 * p) = __floats2bfloat162_rn(o0, o1);
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + i * 32;
+      if (v < vecs) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (dh[i][j] - c1 - xf[i][j] * c2);
+        if (add) {
+          float t[8];
+          unpack8(araw[i], t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += t[j];
+        }
+        *reinterpret_cast<uint4*>(yr + v * 8) = pack8(o);
       }
     }
   }
@@ -285,43 +406,54 @@ __global__ void __launch_bounds__(256) geglu_kernel(const bf16* __restrict__ h, 
        i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / vecs;
     const int c = (int)(i % vecs) * 8;
-    const uint4 ar = *reinterpret_cast<const uint4*>(h + row * ldh + c);
-    const uint4 gr = *reinterpret_cast<const uint4*>(h + row * ldh + F + c);
-    const uint32_t aw[4] = {ar.x, ar.y, ar.z, ar.w};
-    const uint32_t gw[4] = {gr.x, gr.y, gr.z, gr.w};
+    float a[8], g[8];
+    unpack8(ld16(h + row * ldh + c), a);
+    unpack8(ld16(h + row * ldh + F + c), g);
     if (MODE == 0) {
-      uint32_t o[4];
+      float o[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 a = unpack_bf162(aw[j]), g = unpack_bf162(gw[j]);
-        o[j] = pack_bf162(a.x * gelu_f(g.x), a.y * gelu_f(g.y));
-      }
-      *reinterpret_cast<uint4*>(out + row * ldo + c) = make_uint4(o[0], o[1], o[2], o[3]);
+      for (int j = 0; j < 8; ++j) o[j] = a[j] * gelu_f(g[j]);
+      *reinterpret_cast<uint4*>(out + row * ldo + c) = pack8(o);
     } else {
-      const uint4 dr = *reinterpret_cast<const uint4*>(dy + row * lddy + c);
-      const uint32_t dw[4] = {dr.x, dr.y, dr.z, dr.w};
-      uint32_t oa[4], og[4];
+      float d[8], oa[8], og[8];
+      unpack8(ld16(dy + row * lddy + c), d);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 a = unpack_bf162(aw[j]), g = unpack_bf162(gw[j]), d = unpack_bf162(dw[j]);
-        oa[j] = pack_bf162(d.x * gelu_f(g.x), d.y * gelu_f(g.y));
-        og[j] = pack_bf162(d.x * a.x * dgelu_f(g.x), d.y * a.y * dgelu_f(g.y));
+      for (int j = 0; j < 8; ++j) {
+        oa[j] = d[j] * gelu_f(g[j]);
+        og[j] = d[j] * a[j] * dgelu_f(g[j]);
       }
-      *reinterpret_cast<uint4*>(out + row * ldo + c) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
-      *reinterpret_cast<uint4*>(out + row * ldo + F + c) = make_uint4(og[0], og[1], og[2], og[3]);
+      *reinterpret_cast<uint4*>(out + row * ldo + c) = pack8(oa);
+      *reinterpret_cast<uint4*>(out + row * ldo + F + c) = pack8(og);
     }
   }
 }
 
-int gn_ppc(int hw) {  // pixels per CTA: aim for a few hundred CTAs
-  int chunks = hw < 296 ? hw : 296;
-  return vn_cdiv(hw, chunks);
+int gn_check(int C, int groups, long long ldx) {
+  VN_CHECK(groups > 0 && groups <= kMaxGroups && C % groups == 0, "groupnorm: C=%d groups=%d", C, groups);
+  VN_CHECK(C % 8 == 0 && C <= kMaxC * 4, "groupnorm: need C %% 8 == 0 (C=%d)", C);
+  VN_CHECK(C / 8 <= 512, "groupnorm: C=%d too wide (C <= 4096)", C);
+  VN_CHECK(ldx % 8 == 0, "groupnorm: row stride must be a multiple of 8");
+  return 0;
 }
 
-int gn_check(int C, int groups, long long ldx) {
-  VN_CHECK(groups > 0 && groups <= 64 && C % groups == 0, "groupnorm: C=%d groups=%d", C, groups);
-  VN_CHECK((C / groups) % 2 == 0 && C % 8 == 0 && C <= kMaxC, "groupnorm: need even channels/group, C%%8==0, C<=%d (C=%d)", kMaxC, C);
-  VN_CHECK(ldx % 8 == 0, "groupnorm: row stride must be a multiple of 8");
+template <int MODE>
+int ln_launch(const bf16* x, long long ldx, const bf16* dy, long long lddy, const float* gamma, const float* beta,
+              float eps, float* stats, const bf16* add, long long ldadd, bf16* y, long long ldy, int rows, int C,
+              cudaStream_t s) {
+  VN_CHECK(C % 8 == 0 && C <= 2048, "layernorm: C=%d unsupported (C %% 8 == 0, C <= 2048)", C);
+  VN_CHECK(ldx % 8 == 0 && ldy % 8 == 0 && lddy % 8 == 0 && ldadd % 8 == 0, "layernorm: strides must be multiples of 8");
+  const int nv = (C / 8 + 31) / 32;
+  const int grid = vn_cdiv(rows, 8);
+#define VN_LN_CASE(NV)                                                                                              \
+  case NV:                                                                                                          \
+    ln_kernel<MODE, NV><<<grid, 256, 0, s>>>(x, ldx, dy, lddy, gamma, beta, eps, stats, add, ldadd, y, ldy, rows, C); \
+    break;
+  switch (nv) {
+    VN_LN_CASE(1) VN_LN_CASE(2) VN_LN_CASE(3) VN_LN_CASE(4) VN_LN_CASE(5) VN_LN_CASE(6) VN_LN_CASE(7) VN_LN_CASE(8)
+    default: VN_CHECK(false, "layernorm: C=%d unsupported", C);
+  }
+#undef VN_LN_CASE
+  VN_LAUNCH_OK();
   return 0;
 }
 
@@ -330,10 +462,10 @@ int gn_check(int C, int groups, long long ldx) {
 extern "C" int vn_groupnorm_stats(const void* x, int64_t ldx, int nb, int hw, int C, int groups, float* stats,
                                   vn_stream_t s) {
   if (gn_check(C, groups, ldx)) return -1;
-  const int ppc = gn_ppc(hw);
-  dim3 grid(vn_cdiv(hw, ppc), nb);
-  gn_reduce_kernel<0><<<grid, kGNThreads, 0, (cudaStream_t)s>>>((const bf16*)x, ldx, nullptr, 0, nullptr, nullptr,
-                                                                  nullptr, 0.f, 0, stats, hw, C, groups, ppc);
+  const GNGeom g = gn_geom(nb, hw, C);
+  dim3 grid(g.chunks, nb);
+  gn_reduce_kernel<0><<<grid, g.threads, 0, (cudaStream_t)s>>>((const bf16*)x, ldx, nullptr, 0, nullptr, nullptr,
+                                                                 nullptr, 0.f, 0, stats, hw, C, groups, g.k, g.ppc);
   VN_LAUNCH_OK();
   return 0;
 }
@@ -343,12 +475,11 @@ extern "C" int vn_groupnorm_apply(const void* x, int64_t ldx, const float* stats
                                   int groups, vn_stream_t s) {
   if (gn_check(C, groups, ldx)) return -1;
   VN_CHECK(ldy % 8 == 0, "groupnorm: ldy must be a multiple of 8");
-  int ppc = gn_ppc(hw);
-  if (ppc < 4) ppc = hw < 4 ? hw : 4;       // amortise the per-CTA a/b staging
-  dim3 grid(vn_cdiv(hw, ppc), nb);
-  gn_apply_kernel<0><<<grid, kGNThreads, 2 * C * sizeof(float), (cudaStream_t)s>>>(
-      (const bf16*)x, ldx, nullptr, 0, stats, nullptr, gamma, beta, eps, silu, nullptr, 0, nullptr, 0, (bf16*)y, ldy,
-      hw, C, groups, ppc);
+  const GNGeom g = gn_geom(nb, hw, C);
+  dim3 grid(g.chunks, nb);
+  gn_apply_kernel<0><<<grid, g.threads, 0, (cudaStream_t)s>>>((const bf16*)x, ldx, nullptr, 0, stats, nullptr, gamma,
+                                                                beta, eps, silu, nullptr, 0, nullptr, 0, (bf16*)y, ldy,
+                                                                hw, C, groups, g.k, g.ppc);
   VN_LAUNCH_OK();
   return 0;
 }
@@ -357,10 +488,11 @@ extern "C" int vn_groupnorm_bwd_stats(const void* x, int64_t ldx, const void* dy
                                       const float* gamma, const float* beta, float eps, int silu, float* red, int nb,
                                       int hw, int C, int groups, vn_stream_t s) {
   if (gn_check(C, groups, ldx)) return -1;
-  const int ppc = gn_ppc(hw);
-  dim3 grid(vn_cdiv(hw, ppc), nb);
-  gn_reduce_kernel<1><<<grid, kGNThreads, 0, (cudaStream_t)s>>>((const bf16*)x, ldx, (const bf16*)dy, lddy, stats,
-                                                                  gamma, beta, eps, silu, red, hw, C, groups, ppc);
+  VN_CHECK(lddy % 8 == 0, "groupnorm bwd: strides must be multiples of 8");
+  const GNGeom g = gn_geom(nb, hw, C);
+  dim3 grid(g.chunks, nb);
+  gn_reduce_kernel<1><<<grid, g.threads, 0, (cudaStream_t)s>>>((const bf16*)x, ldx, (const bf16*)dy, lddy, stats, gamma,
+                                                                 beta, eps, silu, red, hw, C, groups, g.k, g.ppc);
   VN_LAUNCH_OK();
   return 0;
 }
@@ -371,34 +503,27 @@ extern "C" int vn_groupnorm_bwd_apply(const void* x, int64_t ldx, const void* dy
                                       int64_t lddx, int nb, int hw, int C, int groups, vn_stream_t s) {
   if (gn_check(C, groups, ldx)) return -1;
   VN_CHECK(lddy % 8 == 0 && lddx % 8 == 0 && ldadd1 % 8 == 0 && ldadd2 % 8 == 0, "groupnorm bwd: strides must be multiples of 8");
-  int ppc = gn_ppc(hw);
-  if (ppc < 4) ppc = hw < 4 ? hw : 4;
-  dim3 grid(vn_cdiv(hw, ppc), nb);
-  gn_apply_kernel<1><<<grid, kGNThreads, (2 * C + 4 * groups) * sizeof(float), (cudaStream_t)s>>>(
-      (const bf16*)x, ldx, (const bf16*)dy, lddy, stats, red, gamma, beta, eps, silu, (const bf16*)add1, ldadd1,
-      (const bf16*)add2, ldadd2, (bf16*)dx, lddx, hw, C, groups, ppc);
+  const GNGeom g = gn_geom(nb, hw, C);
+  dim3 grid(g.chunks, nb);
+  gn_apply_kernel<1><<<grid, g.threads, 0, (cudaStream_t)s>>>((const bf16*)x, ldx, (const bf16*)dy, lddy, stats, red,
+                                                                gamma, beta, eps, silu, (const bf16*)add1, ldadd1,
+                                                                (const bf16*)add2, ldadd2, (bf16*)dx, lddx, hw, C, groups,
+                                                                g.k, g.ppc);
   VN_LAUNCH_OK();
   return 0;
 }
 
 extern "C" int vn_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y,
                                 int64_t ldy, float* stats, int rows, int C, vn_stream_t s) {
-  VN_CHECK(C % 2 == 0 && C <= 64 * kLNMaxPairs, "layernorm: C=%d unsupported", C);
-  ln_kernel<0><<<vn_cdiv(rows, 8), 256, 0, (cudaStream_t)s>>>((const bf16*)x, ldx, nullptr, 0, gamma, beta, eps, stats,
-                                                                nullptr, 0, (bf16*)y, ldy, rows, C);
-  VN_LAUNCH_OK();
-  return 0;
+  return ln_launch<0>((const bf16*)x, ldx, nullptr, 0, gamma, beta, eps, stats, nullptr, 0, (bf16*)y, ldy, rows, C,
+                      (cudaStream_t)s);
 }
 
 extern "C" int vn_layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* gamma,
                                 const float* stats, const void* add, int64_t ldadd, void* dx, int64_t lddx, int rows,
                                 int C, vn_stream_t s) {
-  VN_CHECK(C % 2 == 0 && C <= 64 * kLNMaxPairs, "layernorm: C=%d unsupported", C);
-  ln_kernel<1><<<vn_cdiv(rows, 8), 256, 0, (cudaStream_t)s>>>((const bf16*)x, ldx, (const bf16*)dy, lddy, gamma, nullptr,
-                                                                0.f, const_cast<float*>(stats), (const bf16*)add, ldadd,
-                                                                (bf16*)dx, lddx, rows, C);
-  VN_LAUNCH_OK();
-  return 0;
+  return ln_launch<1>((const bf16*)x, ldx, (const bf16*)dy, lddy, gamma, nullptr, 0.f, const_cast<float*>(stats),
+                      (const bf16*)add, ldadd, (bf16*)dx, lddx, rows, C, (cudaStream_t)s);
 }
 
 extern "C" int vn_geglu_fwd(const void* h, int64_t ldh, void* y, int64_t ldy, int rows, int F, vn_stream_t s) {

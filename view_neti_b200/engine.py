@@ -58,6 +58,7 @@ class UNetEngine:
         if self.dev.type != "cuda":
             raise ops._abi.VNError("UNetEngine needs a CUDA device: the hot path has no CPU fallback")
         self._plans: Dict[Tuple[int, int, int], "_Plan"] = {}
+        self.use_graphs = True      # drop-in API: replay CUDA graphs from the second step on
         self._prep_weights(state_dict)
 
     # ------------------------------------------------------------------------------------------------
@@ -178,8 +179,12 @@ class _Plan:
         self.d_ctx = self.buf("out.d_ctx", (2, self.n_layers, nb, self.L, cfg.cross_attention_dim), F32)
         self.target = self.buf("in.target", (nb, cfg.out_channels, h, w), F32)
         self.loss = self.buf("out.loss", (1,), F32)
-        self.fwd_graph = None
-        self.train_graph = None
+        n_gn = 2 * (len(eng.res)) + len(eng.xf) + 1
+        self.stat_f = self.buf("gn.stats", (n_gn, nb, cfg.norm_num_groups, 2), F32)     # (sum x, sum x^2)
+        self.stat_b = self.buf("gn.red", (n_gn, nb, cfg.norm_num_groups, 2), F32)       # backward reductions
+        self._stat_slots: Dict[str, int] = {}
+        self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
+        self.launches: Dict[str, int] = {}
         self._saved = False
         self.trace_f: Dict[str, torch.Tensor] = {}     # block name -> output view   (parity debugging)
         self.trace_b: Dict[str, torch.Tensor] = {}     # block name -> d(output) view
@@ -193,6 +198,14 @@ class _Plan:
         assert tuple(t.shape) == tuple(shape) and t.dtype == dtype, name
         return t
 
+    def _stat(self, name: str, arena: torch.Tensor) -> torch.Tensor:
+        """[nb, groups, 2] fp32 GroupNorm statistics slot; each arena is zeroed by ONE memset per pass."""
+        i = self._stat_slots.get(name)
+        if i is None:
+            i = self._stat_slots[name] = len([k for k in self._stat_slots if k.endswith(name[-3:])])
+            assert i < arena.shape[0], "statistics arena too small"
+        return arena[i]
+
     def act_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self.bufs.values())
 
@@ -200,8 +213,7 @@ class _Plan:
     def _gn(self, name, x, gb, eps, silu, hw):
         """GroupNorm(+SiLU) of a [nb, hw, C] view; stats are kept for the backward."""
         G = self.eng.cfg.norm_num_groups
-        st = self.buf(name + ".st", (self.nb, G, 2), F32)
-        st.zero_()
+        st = self._stat(name + ".st", self.stat_f)
         y = self.buf(name + ".y", (self.nb, hw, x.shape[-1]))
         ops.groupnorm_stats(x, self.nb, hw, G, st)
         ops.groupnorm_apply(x, st, gb[0], gb[1], eps, silu, y, self.nb, hw, G)
@@ -209,9 +221,8 @@ class _Plan:
 
     def _gn_bwd(self, name, x, dy, gb, eps, silu, hw, dx, add1=None, add2=None):
         G = self.eng.cfg.norm_num_groups
-        st = self.bufs[name + ".st"]
-        red = self.buf(name + ".red", (self.nb, G, 2), F32)
-        red.zero_()
+        st = self._stat(name + ".st", self.stat_f)
+        red = self._stat(name + ".red", self.stat_b)
         ops.groupnorm_bwd(x, dy, st, red, gb[0], gb[1], eps, silu, dx, self.nb, hw, G, add1=add1, add2=add2)
 
     def _res_fwd(self, name, x, H, W, out):
@@ -355,6 +366,7 @@ class _Plan:
         nlev = len(ch)
         B = self.bufs
         # time embedding: sinusoid -> Linear -> SiLU -> Linear, then all ResBlock projections in one launch
+        self.stat_f.zero_()
         sin = self.buf("temb.sin", (nb, ch[0]), F32)
         ops.timestep_sinusoid(self.timesteps, sin)
         e1 = self.buf("temb.e1", (nb, cfg.time_embed_dim), F32)
@@ -468,6 +480,7 @@ class _Plan:
         has_attn_up = list(reversed(cfg.down_has_attn))
         cats = self._cats
         H, W = h, w
+        self.stat_b.zero_()
         dy = self.buf("bwd.dy", (nb, H * W, ch[0]))
         ops.conv_out_bwd(self.d_eps, eng.conv_out_w, dy.view(nb, H, W, ch[0]))
         dcur = self.buf(f"bwd.up.{nlev - 1}.out", (nb, H * W, ch[0]))
@@ -557,22 +570,44 @@ class _Plan:
         ops.mse_loss(self.eps, self.target, self.loss, self.d_eps)
         self.backward()
 
-    def capture(self, what: str = "train"):
-        """Capture the launch sequence in a CUDA graph (after one eager warm-up that configures every kernel)."""
-        fn = self.train_step if what == "train" else self.forward
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            fn()
-        torch.cuda.current_stream().wait_stream(s)
+    def _capture(self, fn):
+        """Record fn's launch sequence in a CUDA graph.  Every kernel must already have run once eagerly
+        (function attributes set, all buffers allocated), so nothing but launches happens here."""
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         ops.launch_count_reset()
         with torch.cuda.graph(g):
             fn()
-        n = ops.launch_count()
-        if what == "train":
-            self.train_graph, self.train_launches = g, n
-        else:
-            self.fwd_graph, self.fwd_launches = g, n
-        return g
+        return g, ops.launch_count()
+
+    def capture(self, what: str = "train"):
+        """what: 'train' (forward + MSE + backward), 'fwd', 'bwd'.  Needs one eager run of the same sequence first."""
+        if what not in self.graphs:
+            if not self._saved or (what != "fwd" and "bwd.dy" not in self.bufs):
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self.train_step()
+                torch.cuda.current_stream().wait_stream(s)
+            fn = {"train": self.train_step, "fwd": self.forward, "bwd": self.backward}[what]
+            self.graphs[what], self.launches[what] = self._capture(fn)
+        return self.graphs[what]
+
+    def run_forward(self) -> torch.Tensor:
+        """Used by the drop-in UNet: eager on the first call, CUDA-graph replay afterwards."""
+        if "fwd" in self.graphs:
+            self.graphs["fwd"].replay()
+            self._saved = True
+            return self.eps
+        out = self.forward()
+        if self.eng.use_graphs and "bwd.dy" in self.bufs:
+            # both graphs are captured here (caller's thread), the autograd thread only ever replays
+            self.capture("fwd")
+            self.capture("bwd")
+        return out
+
+    def run_backward(self) -> torch.Tensor:
+        if "bwd" in self.graphs:
+            self.graphs["bwd"].replay()
+            return self.d_ctx
+        return self.backward()

@@ -52,7 +52,7 @@ class _UNetFn(torch.autograd.Function):
         for i in range(n_ctx):
             plan.ctx[0, i].copy_(contexts[i])
             plan.ctx[1, i].copy_(contexts[n_ctx + i])
-        plan.forward()
+        plan.run_forward()
         model._generation += 1
         ctx.plan, ctx.model, ctx.gen, ctx.n_ctx = plan, model, model._generation, n_ctx
         ctx.dtypes = [c.dtype for c in contexts]
@@ -65,7 +65,7 @@ class _UNetFn(torch.autograd.Function):
             raise VNError("backward() after another forward on the same UNet: the static activation plan was "
                           "overwritten (call backward before the next forward, as coach.py:197-214 does)")
         plan.d_eps.copy_(d_eps)
-        plan.backward()
+        plan.run_backward()
         n = ctx.n_ctx
         needs = ctx.needs_input_grad[4:]
         grads: List[Optional[torch.Tensor]] = []
