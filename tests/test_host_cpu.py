@@ -1,0 +1,122 @@
+"""-m "not gpu": the C-ABI library loads and exports every symbol the header declares; host-side logic (context
+protocol, schedulers, flat-gradient all-reduce over gloo with world_size 2)."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from view_neti_b200 import _abi
+    from view_neti_b200.build import build
+    build()
+    lib = _abi.load()
+    hdr = open(os.path.join(ROOT, "include", "viewneti.h")).read()
+    declared = set(re.findall(r"\b(vn_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"vn_stream_t"}
+    assert len(declared) >= 30
+    assert declared == set(_abi.SIGNATURES), (declared ^ set(_abi.SIGNATURES))
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.vn_version() == 1
+    assert isinstance(lib.vn_last_error(), bytes)
+
+
+def test_product_path_fails_loudly_without_cuda():
+    from view_neti_b200._abi import VNError
+    from view_neti_b200.sd21 import TINY, init_state_dict
+    from view_neti_b200.unet import UNet2DConditionModel
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises((VNError, RuntimeError, AssertionError)):
+        UNet2DConditionModel(init_state_dict(TINY, 0), TINY, "cpu")
+
+
+def test_context_protocol_static_binding():
+    """Layer l reads entry (this_idx + l) % 16; K from CONTEXT_TENSOR, V from BYPASS when present (xti...:14-26)."""
+    from view_neti_b200.sd21 import TINY
+    from view_neti_b200.unet import UNet2DConditionModel
+    m = UNet2DConditionModel.__new__(UNet2DConditionModel)
+    m.cfg = TINY
+    d = {"this_idx": 3}
+    for i in range(16):
+        d[f"CONTEXT_TENSOR_{i}"] = torch.full((1, 2, 2), float(i))
+        if i % 2 == 0:
+            d[f"CONTEXT_TENSOR_BYPASS_{i}"] = torch.full((1, 2, 2), 100.0 + i)
+    c = UNet2DConditionModel._contexts(m, d)
+    assert len(c) == 32 and d["this_idx"] == 3
+    for l in range(16):
+        i = (3 + l) % 16
+        assert float(c[l][0, 0, 0]) == i
+        assert float(c[16 + l][0, 0, 0]) == (100.0 + i if i % 2 == 0 else i)
+    t = torch.zeros(1, 2, 2)
+    assert all(x is t for x in UNet2DConditionModel._contexts(m, t))
+
+
+def test_schedulers_match_oracle():
+    import numpy as np
+    from oracle import schedulers as O
+    from view_neti_b200.schedulers import DDIMScheduler, DDPMScheduler, alphas_cumprod
+    assert np.allclose(alphas_cumprod().double().numpy(), O.alphas_cumprod(), rtol=2e-6)
+    s = DDIMScheduler("v_prediction")
+    s.set_timesteps(50)
+    assert s.timesteps.tolist() == O.ddim_timesteps(50).tolist()
+    assert s.timesteps[0] == 981 and s.timesteps[-1] == 1
+    g = torch.Generator().manual_seed(0)
+    x, e = torch.randn(2, 4, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g)
+    for pt in ("epsilon", "v_prediction"):
+        s = DDIMScheduler(pt)
+        s.set_timesteps(50)
+        for t in (981, 501, 1):
+            ours = s.step(e, t, x).prev_sample.numpy()
+            ref = O.ddim_step(e.double().numpy(), t, x.double().numpy(), 50, pt)
+            assert np.allclose(ours, ref, rtol=1e-4, atol=1e-5)
+    d = DDPMScheduler()
+    t = torch.tensor([0, 999])
+    assert np.allclose(d.add_noise(x, e, t).numpy(), O.add_noise(x.double().numpy(), e.double().numpy(), t.numpy()), atol=1e-5)
+    assert np.allclose(d.get_velocity(x, e, t).numpy(), O.get_velocity(x.double().numpy(), e.double().numpy(), t.numpy()), atol=1e-5)
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from view_neti_b200.training.dist import FlatGradAllReducer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    a, b, c = (torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2)))
+    a.grad = torch.full((3, 4), float(rank + 1))
+    b.grad = torch.arange(5.0) * (rank + 1)          # c.grad stays None on every rank -> zeros
+    red = FlatGradAllReducer([a, b, c])
+    flat = red.allreduce_()
+    q.put((rank, a.grad.clone(), b.grad.clone(), c.grad.clone(), flat.numel()))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, a, b, c, n in res:
+        assert n == 12 + 5 + 2
+        assert torch.allclose(a, torch.full((3, 4), 1.5))            # mean of 1 and 2
+        assert torch.allclose(b, torch.arange(5.0) * 1.5)
+        assert torch.equal(c, torch.zeros(2))
+
+
+def test_synthetic_conditioning_emits_xti_dict():
+    from view_neti_b200.training.coach import SyntheticConditioning
+    c = SyntheticConditioning(dim=64, rank=4)
+    d = c(timesteps=torch.zeros(3, dtype=torch.long))
+    assert d["this_idx"] == 0 and len([k for k in d if k.startswith("CONTEXT_TENSOR")]) == 32
+    assert d["CONTEXT_TENSOR_BYPASS_15"].shape == (3, 77, 64) and d["CONTEXT_TENSOR_0"].requires_grad

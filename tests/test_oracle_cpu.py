@@ -1,0 +1,131 @@
+"""-m "not gpu": the oracle against the golden vectors produced by the reference's own code
+(tests/golden/make_golden.py executes /root/reference/models/xti_attention_processor.py), plus structural pins."""
+import os
+
+import pytest
+import torch
+
+from oracle.unet_sd21 import CrossAttention, UNetOracle, XTIAttenProcOracle, train_step_oracle
+from tests.unet_parity import ctx_to, make_inputs
+from view_neti_b200.sd21 import SD21, TINY, cross_attn_layer_names, init_state_dict, num_params, param_table
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "xti_attn.pt")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(GOLD)
+
+
+def _attn(state, qdim, cdim, heads):
+    m = CrossAttention(qdim, cdim, heads)
+    m.load_state_dict(state)
+    m.processor = XTIAttenProcOracle()
+    return m
+
+
+def test_oracle_processor_matches_reference_outputs(gold):
+    cross = _attn(gold["cross_state"], 128, 192, gold["heads"])
+    selfa = _attn(gold["self_state"], 128, None, gold["heads"])
+    h = gold["hidden"]
+    with torch.no_grad():
+        d = dict(gold["ctx"])
+        y = cross(h, encoder_hidden_states=d)
+        assert torch.equal(y, gold["dict_bypass"])
+        assert d["this_idx"] == gold["dict_bypass_this_idx_after"] == 4
+        d = {k: v for k, v in gold["ctx"].items() if "BYPASS" not in k}
+        d["this_idx"] = 15
+        assert torch.equal(cross(h, encoder_hidden_states=d), gold["dict_nobypass_idx15"])
+        assert d["this_idx"] == gold["dict_nobypass_this_idx_after"] == 0          # wraps modulo 16
+        assert torch.equal(cross(h, encoder_hidden_states=gold["ctx"]["CONTEXT_TENSOR_5"]), gold["tensor_ctx"])
+        assert torch.equal(selfa(h, encoder_hidden_states=None), gold["self"])
+
+
+def test_oracle_processor_matches_reference_gradients(gold):
+    cross = _attn(gold["cross_state"], 128, 192, gold["heads"])
+    d = {k: (v.clone().requires_grad_(True) if torch.is_tensor(v) else v) for k, v in gold["ctx"].items()}
+    h = gold["hidden"].clone().requires_grad_(True)
+    y = cross(h, encoder_hidden_states=d)
+    (y * gold["grad_w"]).sum().backward()
+    assert torch.allclose(d["CONTEXT_TENSOR_3"].grad, gold["grad_ctx_k"], rtol=0, atol=1e-6)
+    assert torch.allclose(d["CONTEXT_TENSOR_BYPASS_3"].grad, gold["grad_ctx_v"], rtol=0, atol=1e-6)
+    assert torch.allclose(h.grad, gold["grad_hidden"], rtol=0, atol=1e-6)
+
+
+def test_same_k_and_v_context_is_plain_cross_attention(gold):
+    """XTI with CONTEXT_TENSOR_BYPASS_i == CONTEXT_TENSOR_i is vanilla cross-attention (SURVEY 8c invariant i)."""
+    cross = _attn(gold["cross_state"], 128, 192, gold["heads"])
+    c = gold["ctx"]["CONTEXT_TENSOR_3"]
+    with torch.no_grad():
+        a = cross(gold["hidden"], encoder_hidden_states={"this_idx": 3, "CONTEXT_TENSOR_3": c, "CONTEXT_TENSOR_BYPASS_3": c})
+        b = cross(gold["hidden"], encoder_hidden_states=c)
+    assert torch.equal(a, b)
+
+
+def test_sd21_topology_pins():
+    assert num_params(SD21) == 865_910_724                       # SD-2.1 UNet (diffusers reports 865.91 M)
+    names = cross_attn_layer_names(SD21)
+    assert len(names) == 16 == SD21.num_cross_layers
+    assert names[0] == "down_blocks.0.attentions.0" and names[6] == "mid_block.attentions.0" \
+        and names[-1] == "up_blocks.3.attentions.2"
+    keys = {k for k, _, _ in param_table(SD21)}
+    for k in ("conv_in.weight", "time_embedding.linear_2.bias", "down_blocks.1.attentions.0.transformer_blocks.0.attn2.to_k.weight",
+              "up_blocks.1.upsamplers.0.conv.weight", "up_blocks.3.resnets.2.conv_shortcut.weight", "conv_norm_out.bias"):
+        assert k in keys
+    shp = {k: s for k, s, _ in param_table(SD21)}
+    assert shp["down_blocks.0.attentions.0.transformer_blocks.0.attn2.to_k.weight"] == (320, 1024)
+    assert shp["up_blocks.0.resnets.0.conv1.weight"] == (1280, 2560, 3, 3)
+    assert shp["up_blocks.3.resnets.0.conv1.weight"] == (320, 960, 3, 3)
+
+
+def test_oracle_unet_state_dict_keys_and_this_idx_roundtrip():
+    sd = init_state_dict(TINY, 0)
+    unet = UNetOracle(TINY)
+    missing, unexpected = unet.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    lat, t, tgt, ctx = make_inputs(TINY, 1, 8, 8)
+    c = ctx_to(ctx, "cpu")
+    c["this_idx"] = 5
+    eps, loss, grads = train_step_oracle(unet, lat, t, tgt, c)
+    assert c["this_idx"] == 5                                     # 16 increments modulo 16 (SURVEY 8c invariant iii)
+    assert eps.shape == lat.shape and torch.isfinite(eps).all() and all(g is not None for g in grads)
+
+
+def test_plain_tensor_context_equals_dict_of_identical_entries():
+    """SURVEY 8c invariant ii."""
+    sd = init_state_dict(TINY, 0)
+    unet = UNetOracle(TINY)
+    unet.load_state_dict(sd)
+    lat, t, _, ctx = make_inputs(TINY, 1, 8, 8)
+    c0 = ctx["CONTEXT_TENSOR_0"]
+    with torch.no_grad():
+        a = unet(lat, t, c0).sample
+        b = unet(lat, t, {"this_idx": 0, **{f"CONTEXT_TENSOR_{i}": c0 for i in range(16)}}).sample
+    assert torch.equal(a, b)
+
+
+def test_context_gradient_matches_finite_differences():
+    """SURVEY 8c invariant iv: d loss / d ctx of the oracle agrees with central differences (float64)."""
+    torch.manual_seed(0)
+    sd = {k: v.double() for k, v in init_state_dict(TINY, 0).items()}
+    unet = UNetOracle(TINY).double()
+    unet.load_state_dict(sd)
+    for m in unet.modules():                      # `.float()` logits would inject fp32 noise into the differences
+        if isinstance(m, CrossAttention):
+            m.upcast_attention = False
+    lat, t, tgt, ctx = make_inputs(TINY, 1, 8, 8)
+    c = {k: (v.double().requires_grad_(True) if torch.is_tensor(v) else v) for k, v in ctx.items()}
+    eps, loss, grads = train_step_oracle(unet, lat.double(), t, tgt.double(), c)
+    keys = [k for k, v in c.items() if torch.is_tensor(v)]
+    g = dict(zip(keys, grads))
+    for key, idx in (("CONTEXT_TENSOR_7", (0, 3, 5)), ("CONTEXT_TENSOR_BYPASS_0", (0, 10, 100))):
+        h = 1e-4
+        vals = []
+        for sgn in (+1, -1):
+            c2 = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in c.items()}
+            c2[key][idx] += sgn * h
+            with torch.no_grad():
+                e = unet(lat.double(), t, c2).sample
+            vals.append(torch.nn.functional.mse_loss(e, tgt.double()).item())
+        fd = (vals[0] - vals[1]) / (2 * h)
+        assert abs(fd - g[key][idx].item()) <= 1e-6 + 1e-3 * abs(fd), (key, fd, g[key][idx].item())

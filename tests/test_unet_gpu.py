@@ -1,0 +1,209 @@
+"""-m gpu: the CUDA path, called through the drop-in API / C-ABI, against the CPU oracle and the golden vectors."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.unet_parity import ctx_to, make_inputs, rel, run_parity
+from view_neti_b200.sd21 import SD21, TINY, init_state_dict
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "xti_attn.pt")
+
+# tolerances: BASELINE.json north_star - eps-MSE vs reference < 1e-3, mapper-grad relative error < 1e-2 (judged as
+# the relative L2 error of the flat gradient vector); bf16 operands, fp32 accumulation.
+EPS_MSE_TOL = 1e-3
+GRAD_FLAT_TOL_SD21 = 1e-2
+
+
+@pytest.fixture(scope="module")
+def tiny_model():
+    from view_neti_b200.unet import UNet2DConditionModel
+    return UNet2DConditionModel(init_state_dict(TINY, 0), TINY, "cuda")
+
+
+@pytest.fixture(scope="module")
+def sd_model():
+    from view_neti_b200.unet import UNet2DConditionModel
+    return UNet2DConditionModel(init_state_dict(SD21, 0), SD21, "cuda")
+
+
+def test_unet_parity_tiny_topology(tiny_model):
+    r = run_parity(TINY, 2, 16, 16, model=tiny_model)
+    assert r["eps_mse"] < EPS_MSE_TOL and r["loss_rel"] < 5e-3
+    assert r["grad_flat_rel"] < 3e-2 and r["grad_worst_rel"] < 6e-2      # narrow random-weight net: noisier grads
+    assert r["this_idx"] == 0
+
+
+def test_unet_parity_ragged_shape(tiny_model):
+    r = run_parity(TINY, 1, 24, 8, model=tiny_model)                      # non-square, tiles with tails
+    assert r["eps_mse"] < EPS_MSE_TOL and r["grad_flat_rel"] < 3e-2
+
+
+def test_unet_parity_sd21_256px(sd_model):
+    """BASELINE config 1 shape (256^2 => 32x32 latents), full SD-2.1 widths."""
+    r = run_parity(SD21, 1, 32, 32, model=sd_model)
+    assert r["eps_mse"] < EPS_MSE_TOL and r["loss_rel"] < 2e-3
+    assert r["grad_flat_rel"] < GRAD_FLAT_TOL_SD21, r["grad_flat_rel"]
+    assert r["grad_worst_rel"] < 3e-2
+
+
+def test_unet_parity_sd21_no_bypass_keys(sd_model):
+    """dict without CONTEXT_TENSOR_BYPASS_i: V falls back to the K context (xti_attention_processor.py:39-42)."""
+    r = run_parity(SD21, 1, 16, 16, bypass=False, model=sd_model)
+    assert r["eps_mse"] < EPS_MSE_TOL and r["grad_flat_rel"] < GRAD_FLAT_TOL_SD21 * 1.5
+
+
+def _run(model, lat, t, ehs, tgt):
+    pred = model(lat, t, ehs).sample
+    loss = F.mse_loss(pred.float(), tgt.float())
+    loss.backward()
+    return pred.detach()
+
+
+def test_plain_tensor_context_equals_dict_of_identical_entries(tiny_model):
+    lat, t, tgt, ctx = make_inputs(TINY, 1, 16, 16)
+    lat, t, tgt = lat.cuda(), t.cuda(), tgt.cuda()
+    c0 = ctx["CONTEXT_TENSOR_0"].cuda().requires_grad_(True)
+    a = _run(tiny_model, lat, t, c0, tgt)
+    ga = c0.grad.clone()
+    leaves = [ctx["CONTEXT_TENSOR_0"].cuda().requires_grad_(True) for _ in range(16)]
+    b = _run(tiny_model, lat, t, {"this_idx": 0, **{f"CONTEXT_TENSOR_{i}": leaves[i] for i in range(16)}}, tgt)
+    assert rel(a, b) < 1e-3
+    # the single tensor feeds K and V of all 16 layers: its gradient is the sum over the 16 per-layer gradients
+    assert rel(ga, sum(l.grad for l in leaves)) < 2e-3
+
+
+def test_this_idx_offset_binds_rotated_layers(tiny_model):
+    lat, t, tgt, ctx = make_inputs(TINY, 1, 16, 16)
+    lat, t, tgt = lat.cuda(), t.cuda(), tgt.cuda()
+    c = ctx_to(ctx, "cuda", requires_grad=False)
+    a = tiny_model(lat, t, c).sample
+    rot = {"this_idx": 5}
+    for i in range(16):
+        rot[f"CONTEXT_TENSOR_{(i + 5) % 16}"] = c[f"CONTEXT_TENSOR_{i}"]
+        rot[f"CONTEXT_TENSOR_BYPASS_{(i + 5) % 16}"] = c[f"CONTEXT_TENSOR_BYPASS_{i}"]
+    b = tiny_model(lat, t, rot).sample
+    assert rot["this_idx"] == 5 and rel(a, b) < 1e-3
+
+
+def test_graph_replay_matches_eager_and_guards_stale_backward(tiny_model):
+    from view_neti_b200._abi import VNError
+    lat, t, tgt, ctx = make_inputs(TINY, 1, 8, 8, seed=7)
+    lat, t, tgt = lat.cuda(), t.cuda(), tgt.cuda()
+    outs, grads = [], []
+    for _ in range(3):                       # call 1 eager, call 2 captures, call 3 replays
+        c = ctx_to(ctx, "cuda")
+        outs.append(_run(tiny_model, lat, t, c, tgt))
+        grads.append(c["CONTEXT_TENSOR_9"].grad.clone())
+    assert "fwd" in tiny_model.engine.plan(1, 8, 8).graphs and "bwd" in tiny_model.engine.plan(1, 8, 8).graphs
+    assert rel(outs[2], outs[0]) < 1e-3 and rel(grads[2], grads[0]) < 2e-3
+    c = ctx_to(ctx, "cuda")
+    p1 = tiny_model(lat, t, c).sample
+    tiny_model(lat, t, ctx_to(ctx, "cuda", requires_grad=False))
+    with pytest.raises((VNError, RuntimeError)):
+        p1.sum().backward()
+
+
+def test_backward_is_linear_in_d_eps_at_full_size(sd_model):
+    """Size-independent property at the BASELINE shape (64x64 latents): the dgrad backward is linear, and scaling
+    by a power of two is exact in bf16/fp32, so d_ctx(2 g) == 2 d_ctx(g) up to atomic summation order."""
+    plan = sd_model.engine.plan(1, 64, 64)
+    lat, t, tgt, ctx = make_inputs(SD21, 1, 64, 64, seed=3)
+    plan.latents.copy_(lat); plan.timesteps.copy_(t)
+    for i in range(16):
+        plan.ctx[0, i].copy_(ctx[f"CONTEXT_TENSOR_{i}"]); plan.ctx[1, i].copy_(ctx[f"CONTEXT_TENSOR_BYPASS_{i}"])
+    eps = plan.forward().clone()
+    assert torch.isfinite(eps).all() and 0.2 < float(eps.std()) < 5.0
+    g = torch.randn_like(eps) * 1e-3
+    plan.d_eps.copy_(g); d1 = plan.backward().clone()
+    plan.d_eps.copy_(2 * g); d2 = plan.backward().clone()
+    assert torch.isfinite(d1).all() and float(d1.abs().max()) > 0
+    assert rel(d2, 2 * d1) < 2e-3
+    plan.d_eps.zero_()
+    assert float(plan.backward().abs().max()) == 0.0
+
+
+def test_xti_atten_proc_matches_reference_golden():
+    """Our XTIAttenProc (CUDA kernels) on the module the reference's own processor was run on (tests/golden)."""
+    from oracle.unet_sd21 import CrossAttention
+    from view_neti_b200.models.xti_attention_processor import XTIAttenProc
+    gold = torch.load(GOLD)
+
+    def mod(state, cdim):
+        m = CrossAttention(128, cdim, gold["heads"])
+        m.load_state_dict(state)
+        m.processor = XTIAttenProc()
+        return m.cuda()
+
+    cross, selfa = mod(gold["cross_state"], 192), mod(gold["self_state"], None)
+    h = gold["hidden"].cuda()
+    ctx = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in gold["ctx"].items()}
+    with torch.no_grad():
+        d = dict(ctx)
+        assert rel(cross(h, encoder_hidden_states=d), gold["dict_bypass"]) < 1e-2
+        assert d["this_idx"] == 4
+        d = {k: v for k, v in ctx.items() if "BYPASS" not in k}
+        d["this_idx"] = 15
+        assert rel(cross(h, encoder_hidden_states=d), gold["dict_nobypass_idx15"]) < 1e-2 and d["this_idx"] == 0
+        assert rel(cross(h, encoder_hidden_states=ctx["CONTEXT_TENSOR_5"]), gold["tensor_ctx"]) < 1e-2
+        assert rel(selfa(h, encoder_hidden_states=None), gold["self"]) < 1e-2
+    d = {k: (v.clone().requires_grad_(True) if torch.is_tensor(v) else v) for k, v in ctx.items()}
+    hh = h.clone().requires_grad_(True)
+    y = cross(hh, encoder_hidden_states=d)
+    (y * gold["grad_w"].cuda()).sum().backward()
+    assert rel(d["CONTEXT_TENSOR_3"].grad, gold["grad_ctx_k"]) < 2e-2
+    assert rel(d["CONTEXT_TENSOR_BYPASS_3"].grad, gold["grad_ctx_v"]) < 2e-2
+    assert rel(hh.grad, gold["grad_hidden"]) < 2e-2
+
+
+def test_sd_pipeline_call_matches_oracle_loop(tiny_model):
+    """sd_pipeline_call.py:71-101 — batched CFG + fused DDIM step against the oracle's two-pass loop."""
+    import numpy as np
+    from oracle import schedulers as O
+    from oracle.unet_sd21 import UNetOracle
+    from view_neti_b200.schedulers import DDIMScheduler
+    from view_neti_b200.sd_pipeline_call import ViewNeTIPipeline, sd_pipeline_call
+    steps, gs = 4, 7.5
+    g = torch.Generator().manual_seed(11)
+    x0 = torch.randn(1, 4, 16, 16, generator=g)
+    neg = torch.randn(1, 77, TINY.cross_attention_dim, generator=g)
+    embeds = []
+    for _ in range(steps):
+        d = {"this_idx": 0}
+        for i in range(16):
+            d[f"CONTEXT_TENSOR_{i}"] = torch.randn(1, 77, TINY.cross_attention_dim, generator=g)
+            d[f"CONTEXT_TENSOR_BYPASS_{i}"] = torch.randn(1, 77, TINY.cross_attention_dim, generator=g)
+        embeds.append(d)
+    unet = UNetOracle(TINY)
+    unet.load_state_dict(init_state_dict(TINY, 0))
+    x = x0.clone()
+    with torch.no_grad():
+        for i, t in enumerate(O.ddim_timesteps(steps)):
+            u = unet(x, int(t), neg).sample
+            c = unet(x, int(t), dict(embeds[i])).sample
+            e = u + gs * (c - u)
+            x = torch.from_numpy(O.ddim_step(e.double().numpy(), int(t), x.double().numpy(), steps)).float()
+    pipe = ViewNeTIPipeline(tiny_model, DDIMScheduler("v_prediction"), negative_prompt_embeds=neg.cuda())
+    cuda_embeds = [{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in d.items()} for d in embeds]
+    seen = []
+    out = sd_pipeline_call(pipe, cuda_embeds, height=128, width=128, num_inference_steps=steps, guidance_scale=gs,
+                           latents=x0.cuda(), output_type="latent", callback=lambda i, t, l: seen.append((i, t)))
+    assert [t for _, t in seen] == [int(t) for t in O.ddim_timesteps(steps)]
+    assert rel(out.images, x) < 5e-2                                   # CFG (x7.5) amplifies the bf16 error of eps
+    assert np.isfinite(out.images.cpu().numpy()).all()
+
+
+def test_coach_step_trains_the_conditioning(tiny_model):
+    from types import SimpleNamespace
+    from view_neti_b200.schedulers import DDPMScheduler
+    from view_neti_b200.training.coach import Coach, SyntheticConditioning
+    cond = SyntheticConditioning(dim=TINY.cross_attention_dim, rank=4).cuda()
+    before = cond.base.detach().clone()
+    coach = Coach(SimpleNamespace(optim=SimpleNamespace(learning_rate=1e-2, max_train_steps=3)), tiny_model, cond,
+                  DDPMScheduler("v_prediction"), generator=torch.Generator(device="cuda").manual_seed(0))
+    lat = torch.randn(2, 4, 16, 16, device="cuda")
+    losses = coach.train([lat] * 5)
+    assert len(losses) == 3 and all(torch.isfinite(l) for l in losses)
+    assert float((cond.base.detach() - before).abs().max()) > 0
