@@ -72,18 +72,19 @@ int    vn_gemm(const vn_gemm_desc* d, vn_stream_t stream);
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (+ optional SiLU) over NHWC bf16 [nb, hw, C] — diffusers ResnetBlock2D.norm1/norm2,
  * Transformer2DModel.norm, conv_norm_out (torch native_group_norm + silu).
- * stats/red: fp32 [nb, groups, 2]; must be zero on entry of *_stats (they accumulate with atomics).
+ * stats/red: fp64 [nb, groups, 2]; must be zero on entry of *_stats (they accumulate with atomics; fp64 keeps the
+ * result independent of the accumulation order, i.e. reproducible run to run).
  *   fwd stats = (sum x, sum x^2);  bwd red = (sum dxhat, sum dxhat*xhat)
  * ------------------------------------------------------------------------------------------------ */
-int vn_groupnorm_stats(const void* x, int64_t ldx, int nb, int hw, int C, int groups, float* stats, vn_stream_t s);
-int vn_groupnorm_apply(const void* x, int64_t ldx, const float* stats, const float* gamma, const float* beta,
+int vn_groupnorm_stats(const void* x, int64_t ldx, int nb, int hw, int C, int groups, double* stats, vn_stream_t s);
+int vn_groupnorm_apply(const void* x, int64_t ldx, const double* stats, const float* gamma, const float* beta,
                        float eps, int silu, void* y, int64_t ldy, int nb, int hw, int C, int groups, vn_stream_t s);
-int vn_groupnorm_bwd_stats(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* stats,
-                           const float* gamma, const float* beta, float eps, int silu, float* red,
+int vn_groupnorm_bwd_stats(const void* x, int64_t ldx, const void* dy, int64_t lddy, const double* stats,
+                           const float* gamma, const float* beta, float eps, int silu, double* red,
                            int nb, int hw, int C, int groups, vn_stream_t s);
 /* dx = GN^T(dy) (+ add1) (+ add2) */
-int vn_groupnorm_bwd_apply(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* stats,
-                           const float* red, const float* gamma, const float* beta, float eps, int silu,
+int vn_groupnorm_bwd_apply(const void* x, int64_t ldx, const void* dy, int64_t lddy, const double* stats,
+                           const double* red, const float* gamma, const float* beta, float eps, int silu,
                            const void* add1, int64_t ldadd1, const void* add2, int64_t ldadd2,
                            void* dx, int64_t lddx, int nb, int hw, int C, int groups, vn_stream_t s);
 
@@ -107,8 +108,9 @@ int vn_geglu_bwd(const void* h, int64_t ldh, const void* dy, int64_t lddy, void*
  * so head split/merge copies disappear.  K and V come from DIFFERENT tensors (XTI: K from
  * CONTEXT_TENSOR_i, V from CONTEXT_TENSOR_BYPASS_i).  lse: fp32 [nb, heads, nq] (natural log), delta same shape.
  * fwd: one flash kernel (logits never leave the SM).
- * bwd: dq, dk, dv.  dk/dv may be accumulated in fp32 scratch `dkv_acc` ([2, nb, nk, heads*64] fp32, zero on
- * entry, left zero) when nk is too small to parallelise over keys (cross-attention, nk = 77).
+ * bwd: dq, dk, dv.  dk/dv may be accumulated in fp64 scratch `dkv_acc` ([2, nb, nk, heads*64] fp64, zero on
+ * entry, left zero) when nk is too small to parallelise over keys (cross-attention, nk = 77); fp64 keeps the sum
+ * independent of the order in which the query splits arrive.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct vn_attn_desc {
   int32_t nb, heads, nq, nk;
@@ -124,7 +126,7 @@ typedef struct vn_attn_desc {
   void* dq; int64_t lddq, bsdq;           /* may be NULL (pruned) */
   void* dk; int64_t lddk, bsdk;
   void* dv; int64_t lddv, bsdv;
-  float* dkv_acc;                         /* NULL or zeroed scratch, see above */
+  double* dkv_acc;                        /* NULL or zeroed scratch, see above */
 } vn_attn_desc;
 int vn_attention_fwd(const vn_attn_desc* d, vn_stream_t s);
 int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s);

@@ -108,7 +108,7 @@ def check_conv(nb, H, W, Cc, N, bias=True, rowbias=False, resid=False, force_bn=
 def check_groupnorm(nb, hw, Cc, silu, eps=1e-5, groups=32):
     x = (rnd(nb, hw, Cc, seed=12) * 1.5 + 0.3).to(BF)
     gamma, beta = 1 + 0.1 * rnd(Cc, seed=13), 0.1 * rnd(Cc, seed=14)
-    stats = torch.zeros(nb, groups, 2, device=DEV)
+    stats = torch.zeros(nb, groups, 2, device=DEV, dtype=torch.float64)
     y = torch.empty_like(x)
     ops.groupnorm_stats(x, nb, hw, groups, stats)
     ops.groupnorm_apply(x, stats, gamma, beta, eps, silu, y, nb, hw, groups)
@@ -118,7 +118,7 @@ def check_groupnorm(nb, hw, Cc, silu, eps=1e-5, groups=32):
         yr = F.silu(yr)
     dy = rnd(nb, hw, Cc, seed=15).to(BF)
     yr.backward(dy.float().permute(0, 2, 1))
-    red = torch.zeros(nb, groups, 2, device=DEV)
+    red = torch.zeros(nb, groups, 2, device=DEV, dtype=torch.float64)
     add1 = rnd(nb, hw, Cc, seed=16).to(BF)
     dx = torch.empty_like(x)
     ops.groupnorm_bwd(x, dy, stats, red, gamma, beta, eps, silu, dx, nb, hw, groups, add1=add1)

@@ -123,7 +123,7 @@ struct AttnParams {
   bf16* dq; long long lddq, bsdq;
   bf16* dk; long long lddk, bsdk;
   bf16* dv; long long lddv, bsdv;
-  float* dkv_acc;
+  double* dkv_acc;
   int qsplits, qtiles_per_split;
 };
 
@@ -439,17 +439,17 @@ __global__ void __launch_bounds__(DKV_THREADS) attn_bwd_dkv_kernel(const AttnPar
   const int col = h * D + 2 * (lane & 3);
   if (ATOMIC) {
     const long long C = (long long)p.heads * D;
-    float* ak = p.dkv_acc + ((long long)b * p.nk) * C;
-    float* av = p.dkv_acc + ((long long)p.nb * p.nk) * C + ((long long)b * p.nk) * C;
+    double* ak = p.dkv_acc + ((long long)b * p.nk) * C;
+    double* av = p.dkv_acc + ((long long)p.nb * p.nk) * C + ((long long)b * p.nk) * C;
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       if (row0 < p.nk) {
-        atomicAdd(ak + row0 * C + col + t * 8, dk[t][0]); atomicAdd(ak + row0 * C + col + t * 8 + 1, dk[t][1]);
-        atomicAdd(av + row0 * C + col + t * 8, dv[t][0]); atomicAdd(av + row0 * C + col + t * 8 + 1, dv[t][1]);
+        atomicAdd(ak + row0 * C + col + t * 8, (double)dk[t][0]); atomicAdd(ak + row0 * C + col + t * 8 + 1, (double)dk[t][1]);
+        atomicAdd(av + row0 * C + col + t * 8, (double)dv[t][0]); atomicAdd(av + row0 * C + col + t * 8 + 1, (double)dv[t][1]);
       }
       if (row1 < p.nk) {
-        atomicAdd(ak + row1 * C + col + t * 8, dk[t][2]); atomicAdd(ak + row1 * C + col + t * 8 + 1, dk[t][3]);
-        atomicAdd(av + row1 * C + col + t * 8, dv[t][2]); atomicAdd(av + row1 * C + col + t * 8 + 1, dv[t][3]);
+        atomicAdd(ak + row1 * C + col + t * 8, (double)dk[t][2]); atomicAdd(ak + row1 * C + col + t * 8 + 1, (double)dk[t][3]);
+        atomicAdd(av + row1 * C + col + t * 8, (double)dv[t][2]); atomicAdd(av + row1 * C + col + t * 8 + 1, (double)dv[t][3]);
       }
     }
   } else {
@@ -479,13 +479,13 @@ __global__ void __launch_bounds__(256) attn_dkv_finish_kernel(const AttnParams p
     const int c = (int)(e % C);
     const long long r = e / C;
     const int n = (int)(r % p.nk), b = (int)(r / p.nk);
-    float2* ak = reinterpret_cast<float2*>(p.dkv_acc + e);
-    float2* av = reinterpret_cast<float2*>(p.dkv_acc + per + e);
-    const float2 a = *ak, v = *av;
-    *reinterpret_cast<bf162*>(p.dk + (long long)b * p.bsdk + (long long)n * p.lddk + c) = __floats2bfloat162_rn(a.x, a.y);
-    *reinterpret_cast<bf162*>(p.dv + (long long)b * p.bsdv + (long long)n * p.lddv + c) = __floats2bfloat162_rn(v.x, v.y);
-    *ak = make_float2(0.f, 0.f);
-    *av = make_float2(0.f, 0.f);
+    double2* ak = reinterpret_cast<double2*>(p.dkv_acc + e);
+    double2* av = reinterpret_cast<double2*>(p.dkv_acc + per + e);
+    const double2 a = *ak, v = *av;
+    *reinterpret_cast<bf162*>(p.dk + (long long)b * p.bsdk + (long long)n * p.lddk + c) = __floats2bfloat162_rn((float)a.x, (float)a.y);
+    *reinterpret_cast<bf162*>(p.dv + (long long)b * p.bsdv + (long long)n * p.lddv + c) = __floats2bfloat162_rn((float)v.x, (float)v.y);
+    *ak = make_double2(0.0, 0.0);
+    *av = make_double2(0.0, 0.0);
   }
 }
 

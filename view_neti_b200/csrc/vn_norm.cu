@@ -54,12 +54,14 @@ GNGeom gn_geom(int nb, int hw, int C) {
 template <int MODE>
 __global__ void __launch_bounds__(512) gn_reduce_kernel(const bf16* __restrict__ x, long long ldx,
                                                          const bf16* __restrict__ dy, long long lddy,
-                                                         const float* __restrict__ stats,
+                                                         const double* __restrict__ stats,
                                                          const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float eps, int silu,
-                                                         float* __restrict__ out, int hw, int C, int groups, int k,
+                                                         double* __restrict__ out, int hw, int C, int groups, int k,
                                                          int ppc) {
-  __shared__ float s_acc[kMaxGroups][2];
+  // Per-thread partial sums are fp32 in a fixed order; everything that is combined in a scheduling-dependent order
+  // (threads of a CTA, CTAs of the grid) is accumulated in fp64, so the statistics are reproducible run to run.
+  __shared__ double s_acc[kMaxGroups][2];
   const int b = blockIdx.y;
   const int cpg = C / groups;
   const int vecs = C >> 3;
@@ -67,17 +69,17 @@ __global__ void __launch_bounds__(512) gn_reduce_kernel(const bf16* __restrict__
   const int c0 = v * 8;
   const int p0 = blockIdx.x * ppc;
   const int p1 = min(hw, p0 + ppc);
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) { s_acc[g][0] = 0.f; s_acc[g][1] = 0.f; }
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) { s_acc[g][0] = 0.0; s_acc[g][1] = 0.0; }
   float ga[8], be[8], mean[8], rstd[8];
   if (MODE == 1) {
-    const float n = (float)cpg * (float)hw;
+    const double n = (double)cpg * (double)hw;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       ga[j] = gamma[c0 + j]; be[j] = beta[c0 + j];
       const int g = (c0 + j) / cpg;
-      const float m = stats[(b * groups + g) * 2] / n;
-      const float var = fmaxf(stats[(b * groups + g) * 2 + 1] / n - m * m, 0.f);
-      mean[j] = m; rstd[j] = rsqrtf(var + eps);
+      const double m = stats[(b * groups + g) * 2] / n;
+      const double var = fmax(stats[(b * groups + g) * 2 + 1] / n - m * m, 0.0);
+      mean[j] = (float)m; rstd[j] = (float)(1.0 / sqrt(var + (double)eps));
     }
   }
   __syncthreads();
@@ -141,12 +143,12 @@ __global__ void __launch_bounds__(512) gn_reduce_kernel(const bf16* __restrict__
   for (int j = 0; j < 8; ++j) {
     const int g = (c0 + j) / cpg;
     if (g != gprev) {
-      atomicAdd(&s_acc[gprev][0], s0); atomicAdd(&s_acc[gprev][1], s1);
+      atomicAdd(&s_acc[gprev][0], (double)s0); atomicAdd(&s_acc[gprev][1], (double)s1);
       s0 = 0.f; s1 = 0.f; gprev = g;
     }
     s0 += a0[j]; s1 += a1[j];
   }
-  atomicAdd(&s_acc[gprev][0], s0); atomicAdd(&s_acc[gprev][1], s1);
+  atomicAdd(&s_acc[gprev][0], (double)s0); atomicAdd(&s_acc[gprev][1], (double)s1);
   __syncthreads();
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     atomicAdd(&out[(b * groups + g) * 2], s_acc[g][0]);
@@ -158,8 +160,8 @@ __global__ void __launch_bounds__(512) gn_reduce_kernel(const bf16* __restrict__
 template <int MODE>
 __global__ void __launch_bounds__(512) gn_apply_kernel(const bf16* __restrict__ x, long long ldx,
                                                         const bf16* __restrict__ dy, long long lddy,
-                                                        const float* __restrict__ stats,
-                                                        const float* __restrict__ red,
+                                                        const double* __restrict__ stats,
+                                                        const double* __restrict__ red,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, int silu,
                                                         const bf16* __restrict__ add1, long long ld1,
@@ -173,24 +175,25 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const bf16* __restrict__ 
   const int c0 = v * 8;
   const int p0 = blockIdx.x * ppc;
   const int p1 = min(hw, p0 + ppc);
-  const float n = (float)cpg * (float)hw;
+  const double n = (double)cpg * (double)hw;
   // per-channel constants:  fwd  y = x*A + B            (A = gamma*rstd, B = beta - mean*A)
   //                         bwd  xh = x*R + M (R = rstd, M = -mean*rstd), z = xh*G + Bt, dx = R*(dz*G - S1 - xh*S2)
   float A[8], Bc[8], G[8], S1[8], S2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int g = (c0 + j) / cpg;
-    const float m = stats[(b * groups + g) * 2] / n;
-    const float var = fmaxf(stats[(b * groups + g) * 2 + 1] / n - m * m, 0.f);
-    const float rs = rsqrtf(var + eps);
+    const double md = stats[(b * groups + g) * 2] / n;
+    const double var = fmax(stats[(b * groups + g) * 2 + 1] / n - md * md, 0.0);
+    const float rs = (float)(1.0 / sqrt(var + (double)eps));
+    const float m = (float)md;
     if (MODE == 0) {
       A[j] = gamma[c0 + j] * rs;
       Bc[j] = beta[c0 + j] - m * A[j];
     } else {
       A[j] = rs; Bc[j] = -m * rs;
       G[j] = gamma[c0 + j];
-      S1[j] = red[(b * groups + g) * 2] / n;
-      S2[j] = red[(b * groups + g) * 2 + 1] / n;
+      S1[j] = (float)(red[(b * groups + g) * 2] / n);
+      S2[j] = (float)(red[(b * groups + g) * 2 + 1] / n);
     }
   }
   float Bt[8];
@@ -459,7 +462,7 @@ int ln_launch(const bf16* x, long long ldx, const bf16* dy, long long lddy, cons
 
 }  // namespace
 
-extern "C" int vn_groupnorm_stats(const void* x, int64_t ldx, int nb, int hw, int C, int groups, float* stats,
+extern "C" int vn_groupnorm_stats(const void* x, int64_t ldx, int nb, int hw, int C, int groups, double* stats,
                                   vn_stream_t s) {
   if (gn_check(C, groups, ldx)) return -1;
   const GNGeom g = gn_geom(nb, hw, C);
@@ -470,7 +473,7 @@ extern "C" int vn_groupnorm_stats(const void* x, int64_t ldx, int nb, int hw, in
   return 0;
 }
 
-extern "C" int vn_groupnorm_apply(const void* x, int64_t ldx, const float* stats, const float* gamma,
+extern "C" int vn_groupnorm_apply(const void* x, int64_t ldx, const double* stats, const float* gamma,
                                   const float* beta, float eps, int silu, void* y, int64_t ldy, int nb, int hw, int C,
                                   int groups, vn_stream_t s) {
   if (gn_check(C, groups, ldx)) return -1;
@@ -484,8 +487,8 @@ extern "C" int vn_groupnorm_apply(const void* x, int64_t ldx, const float* stats
   return 0;
 }
 
-extern "C" int vn_groupnorm_bwd_stats(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* stats,
-                                      const float* gamma, const float* beta, float eps, int silu, float* red, int nb,
+extern "C" int vn_groupnorm_bwd_stats(const void* x, int64_t ldx, const void* dy, int64_t lddy, const double* stats,
+                                      const float* gamma, const float* beta, float eps, int silu, double* red, int nb,
                                       int hw, int C, int groups, vn_stream_t s) {
   if (gn_check(C, groups, ldx)) return -1;
   VN_CHECK(lddy % 8 == 0, "groupnorm bwd: strides must be multiples of 8");
@@ -497,8 +500,8 @@ extern "C" int vn_groupnorm_bwd_stats(const void* x, int64_t ldx, const void* dy
   return 0;
 }
 
-extern "C" int vn_groupnorm_bwd_apply(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* stats,
-                                      const float* red, const float* gamma, const float* beta, float eps, int silu,
+extern "C" int vn_groupnorm_bwd_apply(const void* x, int64_t ldx, const void* dy, int64_t lddy, const double* stats,
+                                      const double* red, const float* gamma, const float* beta, float eps, int silu,
                                       const void* add1, int64_t ldadd1, const void* add2, int64_t ldadd2, void* dx,
                                       int64_t lddx, int nb, int hw, int C, int groups, vn_stream_t s) {
   if (gn_check(C, groups, ldx)) return -1;

@@ -180,8 +180,8 @@ class _Plan:
         self.target = self.buf("in.target", (nb, cfg.out_channels, h, w), F32)
         self.loss = self.buf("out.loss", (1,), F32)
         n_gn = 2 * (len(eng.res)) + len(eng.xf) + 1
-        self.stat_f = self.buf("gn.stats", (n_gn, nb, cfg.norm_num_groups, 2), F32)     # (sum x, sum x^2)
-        self.stat_b = self.buf("gn.red", (n_gn, nb, cfg.norm_num_groups, 2), F32)       # backward reductions
+        self.stat_f = self.buf("gn.stats", (n_gn, nb, cfg.norm_num_groups, 2), torch.float64)     # (sum x, sum x^2)
+        self.stat_b = self.buf("gn.red", (n_gn, nb, cfg.norm_num_groups, 2), torch.float64)       # backward reductions
         self._stat_slots: Dict[str, int] = {}
         self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self.launches: Dict[str, int] = {}

@@ -72,7 +72,7 @@ class _XTIAttnFn(torch.autograd.Function):
         ops.gemm(dob, W["ob"], d_o)
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         delta = torch.empty(B, heads, N, dtype=torch.float32, device=dev)
-        acc = torch.zeros(2 * B * L * inner, dtype=torch.float32, device=dev) if L < 256 else None
+        acc = torch.zeros(2 * B * L * inner, dtype=torch.float64, device=dev) if L < 256 else None
         ops.attention_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, heads, ctx.scale, dkv_acc=acc)
         d_hidden = torch.empty(B, N, W["qb"].shape[0], dtype=torch.float32, device=dev)
         ops.gemm(dq, W["qb"], d_hidden)

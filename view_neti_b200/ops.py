@@ -29,6 +29,19 @@ def _ld(t: torch.Tensor) -> int:
     return ld
 
 
+def _pix_ld(x: torch.Tensor) -> int:
+    """Pixel stride (elements) of an NHWC view [nb,H,W,C] whose pixels are evenly strided; size-1 dims carry no
+    stride information in torch, so they are skipped."""
+    nb, H, W, Cc = x.shape
+    assert x.stride(3) == 1
+    ld = x.stride(2) if W > 1 else (x.stride(1) if H > 1 else (x.stride(0) if nb > 1 else Cc))
+    if W > 1 and H > 1:
+        assert x.stride(1) == W * ld, f"rows of the NHWC view are not evenly strided: {tuple(x.shape)} {x.stride()}"
+    if nb > 1 and H * W > 1:
+        assert x.stride(0) == H * W * ld, f"images of the NHWC view are not evenly strided: {tuple(x.shape)} {x.stride()}"
+    return ld
+
+
 class Workspace:
     """Split-K scratch for vn_gemm (zero on entry, left zero by every call) + fp32 dK/dV accumulator."""
 
@@ -36,7 +49,7 @@ class Workspace:
         lib = _abi.load()
         self.bytes = int(lib.vn_gemm_workspace_bytes(max_m, max_n))
         self.buf = torch.zeros(self.bytes, dtype=torch.uint8, device=device)
-        self.dkv = torch.zeros(max(dkv_elems, 1), dtype=torch.float32, device=device)
+        self.dkv = torch.zeros(max(dkv_elems, 1), dtype=torch.float64, device=device)
 
 
 def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, bias=None, rowbias=None, rows_per_batch: int = 0,
@@ -71,21 +84,20 @@ def conv3x3(x: torch.Tensor, Wk: torch.Tensor, D: torch.Tensor, *, bias=None, ro
     lib = _abi.load()
     nb, H, W, Cc = x.shape
     N = Wk.shape[0]
-    assert Wk.shape[1] == 9 * Cc and x.stride(3) == 1
-    assert x.stride(1) == W * x.stride(2) and (nb == 1 or x.stride(0) == H * x.stride(1))
+    assert Wk.shape[1] == 9 * Cc
     d = GemmDesc()
     d.mode = 1
     d.M, d.N, d.K = nb * H * W, N, 9 * Cc
     d.nb, d.H, d.W, d.C = nb, H, W, Cc
-    d.A, d.lda = ptr(x), x.stride(2)
+    d.A, d.lda = ptr(x), _pix_ld(x)
     d.B, d.ldb = ptr(Wk), Wk.stride(0)
-    d.D, d.ldd = ptr(D), D.stride(-2)
+    d.D, d.ldd = ptr(D), _pix_ld(D)
     d.out_fp32 = 1 if D.dtype == torch.float32 else 0
     d.bias = ptr(bias)
     if rowbias is not None:
         d.rowbias, d.ld_rowbias, d.rows_per_batch = ptr(rowbias), rowbias.stride(0), H * W
     if R is not None:
-        d.R, d.ldr = ptr(R), R.stride(-2)
+        d.R, d.ldr = ptr(R), _pix_ld(R)
     if ws is not None:
         d.workspace, d.workspace_bytes = ptr(ws.buf), ws.bytes
     d.force_bn, d.force_split = force_bn, force_split
@@ -167,41 +179,41 @@ def attention_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, heads, scale=0.125, d
 # ---- resampling / edge convs / glue -------------------------------------------------------------
 def upsample2x_fwd(x, y):
     nb, H, W, Cc = x.shape
-    check(_abi.load().vn_upsample2x_fwd(ptr(x), x.stride(2), ptr(y), y.stride(2), nb, H, W, Cc, stream()), "upsample")
+    check(_abi.load().vn_upsample2x_fwd(ptr(x), _pix_ld(x), ptr(y), _pix_ld(y), nb, H, W, Cc, stream()), "upsample")
 
 
 def upsample2x_bwd(dy, dx):
     nb, H, W, Cc = dx.shape
-    check(_abi.load().vn_upsample2x_bwd(ptr(dy), dy.stride(2), ptr(dx), dx.stride(2), nb, H, W, Cc, stream()),
+    check(_abi.load().vn_upsample2x_bwd(ptr(dy), _pix_ld(dy), ptr(dx), _pix_ld(dx), nb, H, W, Cc, stream()),
           "upsample_bwd")
 
 
 def im2col_s2(x, col):
     nb, H, W, Cc = x.shape
-    check(_abi.load().vn_im2col_s2(ptr(x), x.stride(2), ptr(col), nb, H, W, Cc, stream()), "im2col_s2")
+    check(_abi.load().vn_im2col_s2(ptr(x), _pix_ld(x), ptr(col), nb, H, W, Cc, stream()), "im2col_s2")
 
 
 def col2im_s2(dcol, dx, add=None):
     nb, H, W, Cc = dx.shape
-    check(_abi.load().vn_col2im_s2(ptr(dcol), ptr(add), add.stride(2) if add is not None else 0, ptr(dx), dx.stride(2),
+    check(_abi.load().vn_col2im_s2(ptr(dcol), ptr(add), _pix_ld(add) if add is not None else 0, ptr(dx), _pix_ld(dx),
                                    nb, H, W, Cc, stream()), "col2im_s2")
 
 
 def conv_in_fwd(x, w, bias, y):
     nb, Cin, H, W = x.shape
-    check(_abi.load().vn_conv_in_fwd(ptr(x), ptr(w), ptr(bias), ptr(y), y.stride(2), nb, Cin, H, W, y.shape[-1],
+    check(_abi.load().vn_conv_in_fwd(ptr(x), ptr(w), ptr(bias), ptr(y), _pix_ld(y), nb, Cin, H, W, y.shape[-1],
                                      stream()), "conv_in")
 
 
 def conv_out_fwd(x, w, bias, y):
     nb, H, W, Cin = x.shape
-    check(_abi.load().vn_conv_out_fwd(ptr(x), x.stride(2), ptr(w), ptr(bias), ptr(y), nb, Cin, H, W, y.shape[1],
+    check(_abi.load().vn_conv_out_fwd(ptr(x), _pix_ld(x), ptr(w), ptr(bias), ptr(y), nb, Cin, H, W, y.shape[1],
                                       stream()), "conv_out")
 
 
 def conv_out_bwd(dy, w, dx):
     nb, Cout, H, W = dy.shape
-    check(_abi.load().vn_conv_out_bwd(ptr(dy), ptr(w), ptr(dx), dx.stride(2), nb, dx.shape[-1], H, W, Cout, stream()),
+    check(_abi.load().vn_conv_out_bwd(ptr(dy), ptr(w), ptr(dx), _pix_ld(dx), nb, dx.shape[-1], H, W, Cout, stream()),
           "conv_out_bwd")
 
 
