@@ -8,10 +8,9 @@
 // Data layout: token-major, heads side by side: element (b, n, h, d) at base + b*bs + n*ld + h*64 + d, so the
 // head split / merge copies of the reference do not exist.  bf16 operands, fp32 logits / softmax / accumulators.
 //
-// v1 engine: warp-level mma.sync m16n8k16 (bf16 -> fp32) with ldmatrix from XOR-swizzled shared memory and a
-// cp.async double buffer.  (The tcgen05 / TMEM version of the self-attention core is the planned replacement.)
-//   fwd   : CTA = 128 queries x 8 warps, loops over 64-key tiles, online softmax in registers.
-//   bwd dQ: same tiling; recomputes P from the saved log-sum-exp.
+// This file holds the BACKWARD (the forward is the tcgen05 / TMEM kernel in vn_attn_tc.cu): warp-level mma.sync
+// m16n8k16 (bf16 -> fp32) with ldmatrix from XOR-swizzled shared memory and a cp.async double buffer.
+//   bwd dQ: CTA = 128 queries x 8 warps, loops over 64-key tiles; recomputes P from the saved log-sum-exp.
 //   bwd dK/dV: CTA = 64 keys x 4 warps, loops over 64-query tiles; optional split over the query range with fp32
 //           atomics into a scratch accumulator when nk is tiny (cross-attention: nk = 77).
 #include "vn_common.cuh"
@@ -127,122 +126,46 @@ struct AttnParams {
   int qsplits, qtiles_per_split;
 };
 
-// =================================================================================================
-// forward
-// =================================================================================================
+// tile geometry shared by the backward kernels (the forward lives in vn_attn_tc.cu)
 constexpr int FWD_THREADS = 256;
 constexpr int FWD_BM = 128;
 constexpr int BN = 64;
-constexpr int FWD_SMEM = FWD_BM * ROWB + 2 * 2 * BN * ROWB;   // Q + 2 stages x (K, V) = 48 KB
-
-__global__ void __launch_bounds__(FWD_THREADS) attn_fwd_kernel(const AttnParams p) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  const uint32_t sQ = smem_u32(smem_raw);
-  const uint32_t sKV = sQ + FWD_BM * ROWB;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int q0 = blockIdx.x * FWD_BM, h = blockIdx.y, b = blockIdx.z;
-  const bf16* gq = p.q + (long long)b * p.bsq + h * D;
-  const bf16* gk = p.k + (long long)b * p.bsk + h * D;
-  const bf16* gv = p.v + (long long)b * p.bsv + h * D;
-  const int ntiles = (p.nk + BN - 1) / BN;
-
-  load_tile<FWD_BM, FWD_THREADS>(sQ, gq, p.ldq, q0, p.nq);
-  load_tile<BN, FWD_THREADS>(sKV, gk, p.ldk, 0, p.nk);
-  load_tile<BN, FWD_THREADS>(sKV + BN * ROWB, gv, p.ldv, 0, p.nk);
-  cp_async_commit();
-
-  uint32_t qf[4][4];
-  float o[8][4];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // rows g and g+8, in scaled-log2 units
-  const float sl2 = p.scale * kLog2e;
-
-  for (int j = 0; j < ntiles; ++j) {
-    if (j + 1 < ntiles) {
-      const uint32_t nb_ = sKV + ((j + 1) & 1) * 2 * BN * ROWB;
-      load_tile<BN, FWD_THREADS>(nb_, gk, p.ldk, (j + 1) * BN, p.nk);
-      load_tile<BN, FWD_THREADS>(nb_ + BN * ROWB, gv, p.ldv, (j + 1) * BN, p.nk);
-    }
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    if (j == 0) load_a_frags(qf, sQ, warp * 16, lane);
-    const uint32_t sK = sKV + (j & 1) * 2 * BN * ROWB;
-    const uint32_t sV = sK + BN * ROWB;
-
-    float s[8][4];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) { s[t][0] = s[t][1] = s[t][2] = s[t][3] = 0.f; }
-    mma_nt(s, qf, sK, lane);
-
-    // mask keys beyond nk, running max
-    const int kbase = j * BN + 2 * (lane & 3);
-    float mx0 = m0, mx1 = m1;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int kc = kbase + t * 8;
-      if (kc >= p.nk) { s[t][0] = -INFINITY; s[t][2] = -INFINITY; }
-      if (kc + 1 >= p.nk) { s[t][1] = -INFINITY; s[t][3] = -INFINITY; }
-      s[t][0] *= sl2; s[t][1] *= sl2; s[t][2] *= sl2; s[t][3] *= sl2;
-      mx0 = fmaxf(mx0, fmaxf(s[t][0], s[t][1]));
-      mx1 = fmaxf(mx1, fmaxf(s[t][2], s[t][3]));
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float c0 = exp2f(m0 - mx0), c1 = exp2f(m1 - mx1);   // m = -inf on the first tile -> 0
-    m0 = mx0; m1 = mx1;
-    float r0 = 0.f, r1 = 0.f;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      s[t][0] = exp2f(s[t][0] - m0); s[t][1] = exp2f(s[t][1] - m0);
-      s[t][2] = exp2f(s[t][2] - m1); s[t][3] = exp2f(s[t][3] - m1);
-      r0 += s[t][0] + s[t][1];
-      r1 += s[t][2] + s[t][3];
-    }
-    l0 = l0 * c0 + r0; l1 = l1 * c1 + r1;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) { o[t][0] *= c0; o[t][1] *= c0; o[t][2] *= c1; o[t][3] *= c1; }
-    uint32_t pf[4][4];
-    c_to_a(pf, s);
-    mma_nn(o, pf, sV, lane);
-    __syncthreads();
-  }
-  cp_async_wait<0>();
-
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float i0 = 1.f / l0, i1 = 1.f / l1;
-  const int row0 = q0 + warp * 16 + (lane >> 2), row1 = row0 + 8;
-  bf16* go = p.o + (long long)b * p.bso + h * D + 2 * (lane & 3);
-#pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    if (row0 < p.nq) *reinterpret_cast<uint32_t*>(go + (long long)row0 * p.ldo + t * 8) = pack_bf162(o[t][0] * i0, o[t][1] * i0);
-    if (row1 < p.nq) *reinterpret_cast<uint32_t*>(go + (long long)row1 * p.ldo + t * 8) = pack_bf162(o[t][2] * i1, o[t][3] * i1);
-  }
-  if (p.lse && (lane & 3) == 0) {
-    float* gl = p.lse + ((long long)b * p.heads + h) * p.nq;
-    if (row0 < p.nq) gl[row0] = (m0 + log2f(l0)) / kLog2e;    // natural-log LSE of the scaled logits
-    if (row1 < p.nq) gl[row1] = (m1 + log2f(l1)) / kLog2e;
-  }
-}
 
 // =================================================================================================
 // backward: delta = rowsum(dO * O)
 // =================================================================================================
 __global__ void __launch_bounds__(256) attn_delta_kernel(const AttnParams p) {
-  const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);   // over nb * nq
-  if (row >= (long long)p.nb * p.nq) return;
-  const int b = (int)(row / p.nq), n = (int)(row % p.nq);
-  const bf16* go = p.o + (long long)b * p.bso + (long long)n * p.ldo;
-  const bf16* gd = p.d_o + (long long)b * p.bsdo + (long long)n * p.lddo;
-  for (int h = 0; h < p.heads; ++h) {
-    const float2 a = __bfloat1622float2(*reinterpret_cast<const bf162*>(go + h * D + 2 * lane));
-    const float2 c = __bfloat1622float2(*reinterpret_cast<const bf162*>(gd + h * D + 2 * lane));
-    const float s = warp_sum(a.x * c.x + a.y * c.y);
-    if (lane == 0) p.delta[((long long)b * p.heads + h) * p.nq + n] = s;
+  // one 16-byte vector per lane: 8 lanes cover one (row, head) = 64 elements, a warp covers 4 consecutive (row, head)
+  const int C = p.heads * D;
+  const long long nvec = (long long)p.nb * p.nq * p.heads * 8;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float s = 0.f;
+  long long rh = 0;
+  const bool ok = i < nvec;
+  if (ok) {
+    rh = i >> 3;                                   // (b*nq + n)*heads + h
+    const int h = (int)(rh % p.heads);
+    const long long bn = rh / p.heads;
+    const int n = (int)(bn % p.nq), b = (int)(bn / p.nq);
+    const int c = h * D + (int)(i & 7) * 8;
+    const uint4 ov = *reinterpret_cast<const uint4*>(p.o + (long long)b * p.bso + (long long)n * p.ldo + c);
+    const uint4 dv = *reinterpret_cast<const uint4*>(p.d_o + (long long)b * p.bsdo + (long long)n * p.lddo + c);
+    float2 a, g;
+    a = unpack_bf162(ov.x); g = unpack_bf162(dv.x); s = fmaf(a.x, g.x, fmaf(a.y, g.y, s));
+    a = unpack_bf162(ov.y); g = unpack_bf162(dv.y); s = fmaf(a.x, g.x, fmaf(a.y, g.y, s));
+    a = unpack_bf162(ov.z); g = unpack_bf162(dv.z); s = fmaf(a.x, g.x, fmaf(a.y, g.y, s));
+    a = unpack_bf162(ov.w); g = unpack_bf162(dv.w); s = fmaf(a.x, g.x, fmaf(a.y, g.y, s));
   }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (ok && (threadIdx.x & 7) == 0) {
+    const int h = (int)(rh % p.heads);
+    const long long bn = rh / p.heads;
+    const int n = (int)(bn % p.nq), b = (int)(bn / p.nq);
+    p.delta[((long long)b * p.heads + h) * p.nq + n] = s;
+  }
+  (void)C;
 }
 
 // =================================================================================================
@@ -527,17 +450,6 @@ int set_smem(K kernel, int bytes) {
 
 }  // namespace
 
-extern "C" int vn_attention_fwd(const vn_attn_desc* d, vn_stream_t s) {
-  AttnParams p{};
-  if (fill_params(d, &p, false)) return -1;
-  static bool configured = false;
-  if (!configured) { if (set_smem(attn_fwd_kernel, FWD_SMEM)) return -2; configured = true; }
-  dim3 grid(vn_cdiv(p.nq, FWD_BM), p.heads, p.nb);
-  attn_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)s>>>(p);
-  VN_LAUNCH_OK();
-  return 0;
-}
-
 extern "C" int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s) {
   AttnParams p{};
   if (fill_params(d, &p, true)) return -1;
@@ -549,7 +461,7 @@ extern "C" int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s) {
     if (set_smem(attn_bwd_dkv_kernel<true>, DKV_SMEM)) return -2;
     configured = true;
   }
-  attn_delta_kernel<<<(unsigned)vn_cdiv64((long long)p.nb * p.nq, 8), 256, 0, st>>>(p);
+  attn_delta_kernel<<<(unsigned)vn_cdiv64((long long)p.nb * p.nq * p.heads * 8, 256), 256, 0, st>>>(p);
   VN_LAUNCH_OK();
   if (p.dq) {
     dim3 grid(vn_cdiv(p.nq, FWD_BM), p.heads, p.nb);

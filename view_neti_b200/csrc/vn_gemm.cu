@@ -20,7 +20,7 @@
 //     S in {2,4,8} CTAs shares one output tile, each CTA accumulates K/S in its own TMEM; partials are exchanged
 //     through DISTRIBUTED SHARED MEMORY (st.shared::cluster), CTA r reduces rows [r*128/S, (r+1)*128/S) and runs
 //     the epilogue for them.  No global atomics, no workspace, deterministic.
-#include "vn_common.cuh"
+#include "vn_tma.cuh"
 
 #include <string.h>
 
@@ -481,33 +481,9 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
              const cuuint32_t* box) {
-  EncodeTiledFn fn = get_encode_fn();
-  VN_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not found (no CUDA driver?)");
-  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
-                  box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  VN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)",
-           (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
-  return 0;
+  return vn_make_map(m, base, rank, dims, strides_bytes, box);
 }
 
 int g_num_sms = 0;

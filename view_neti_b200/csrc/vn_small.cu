@@ -144,6 +144,14 @@ __global__ void __launch_bounds__(256) conv_thin_to_wide_kernel(const float* __r
                                                                 const float* __restrict__ wgt,
                                                                 const float* __restrict__ bias, bf16* __restrict__ y,
                                                                 long long ldy, int nb, int Ct, int H, int W, int Cw) {
+  extern __shared__ float s_w[];   // [9 taps][Ct][Cw]: a thread reads its 8 output channels as two 16-byte vectors
+  for (int i = threadIdx.x; i < 9 * Ct * Cw; i += blockDim.x) {
+    const int cw = i % Cw;
+    const int ct = (i / Cw) % Ct;
+    const int tap = i / (Cw * Ct);
+    s_w[i] = FLIP ? wgt[((long long)ct * Cw + cw) * 9 + (8 - tap)] : wgt[((long long)cw * Ct + ct) * 9 + tap];
+  }
+  __syncthreads();
   const int vecs = Cw >> 3;
   const long long total = (long long)nb * H * W * vecs;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -163,12 +171,10 @@ __global__ void __launch_bounds__(256) conv_thin_to_wide_kernel(const float* __r
         const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
         if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
         const float v = __ldg(xp + hh * W + ww);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float wv = FLIP ? __ldg(wgt + ((long long)ct * Cw + c0 + j) * 9 + (8 - tap))
-                                : __ldg(wgt + ((long long)(c0 + j) * Ct + ct) * 9 + tap);
-          a[j] = fmaf(v, wv, a[j]);
-        }
+        const float4 w0 = *reinterpret_cast<const float4*>(s_w + ((long long)tap * Ct + ct) * Cw + c0);
+        const float4 w1 = *reinterpret_cast<const float4*>(s_w + ((long long)tap * Ct + ct) * Cw + c0 + 4);
+        a[0] = fmaf(v, w0.x, a[0]); a[1] = fmaf(v, w0.y, a[1]); a[2] = fmaf(v, w0.z, a[2]); a[3] = fmaf(v, w0.w, a[3]);
+        a[4] = fmaf(v, w1.x, a[4]); a[5] = fmaf(v, w1.y, a[5]); a[6] = fmaf(v, w1.z, a[6]); a[7] = fmaf(v, w1.w, a[7]);
       }
     }
     const long long dst = ((long long)b * H + h) * W + w;
@@ -329,6 +335,13 @@ __global__ void __launch_bounds__(256) cfg_ddim_kernel(float* __restrict__ laten
   }
 }
 
+template <typename K>
+int thin_smem_config(K kernel, size_t smem) {
+  VN_CHECK(smem <= 200 * 1024, "edge conv: weights (%zu B) do not fit in shared memory", smem);
+  if (smem > 48 * 1024) VN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return 0;
+}
+
 }  // namespace
 
 extern "C" int vn_upsample2x_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, int nb, int H, int W, int C,
@@ -376,8 +389,11 @@ extern "C" int vn_conv_in_fwd(const float* x, const float* w, const float* bias,
                               int H, int W, int Cout, vn_stream_t s) {
   VN_CHECK(Cout % 8 == 0 && ldy % 8 == 0 && Cin >= 1, "conv_in: Cout and ldy must be multiples of 8");
   const long long total = (long long)nb * H * W * (Cout / 8);
-  conv_thin_to_wide_kernel<0><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>(x, w, bias, (bf16*)y, ldy, nb, Cin, H,
-                                                                                  W, Cout);
+  const size_t smem = (size_t)9 * Cin * Cout * sizeof(float);
+  if (thin_smem_config(conv_thin_to_wide_kernel<0>, smem)) return -2;
+  int blocks = grid_for(total, 256);
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  conv_thin_to_wide_kernel<0><<<blocks, 256, smem, (cudaStream_t)s>>>(x, w, bias, (bf16*)y, ldy, nb, Cin, H, W, Cout);
   VN_LAUNCH_OK();
   return 0;
 }
@@ -386,8 +402,11 @@ extern "C" int vn_conv_out_bwd(const float* dy, const float* w, void* dx, int64_
                                int Cout, vn_stream_t s) {
   VN_CHECK(Cin % 8 == 0 && lddx % 8 == 0 && Cout >= 1, "conv_out_bwd: Cin and lddx must be multiples of 8");
   const long long total = (long long)nb * H * W * (Cin / 8);
-  conv_thin_to_wide_kernel<1><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>(dy, w, nullptr, (bf16*)dx, lddx, nb,
-                                                                                  Cout, H, W, Cin);
+  const size_t smem = (size_t)9 * Cin * Cout * sizeof(float);
+  if (thin_smem_config(conv_thin_to_wide_kernel<1>, smem)) return -2;
+  int blocks = grid_for(total, 256);
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  conv_thin_to_wide_kernel<1><<<blocks, 256, smem, (cudaStream_t)s>>>(dy, w, nullptr, (bf16*)dx, lddx, nb, Cout, H, W, Cin);
   VN_LAUNCH_OK();
   return 0;
 }
