@@ -39,7 +39,7 @@ for idx, (kind, m, N, K) in enumerate(shapes):
         D = torch.empty(m, N, dtype=BF, device=dev)
         R = torch.randn(m, N, device=dev).to(BF)
         bias = torch.randn(N, device=dev)
-        f = lambda: ops.gemm(A, B, D, bias=bias, R=R, ws=ws)
+        f = lambda: ops.gemm(A, B, D, bias=bias, R=R, ws=ws, force_bn=int(os.environ.get('FORCE_BN', 0)), force_split=int(os.environ.get('FORCE_SPLIT', 0)))
         fl = 2.0 * m * N * K
         lab = f"lin  M{m} N{N} K{K}"
     else:
@@ -49,7 +49,7 @@ for idx, (kind, m, N, K) in enumerate(shapes):
         D = torch.empty(nb, H, W, N, dtype=BF, device=dev)
         R = torch.randn(nb, H, W, N, device=dev).to(BF)
         bias = torch.randn(N, device=dev)
-        f = lambda: ops.conv3x3(x, B, D, bias=bias, R=R, ws=ws)
+        f = lambda: ops.conv3x3(x, B, D, bias=bias, R=R, ws=ws, force_bn=int(os.environ.get('FORCE_BN', 0)), force_split=int(os.environ.get('FORCE_SPLIT', 0)))
         fl = 2.0 * nb * H * W * N * 9 * K
         lab = f"conv {H}x{W} C{K} N{N}"
     for _ in range(3):

@@ -22,6 +22,7 @@
 //     the epilogue for them.  No global atomics, no workspace, deterministic.
 #include "vn_tma.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -674,7 +675,10 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
     const int grid = tiles < num_sms() ? tiles : num_sms();
     switch (bn) {
       case 64: return launch<64, 6, false>(ta, tb, td, tr, p, grid, st);
-      case 128: return launch<128, 5, false>(ta, tb, td, tr, p, grid, st);
+      case 128:
+        if (getenv("VN_GEMM_STAGES3")) return launch<128, 3, false>(ta, tb, td, tr, p, grid, st);
+        if (getenv("VN_GEMM_STAGES2")) return launch<128, 2, false>(ta, tb, td, tr, p, grid, st);
+        return launch<128, 5, false>(ta, tb, td, tr, p, grid, st);
       default: return launch<256, 3, false>(ta, tb, td, tr, p, grid, st);
     }
   }

@@ -42,6 +42,25 @@ def _pix_ld(x: torch.Tensor) -> int:
     return ld
 
 
+def tuning_key(mode: int, M: int, N: int, K: int, H: int, W: int) -> str:
+    return f"{mode}:{M}:{N}:{K}:{H}:{W}"
+
+
+def _load_tuning():
+    """(BN, split) choices measured on B200 by scripts/gemm_autotune.py for the SD-2.1 layer shapes; shapes not in the
+    table use the library's cost model."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gemm_tuning.json")
+    if not os.path.exists(path):
+        return {}
+    with open(path) as f:
+        return {k: (int(v[0]), int(v[1])) for k, v in json.load(f).items()}
+
+
+TUNING = _load_tuning()
+
+
 class Workspace:
     """Split-K scratch for vn_gemm (zero on entry, left zero by every call) + fp32 dK/dV accumulator."""
 
@@ -73,6 +92,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, bias=None, rowbia
         d.R, d.ldr = ptr(R), _ld(R)
     if ws is not None:
         d.workspace, d.workspace_bytes = ptr(ws.buf), ws.bytes
+    if not force_bn and not force_split:
+        force_bn, force_split = TUNING.get(tuning_key(0, M, N, K, 0, 0), (0, 0))
     d.force_bn, d.force_split = force_bn, force_split
     check(lib.vn_gemm(C.byref(d), stream()), "vn_gemm")
     return D
@@ -100,6 +121,8 @@ def conv3x3(x: torch.Tensor, Wk: torch.Tensor, D: torch.Tensor, *, bias=None, ro
         d.R, d.ldr = ptr(R), _pix_ld(R)
     if ws is not None:
         d.workspace, d.workspace_bytes = ptr(ws.buf), ws.bytes
+    if not force_bn and not force_split:
+        force_bn, force_split = TUNING.get(tuning_key(1, nb * H * W, N, 9 * Cc, H, W), (0, 0))
     d.force_bn, d.force_split = force_bn, force_split
     check(lib.vn_gemm(C.byref(d), stream()), "vn_gemm(conv)")
     return D
