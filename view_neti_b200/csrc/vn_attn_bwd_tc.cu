@@ -1,0 +1,534 @@
+// vn_attn_bwd_tc.cu — attention backward on tcgen05 / TMEM / TMA (head_dim 64): the autograd backward of
+// reference models/xti_attention_processor.py:44-50 (training/coach.py:214), logits recomputed from the saved
+// log-sum-exp, nothing of size nq x nk ever leaves the SM.
+//
+//   delta = rowsum(dO * O)                                        (small CUDA-core kernel)
+//   dKV kernel, CTA = (128-key tile, head, image[, query split]), loop over 128-query tiles:
+//       S^T = K Q^T, dP^T = V dO^T            tcgen05.mma  -> TMEM [0,128) and [128,256)
+//       P^T = exp2(S^T*c - lse[q]),  dS^T = P^T * (dP^T - delta[q]) * scale        (8 warps, thread = key row x 64 queries)
+//       dV += P^T dO,  dK += dS^T Q           tcgen05.mma, A = P^T / dS^T from shared memory, B = the dO / Q tile used in
+//                                             place as an MN-major operand        -> TMEM [256,320) and [320,384)
+//   dQ kernel, CTA = (128-query tile, head, image), loop over 128-key tiles:
+//       S = Q K^T, dP = dO V^T -> TMEM; dS = P * (dP - delta) * scale -> smem; dQ += dS K (K tile in place, MN-major).
+// Two kernels (S recomputed twice) instead of one with global atomics on dQ: results stay deterministic.
+// Cross-attention (nk = 77) has a single key tile: the dKV kernel then splits the query range over CTAs and adds its
+// partial dK / dV into an fp64 scratch (order-independent), finished by a small conversion kernel.
+#include "vn_tma.cuh"
+
+namespace {
+
+constexpr int D = 64;
+constexpr int T = 128;                            // tile edge (queries and keys)
+constexpr int TILE_BYTES = T * 128;               // [128 rows x 64 bf16], 128B-swizzled
+constexpr int kThreads = 320;                     // producer warp, MMA warp, 8 compute warps
+constexpr int TMEM_COLS = 512;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct BwdParams {
+  int nb, heads, nq, nk;
+  float scale;
+  const float* lse; const float* delta;
+  bf16* dq; long long lddq, bsdq;
+  bf16* dk; long long lddk, bsdk;
+  bf16* dv; long long lddv, bsdv;
+  double* dkv_acc;
+  int qsplits, qtiles_per_split;
+};
+
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc(int m, int n, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 1-D bulk copy global -> shared, completion on an mbarrier (bytes % 16 == 0, 16-byte aligned)
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[128 x 64 k, K-major] * B[N x 64 k, K-major]^T : 4 k-steps
+__device__ __forceinline__ void mma_kk(uint32_t tacc, uint32_t a, uint32_t b, uint32_t id) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_bf16(tacc, umma_desc_k_sw128(a) + (uint64_t)(k * 2), umma_desc_k_sw128(b) + (uint64_t)(k * 2), id, k ? 1u : 0u);
+}
+// D[tmem] (+)= A[128 x 128 k: two K-major 64-wide blocks] * B[128 k x 64 n, MN-major tile used in place] : 8 k-steps
+__device__ __forceinline__ void mma_kmn(uint32_t tacc, uint32_t a, uint32_t b, uint32_t id, bool accumulate) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    umma_bf16(tacc, umma_desc_k_sw128(a + (k >> 2) * TILE_BYTES) + (uint64_t)((k & 3) * 2), desc_mn_sw128(b + k * 2048), id,
+              (accumulate || k) ? 1u : 0u);
+}
+__device__ __forceinline__ void ld64(uint32_t taddr, uint32_t (&v)[64]) {
+  uint32_t(&c0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+  uint32_t(&c1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+  tmem_ld32(taddr, c0);
+  tmem_ld32(taddr + 32, c1);
+}
+__device__ __forceinline__ void store_row8(uint8_t* row, int chunk, int r, const float (&e)[8]) {
+  uint4 w;
+  w.x = pack_bf162(e[0], e[1]); w.y = pack_bf162(e[2], e[3]);
+  w.z = pack_bf162(e[4], e[5]); w.w = pack_bf162(e[6], e[7]);
+  *reinterpret_cast<uint4*>(row + ((chunk ^ (r & 7)) << 4)) = w;
+}
+
+// =================================================================================================
+// dK, dV
+// =================================================================================================
+constexpr int DKV_STAGE_BYTES = 2 * TILE_BYTES + 2 * T * 4;        // Q, dO, lse, delta
+constexpr int DKV_SMEM = 2 * TILE_BYTES /*K,V*/ + 2 * DKV_STAGE_BYTES + 2 * 2 * TILE_BYTES /*P^T, dS^T*/ + 256 + 1024;
+
+template <bool ATOMIC>
+__global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                       const __grid_constant__ CUtensorMap tmK,
+                                                                       const __grid_constant__ CUtensorMap tmV,
+                                                                       const __grid_constant__ CUtensorMap tmdO,
+                                                                       const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + TILE_BYTES;
+  uint8_t* sP = sV + TILE_BYTES;                     // P^T  : two [128 keys x 64 queries] blocks
+  uint8_t* sdS = sP + 2 * TILE_BYTES;                // dS^T : same
+  uint8_t* sStage = sdS + 2 * TILE_BYTES;            // 2 x {Q tile, dO tile, lse[128], delta[128]}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 2 * DKV_STAGE_BYTES);
+  uint64_t* kv_full = bars;
+  uint64_t* st_full = bars + 1;                      // [2]
+  uint64_t* st_empty = bars + 3;                     // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* acc_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * T, h = blockIdx.y;
+  const int b = blockIdx.z / p.qsplits, split = blockIdx.z % p.qsplits;
+  const int total_qt = (p.nq + T - 1) / T;
+  const int qt_begin = split * p.qtiles_per_split;
+  const int nt = min(total_qt, qt_begin + p.qtiles_per_split) - qt_begin;      // host guarantees >= 1
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 256);
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tST = tmem_base, tdPT = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320;
+  const long long sidx = ((long long)b * p.heads + h) * p.nq;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+      tma_load_3d(sK, &tmK, kv_full, h * D, k0, b);
+      tma_load_3d(sV, &tmV, kv_full, h * D, k0, b);
+      for (int i = 0; i < nt; ++i) {
+        const int s = i & 1;
+        const int q0 = (qt_begin + i) * T;
+        const int nvalid = min(T, p.nq - q0);
+        const uint32_t vec_bytes = (uint32_t)(((nvalid * 4) + 15) & ~15);      // nq % 4 == 0 is checked on the host
+        uint8_t* st = sStage + s * DKV_STAGE_BYTES;
+        mbar_wait(&st_empty[s], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&st_full[s], 2 * TILE_BYTES + 2 * vec_bytes);
+        tma_load_3d(st, &tmQ, &st_full[s], h * D, q0, b);
+        tma_load_3d(st + TILE_BYTES, &tmdO, &st_full[s], h * D, q0, b);
+        bulk_load(st + 2 * TILE_BYTES, p.lse + sidx + q0, vec_bytes, &st_full[s]);
+        bulk_load(st + 2 * TILE_BYTES + T * 4, p.delta + sidx + q0, vec_bytes, &st_full[s]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t id_s = idesc(T, T, 0);        // 128 x 128, both K-major
+      constexpr uint32_t id_acc = idesc(T, D, 1);      // 128 x 64, B MN-major
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), adS = smem_u32(sdS);
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < nt; ++i) {
+        const int s = i & 1;
+        const uint32_t aQ = smem_u32(sStage + s * DKV_STAGE_BYTES), adO = aQ + TILE_BYTES;
+        mbar_wait(&st_full[s], (i >> 1) & 1);
+        tc_fence_after();
+        // (TMEM S^T / dP^T are free: the compute warps arrived on p_full(i-1) before the accumulations below were issued)
+        mma_kk(tST, aK, aQ, id_s);                     // S^T  = K Q^T
+        mma_kk(tdPT, aV, adO, id_s);                   // dP^T = V dO^T
+        umma_commit(s_full);                           // (in-order retirement: also says dV/dK(i-1) are done -> sP/sdS free)
+        mbar_wait(p_full, i & 1);
+        tc_fence_after();
+        mma_kmn(tdV, aP, adO, id_acc, i > 0);          // dV += P^T dO
+        mma_kmn(tdK, adS, aQ, id_acc, i > 0);          // dK += dS^T Q
+        umma_commit(&st_empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    const int qd = warp & 3, hf = (warp - 2) >> 2;
+    const int r = qd * 32 + lane;                      // key row of the tile
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const float sl2 = p.scale * kLog2e;
+    for (int i = 0; i < nt; ++i) {
+      const int s = i & 1;
+      const int q0 = (qt_begin + i) * T;
+      const float* lse = reinterpret_cast<const float*>(sStage + s * DKV_STAGE_BYTES + 2 * TILE_BYTES) + hf * 64;
+      const float* dl = lse + T;
+      mbar_wait(&st_full[s], (i >> 1) & 1);            // lse / delta of this query tile are in shared memory
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+      uint32_t sv[64], dp[64];
+      ld64(tST + lane_addr + hf * 64, sv);
+      ld64(tdPT + lane_addr + hf * 64, dp);
+      tmem_ld_wait();
+      const int qvalid = p.nq - q0 - hf * 64;          // queries of this half-tile that exist
+      uint8_t* prow = sP + hf * TILE_BYTES + r * 128;
+      uint8_t* drow = sdS + hf * TILE_BYTES + r * 128;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 l0 = *reinterpret_cast<const float4*>(lse + g * 8), l1 = *reinterpret_cast<const float4*>(lse + g * 8 + 4);
+        const float4 d0 = *reinterpret_cast<const float4*>(dl + g * 8), d1 = *reinterpret_cast<const float4*>(dl + g * 8 + 4);
+        const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        float pe[8], de[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float pv = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + c]), sl2, -lv[c] * kLog2e));
+          if (g * 8 + c >= qvalid) pv = 0.f;           // padded queries (their lse / delta slots hold stale data)
+          pe[c] = pv;
+          de[c] = pv * (__uint_as_float(dp[g * 8 + c]) - dv[c]) * p.scale;
+          if (g * 8 + c >= qvalid) de[c] = 0.f;
+        }
+        store_row8(prow, g, r, pe);
+        store_row8(drow, g, r, de);
+      }
+      tc_fence_before();
+      fence_async_smem();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    // half 0 finishes dV, half 1 finishes dK
+    uint32_t acc[64];
+    ld64((hf == 0 ? tdV : tdK) + lane_addr, acc);
+    tmem_ld_wait();
+    tc_fence_before();
+    const int krow = k0 + r;
+    if (krow < p.nk) {
+      if (ATOMIC) {
+        const long long C = (long long)p.heads * D;
+        double* dst = p.dkv_acc + (hf == 0 ? (long long)p.nb * p.nk * C : 0) + ((long long)b * p.nk + krow) * C + h * D;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) atomicAdd(dst + c, (double)__uint_as_float(acc[c]));
+      } else {
+        bf16* dst = hf == 0 ? p.dv + (long long)b * p.bsdv + (long long)krow * p.lddv + h * D
+                            : p.dk + (long long)b * p.bsdk + (long long)krow * p.lddk + h * D;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          uint4 w;
+          w.x = pack_bf162(__uint_as_float(acc[g * 8 + 0]), __uint_as_float(acc[g * 8 + 1]));
+          w.y = pack_bf162(__uint_as_float(acc[g * 8 + 2]), __uint_as_float(acc[g * 8 + 3]));
+          w.z = pack_bf162(__uint_as_float(acc[g * 8 + 4]), __uint_as_float(acc[g * 8 + 5]));
+          w.w = pack_bf162(__uint_as_float(acc[g * 8 + 6]), __uint_as_float(acc[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst + g * 8) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// =================================================================================================
+// dQ
+// =================================================================================================
+constexpr int DQ_SMEM = 2 * TILE_BYTES /*Q,dO*/ + 2 * 2 * TILE_BYTES /*K,V x 2 stages*/ + 2 * TILE_BYTES /*dS*/ + 256 + 1024;
+
+__global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                      const __grid_constant__ CUtensorMap tmK,
+                                                                      const __grid_constant__ CUtensorMap tmV,
+                                                                      const __grid_constant__ CUtensorMap tmdO,
+                                                                      const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + TILE_BYTES;
+  uint8_t* sdS = sdO + TILE_BYTES;                   // two [128 queries x 64 keys] blocks
+  uint8_t* sKV = sdS + 2 * TILE_BYTES;               // stage s: K at s*2*TILE, V right after
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + 4 * TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;                      // [2]
+  uint64_t* kv_empty = bars + 3;                     // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* acc_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * T, h = blockIdx.y, b = blockIdx.z;
+  const int nt = (p.nk + T - 1) / T;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 256);
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdQ = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * TILE_BYTES);
+      tma_load_3d(sQ, &tmQ, q_full, h * D, q0, b);
+      tma_load_3d(sdO, &tmdO, q_full, h * D, q0, b);
+      for (int j = 0; j < nt; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+        tma_load_3d(sKV + s * 2 * TILE_BYTES, &tmK, &kv_full[s], h * D, j * T, b);
+        tma_load_3d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &tmV, &kv_full[s], h * D, j * T, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t id_s = idesc(T, T, 0);
+      constexpr uint32_t id_acc = idesc(T, D, 1);
+      const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), adS = smem_u32(sdS);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nt; ++j) {
+        const int s = j & 1;
+        const uint32_t aK = smem_u32(sKV + s * 2 * TILE_BYTES), aV = aK + TILE_BYTES;
+        mbar_wait(&kv_full[s], (j >> 1) & 1);
+        tc_fence_after();
+        mma_kk(tS, aQ, aK, id_s);                      // S  = Q K^T
+        mma_kk(tdP, adO, aV, id_s);                    // dP = dO V^T
+        umma_commit(s_full);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        mma_kmn(tdQ, adS, aK, id_acc, j > 0);          // dQ += dS K
+        umma_commit(&kv_empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    const int qd = warp & 3, hf = (warp - 2) >> 2;
+    const int r = qd * 32 + lane;                      // query row of the tile
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const float sl2 = p.scale * kLog2e;
+    const int row = q0 + r;
+    const long long sidx = ((long long)b * p.heads + h) * p.nq;
+    const float lse2 = row < p.nq ? p.lse[sidx + row] * kLog2e : INFINITY;     // padded query rows: P = 0
+    const float dl = row < p.nq ? p.delta[sidx + row] : 0.f;
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      uint32_t sv[64], dp[64];
+      ld64(tS + lane_addr + hf * 64, sv);
+      ld64(tdP + lane_addr + hf * 64, dp);
+      tmem_ld_wait();
+      const int kvalid = p.nk - j * T - hf * 64;
+      uint8_t* drow = sdS + hf * TILE_BYTES + r * 128;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        float de[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float pv = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + c]), sl2, -lse2));
+          de[c] = (g * 8 + c < kvalid) ? pv * (__uint_as_float(dp[g * 8 + c]) - dl) * p.scale : 0.f;
+        }
+        store_row8(drow, g, r, de);
+      }
+      tc_fence_before();
+      fence_async_smem();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    uint32_t acc[32];
+    tmem_ld32(tdQ + lane_addr + hf * 32, acc);
+    tmem_ld_wait();
+    tc_fence_before();
+    if (row < p.nq) {
+      bf16* dst = p.dq + (long long)b * p.bsdq + (long long)row * p.lddq + h * D + hf * 32;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 w;
+        w.x = pack_bf162(__uint_as_float(acc[g * 8 + 0]), __uint_as_float(acc[g * 8 + 1]));
+        w.y = pack_bf162(__uint_as_float(acc[g * 8 + 2]), __uint_as_float(acc[g * 8 + 3]));
+        w.z = pack_bf162(__uint_as_float(acc[g * 8 + 4]), __uint_as_float(acc[g * 8 + 5]));
+        w.w = pack_bf162(__uint_as_float(acc[g * 8 + 6]), __uint_as_float(acc[g * 8 + 7]));
+        *reinterpret_cast<uint4*>(dst + g * 8) = w;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// delta[b,h,n] = sum_d dO * O : one 16-byte vector per lane, 8 lanes per (row, head)
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, long long ldo, long long bso,
+                                                         const bf16* __restrict__ d_o, long long lddo, long long bsdo,
+                                                         float* __restrict__ delta, int nb, int heads, int nq) {
+  const long long nvec = (long long)nb * nq * heads * 8;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float s = 0.f;
+  long long rh = 0;
+  const bool ok = i < nvec;
+  if (ok) {
+    rh = i >> 3;
+    const int h = (int)(rh % heads);
+    const long long bn = rh / heads;
+    const int n = (int)(bn % nq), b = (int)(bn / nq);
+    const int c = h * D + (int)(i & 7) * 8;
+    const uint4 ov = *reinterpret_cast<const uint4*>(o + (long long)b * bso + (long long)n * ldo + c);
+    const uint4 dv = *reinterpret_cast<const uint4*>(d_o + (long long)b * bsdo + (long long)n * lddo + c);
+    float2 a, g;
+    a = unpack_bf162(ov.x); g = unpack_bf162(dv.x); s = fmaf(a.x, g.x, fmaf(a.y, g.y, s));
+    a = unpack_bf162(ov.y); g = unpack_bf162(dv.y); s = fmaf(a.x, g.x, fmaf(a.y, g.y, s));
+    a = unpack_bf162(ov.z); g = unpack_bf162(dv.z); s = fmaf(a.x, g.x, fmaf(a.y, g.y, s));
+    a = unpack_bf162(ov.w); g = unpack_bf162(dv.w); s = fmaf(a.x, g.x, fmaf(a.y, g.y, s));
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (ok && (threadIdx.x & 7) == 0) {
+    const int h = (int)(rh % heads);
+    const long long bn = rh / heads;
+    const int n = (int)(bn % nq), b = (int)(bn / nq);
+    delta[((long long)b * heads + h) * nq + n] = s;
+  }
+}
+
+// fp64 scratch -> bf16 dk / dv, leaving the scratch zeroed for the next launch
+__global__ void __launch_bounds__(256) attn_dkv_finish_kernel(const BwdParams p) {
+  const int C = p.heads * D;
+  const long long per = (long long)p.nb * p.nk * C;
+  const long long total = per / 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 2;
+    const int c = (int)(e % C);
+    const long long r = e / C;
+    const int n = (int)(r % p.nk), b = (int)(r / p.nk);
+    double2* ak = reinterpret_cast<double2*>(p.dkv_acc + e);
+    double2* av = reinterpret_cast<double2*>(p.dkv_acc + per + e);
+    const double2 a = *ak, v = *av;
+    *reinterpret_cast<bf162*>(p.dk + (long long)b * p.bsdk + (long long)n * p.lddk + c) = __floats2bfloat162_rn((float)a.x, (float)a.y);
+    *reinterpret_cast<bf162*>(p.dv + (long long)b * p.bsdv + (long long)n * p.lddv + c) = __floats2bfloat162_rn((float)v.x, (float)v.y);
+    *ak = make_double2(0.0, 0.0);
+    *av = make_double2(0.0, 0.0);
+  }
+}
+
+int qkv_map(CUtensorMap* m, const void* base, int width, int rows, int nb, long long ld, long long bs) {
+  cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)rows, (cuuint64_t)nb};
+  cuuint64_t str[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(nb > 1 ? bs : ld * rows) * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  return vn_make_map(m, base, 3, dims, str, box);
+}
+
+}  // namespace
+
+extern "C" int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s) {
+  cudaStream_t st = (cudaStream_t)s;
+  VN_CHECK(d != nullptr, "attention bwd: null descriptor");
+  VN_CHECK(d->nb > 0 && d->heads > 0 && d->nq > 0 && d->nk > 0, "attention bwd: empty problem");
+  VN_CHECK(d->lse && d->delta && d->d_o && d->dk && d->dv, "attention bwd: lse, delta, d_o, dk, dv are required");
+  VN_CHECK(d->nq % 4 == 0, "attention bwd: nq must be a multiple of 4 (16-byte bulk loads of lse / delta)");
+  VN_CHECK(d->ldq % 8 == 0 && d->ldk % 8 == 0 && d->ldv % 8 == 0 && d->ldo % 8 == 0 && d->lddo % 8 == 0 && d->bsq % 8 == 0 &&
+               d->bsk % 8 == 0 && d->bsv % 8 == 0 && d->bso % 8 == 0 && d->bsdo % 8 == 0 && d->lddk % 8 == 0 &&
+               d->lddv % 8 == 0 && d->bsdk % 8 == 0 && d->bsdv % 8 == 0 && (!d->dq || (d->lddq % 8 == 0 && d->bsdq % 8 == 0)),
+           "attention bwd: strides must be multiples of 8 elements");
+  VN_CHECK(((reinterpret_cast<uintptr_t>(d->q) | reinterpret_cast<uintptr_t>(d->k) | reinterpret_cast<uintptr_t>(d->v) |
+             reinterpret_cast<uintptr_t>(d->o) | reinterpret_cast<uintptr_t>(d->d_o) | reinterpret_cast<uintptr_t>(d->dq) |
+             reinterpret_cast<uintptr_t>(d->dk) | reinterpret_cast<uintptr_t>(d->dv) | reinterpret_cast<uintptr_t>(d->lse) |
+             reinterpret_cast<uintptr_t>(d->delta)) & 15) == 0, "attention bwd: tensors must be 16-byte aligned");
+  const int width = d->heads * D;
+  CUtensorMap tq, tk, tv, tdo;
+  if (qkv_map(&tq, d->q, width, d->nq, d->nb, d->ldq, d->bsq)) return -1;
+  if (qkv_map(&tk, d->k, width, d->nk, d->nb, d->ldk, d->bsk)) return -1;
+  if (qkv_map(&tv, d->v, width, d->nk, d->nb, d->ldv, d->bsv)) return -1;
+  if (qkv_map(&tdo, d->d_o, width, d->nq, d->nb, d->lddo, d->bsdo)) return -1;
+  BwdParams p{};
+  p.nb = d->nb; p.heads = d->heads; p.nq = d->nq; p.nk = d->nk; p.scale = d->scale;
+  p.lse = d->lse; p.delta = d->delta;
+  p.dq = (bf16*)d->dq; p.lddq = d->lddq; p.bsdq = d->bsdq;
+  p.dk = (bf16*)d->dk; p.lddk = d->lddk; p.bsdk = d->bsdk;
+  p.dv = (bf16*)d->dv; p.lddv = d->lddv; p.bsdv = d->bsdv;
+  p.dkv_acc = d->dkv_acc;
+  static bool configured = false;
+  if (!configured) {
+    VN_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    VN_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    VN_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    configured = true;
+  }
+  attn_delta_kernel<<<(unsigned)vn_cdiv64((long long)d->nb * d->nq * d->heads * 8, 256), 256, 0, st>>>(
+      (const bf16*)d->o, d->ldo, d->bso, (const bf16*)d->d_o, d->lddo, d->bsdo, d->delta, d->nb, d->heads, d->nq);
+  VN_LAUNCH_OK();
+  if (d->dq) {
+    p.qsplits = 1; p.qtiles_per_split = 1 << 30;
+    dim3 grid(vn_cdiv(d->nq, T), d->heads, d->nb);
+    attn_bwd_dq_tc_kernel<<<grid, kThreads, DQ_SMEM, st>>>(tq, tk, tv, tdo, p);
+    VN_LAUNCH_OK();
+  }
+  const int ktiles = vn_cdiv(d->nk, T), qtiles = vn_cdiv(d->nq, T);
+  const long long base_ctas = (long long)ktiles * d->heads * d->nb;
+  int splits = 1;
+  if (d->dkv_acc && base_ctas < 148) {
+    splits = (int)((148 + base_ctas - 1) / base_ctas);
+    if (splits > qtiles) splits = qtiles;
+    if (splits < 1) splits = 1;
+  }
+  p.qtiles_per_split = vn_cdiv(qtiles, splits);
+  splits = vn_cdiv(qtiles, p.qtiles_per_split);
+  p.qsplits = splits;
+  dim3 grid(ktiles, d->heads, d->nb * splits);
+  if (splits > 1) {
+    attn_bwd_dkv_tc_kernel<true><<<grid, kThreads, DKV_SMEM, st>>>(tq, tk, tv, tdo, p);
+    VN_LAUNCH_OK();
+    const long long pairs = (long long)d->nb * d->nk * d->heads * D / 2;
+    int blocks = (int)vn_cdiv64(pairs, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    attn_dkv_finish_kernel<<<blocks, 256, 0, st>>>(p);
+    VN_LAUNCH_OK();
+  } else {
+    attn_bwd_dkv_tc_kernel<false><<<grid, kThreads, DKV_SMEM, st>>>(tq, tk, tv, tdo, p);
+    VN_LAUNCH_OK();
+  }
+  return 0;
+}
