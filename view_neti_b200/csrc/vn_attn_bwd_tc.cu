@@ -33,6 +33,7 @@ struct BwdParams {
   bf16* dv; long long lddv, bsdv;
   double* dkv_acc;
   int qsplits, qtiles_per_split;
+  int n_dkv, ktiles, qtiles;        // fused-grid decomposition
 };
 
 __device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr) {
@@ -92,11 +93,8 @@ constexpr int DKV_STAGE_BYTES = 2 * TILE_BYTES + 2 * T * 4;        // Q, dO, lse
 constexpr int DKV_SMEM = 2 * TILE_BYTES /*K,V*/ + 2 * DKV_STAGE_BYTES + 2 * 2 * TILE_BYTES /*P^T, dS^T*/ + 256 + 1024;
 
 template <bool ATOMIC>
-__global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                                       const __grid_constant__ CUtensorMap tmK,
-                                                                       const __grid_constant__ CUtensorMap tmV,
-                                                                       const __grid_constant__ CUtensorMap tmdO,
-                                                                       const BwdParams p) {
+__device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                                         const CUtensorMap& tmdO, const BwdParams& p, int bx, int by, int bz) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
@@ -114,8 +112,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkv_tc_kernel(const __gr
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k0 = blockIdx.x * T, h = blockIdx.y;
-  const int b = blockIdx.z / p.qsplits, split = blockIdx.z % p.qsplits;
+  const int k0 = bx * T, h = by;
+  const int b = bz / p.qsplits, split = bz % p.qsplits;
   const int total_qt = (p.nq + T - 1) / T;
   const int qt_begin = split * p.qtiles_per_split;
   const int nt = min(total_qt, qt_begin + p.qtiles_per_split) - qt_begin;      // host guarantees >= 1
@@ -265,11 +263,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkv_tc_kernel(const __gr
 // =================================================================================================
 constexpr int DQ_SMEM = 2 * TILE_BYTES /*Q,dO*/ + 2 * 2 * TILE_BYTES /*K,V x 2 stages*/ + 2 * TILE_BYTES /*dS*/ + 256 + 1024;
 
-__global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                                      const __grid_constant__ CUtensorMap tmK,
-                                                                      const __grid_constant__ CUtensorMap tmV,
-                                                                      const __grid_constant__ CUtensorMap tmdO,
-                                                                      const BwdParams p) {
+__device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                                        const CUtensorMap& tmdO, const BwdParams& p, int bx, int by, int bz) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -286,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_tc_kernel(const __gri
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * T, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = bx * T, h = by, b = bz;
   const int nt = (p.nk + T - 1) / T;
 
   if (warp == 0 && lane == 0) {
@@ -400,6 +395,28 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_tc_kernel(const __gri
   }
 }
 
+// One launch for both directions: CTAs [0, n_dkv) run the dK/dV body, the rest the dQ body.  With ~160 work items of each
+// kind on 148 SMs, two separate launches cost two partial waves each; fused, the hardware scheduler back-fills SMs as
+// CTAs retire (the longer dK/dV items are scheduled first).
+template <bool ATOMIC>
+__global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                   const __grid_constant__ CUtensorMap tmK,
+                                                                   const __grid_constant__ CUtensorMap tmV,
+                                                                   const __grid_constant__ CUtensorMap tmdO,
+                                                                   const BwdParams p) {
+  int id = blockIdx.x;
+  if (id < p.n_dkv) {
+    const int bx = id % p.ktiles; id /= p.ktiles;
+    const int by = id % p.heads;
+    dkv_body<ATOMIC>(tmQ, tmK, tmV, tmdO, p, bx, by, id / p.heads);
+  } else {
+    id -= p.n_dkv;
+    const int bx = id % p.qtiles; id /= p.qtiles;
+    const int by = id % p.heads;
+    dq_body(tmQ, tmK, tmV, tmdO, p, bx, by, id / p.heads);
+  }
+}
+
 // delta[b,h,n] = sum_d dO * O : one 16-byte vector per lane, 8 lanes per (row, head)
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, long long ldo, long long bso,
                                                          const bf16* __restrict__ d_o, long long lddo, long long bsdo,
@@ -490,22 +507,16 @@ extern "C" int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s) {
   p.dk = (bf16*)d->dk; p.lddk = d->lddk; p.bsdk = d->bsdk;
   p.dv = (bf16*)d->dv; p.lddv = d->lddv; p.bsdv = d->bsdv;
   p.dkv_acc = d->dkv_acc;
+  constexpr int SMEM = DKV_SMEM > DQ_SMEM ? DKV_SMEM : DQ_SMEM;
   static bool configured = false;
   if (!configured) {
-    VN_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
-    VN_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
-    VN_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    VN_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    VN_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
   attn_delta_kernel<<<(unsigned)vn_cdiv64((long long)d->nb * d->nq * d->heads * 8, 256), 256, 0, st>>>(
       (const bf16*)d->o, d->ldo, d->bso, (const bf16*)d->d_o, d->lddo, d->bsdo, d->delta, d->nb, d->heads, d->nq);
   VN_LAUNCH_OK();
-  if (d->dq) {
-    p.qsplits = 1; p.qtiles_per_split = 1 << 30;
-    dim3 grid(vn_cdiv(d->nq, T), d->heads, d->nb);
-    attn_bwd_dq_tc_kernel<<<grid, kThreads, DQ_SMEM, st>>>(tq, tk, tv, tdo, p);
-    VN_LAUNCH_OK();
-  }
   const int ktiles = vn_cdiv(d->nk, T), qtiles = vn_cdiv(d->nq, T);
   const long long base_ctas = (long long)ktiles * d->heads * d->nb;
   int splits = 1;
@@ -517,9 +528,12 @@ extern "C" int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s) {
   p.qtiles_per_split = vn_cdiv(qtiles, splits);
   splits = vn_cdiv(qtiles, p.qtiles_per_split);
   p.qsplits = splits;
-  dim3 grid(ktiles, d->heads, d->nb * splits);
+  p.ktiles = ktiles; p.qtiles = qtiles;
+  p.n_dkv = ktiles * d->heads * d->nb * splits;
+  const int n_dq = d->dq ? qtiles * d->heads * d->nb : 0;
+  const unsigned grid = (unsigned)(p.n_dkv + n_dq);
   if (splits > 1) {
-    attn_bwd_dkv_tc_kernel<true><<<grid, kThreads, DKV_SMEM, st>>>(tq, tk, tv, tdo, p);
+    attn_bwd_tc_kernel<true><<<grid, kThreads, SMEM, st>>>(tq, tk, tv, tdo, p);
     VN_LAUNCH_OK();
     const long long pairs = (long long)d->nb * d->nk * d->heads * D / 2;
     int blocks = (int)vn_cdiv64(pairs, 256);
@@ -527,7 +541,7 @@ extern "C" int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s) {
     attn_dkv_finish_kernel<<<blocks, 256, 0, st>>>(p);
     VN_LAUNCH_OK();
   } else {
-    attn_bwd_dkv_tc_kernel<false><<<grid, kThreads, DKV_SMEM, st>>>(tq, tk, tv, tdo, p);
+    attn_bwd_tc_kernel<false><<<grid, kThreads, SMEM, st>>>(tq, tk, tv, tdo, p);
     VN_LAUNCH_OK();
   }
   return 0;
