@@ -54,12 +54,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 1-D bulk copy global -> shared, completion on an mbarrier (bytes % 16 == 0, 16-byte aligned)
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 // D[tmem] (+)= A[128 x 64 k, K-major] * B[N x 64 k, K-major]^T : 4 k-steps
 __device__ __forceinline__ void mma_kk(uint32_t tacc, uint32_t a, uint32_t b, uint32_t id) {
 #pragma unroll
@@ -143,15 +137,11 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
       for (int i = 0; i < nt; ++i) {
         const int s = i & 1;
         const int q0 = (qt_begin + i) * T;
-        const int nvalid = min(T, p.nq - q0);
-        const uint32_t vec_bytes = (uint32_t)(((nvalid * 4) + 15) & ~15);      // nq % 4 == 0 is checked on the host
         uint8_t* st = sStage + s * DKV_STAGE_BYTES;
         mbar_wait(&st_empty[s], ((i >> 1) & 1) ^ 1);
-        mbar_expect_tx(&st_full[s], 2 * TILE_BYTES + 2 * vec_bytes);
+        mbar_expect_tx(&st_full[s], 2 * TILE_BYTES);
         tma_load_3d(st, &tmQ, &st_full[s], h * D, q0, b);
         tma_load_3d(st + TILE_BYTES, &tmdO, &st_full[s], h * D, q0, b);
-        bulk_load(st + 2 * TILE_BYTES, p.lse + sidx + q0, vec_bytes, &st_full[s]);
-        bulk_load(st + 2 * TILE_BYTES + T * 4, p.delta + sidx + q0, vec_bytes, &st_full[s]);
       }
     }
     __syncwarp();
@@ -184,12 +174,22 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
     const int r = qd * 32 + lane;                      // key row of the tile
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     const float sl2 = p.scale * kLog2e;
+    // per-query lse (pre-scaled by log2 e) and delta of a query tile live in the stage's [2][128] fp32 vector; the 256
+    // compute threads fetch the NEXT tile's values into a register while they work on the current one
+    const int te = threadIdx.x - 64;                   // 0..255: [0,128) -> lse, [128,256) -> delta
+    auto fetch = [&](int i) -> float {
+      const int q = (qt_begin + i) * T + (te & 127);
+      if (i >= nt || q >= p.nq) return 0.f;
+      return te < 128 ? p.lse[sidx + q] * kLog2e : p.delta[sidx + q];
+    };
+    reinterpret_cast<float*>(sStage + 2 * TILE_BYTES)[te] = fetch(0);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     for (int i = 0; i < nt; ++i) {
       const int s = i & 1;
       const int q0 = (qt_begin + i) * T;
       const float* lse = reinterpret_cast<const float*>(sStage + s * DKV_STAGE_BYTES + 2 * TILE_BYTES) + hf * 64;
       const float* dl = lse + T;
-      mbar_wait(&st_full[s], (i >> 1) & 1);            // lse / delta of this query tile are in shared memory
+      const float next_val = fetch(i + 1);
       mbar_wait(s_full, i & 1);
       tc_fence_after();
       uint32_t sv[64], dp[64];
@@ -208,7 +208,7 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
         float pe[8], de[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          float pv = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + c]), sl2, -lv[c] * kLog2e));
+          float pv = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + c]), sl2, -lv[c]));
           if (g * 8 + c >= qvalid) pv = 0.f;           // padded queries (their lse / delta slots hold stale data)
           pe[c] = pv;
           de[c] = pv * (__uint_as_float(dp[g * 8 + c]) - dv[c]) * p.scale;
@@ -220,6 +220,8 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
       tc_fence_before();
       fence_async_smem();
       mbar_arrive(p_full);
+      reinterpret_cast<float*>(sStage + ((i + 1) & 1) * DKV_STAGE_BYTES + 2 * TILE_BYTES)[te] = next_val;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
@@ -485,7 +487,6 @@ extern "C" int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s) {
   VN_CHECK(d != nullptr, "attention bwd: null descriptor");
   VN_CHECK(d->nb > 0 && d->heads > 0 && d->nq > 0 && d->nk > 0, "attention bwd: empty problem");
   VN_CHECK(d->lse && d->delta && d->d_o && d->dk && d->dv, "attention bwd: lse, delta, d_o, dk, dv are required");
-  VN_CHECK(d->nq % 4 == 0, "attention bwd: nq must be a multiple of 4 (16-byte bulk loads of lse / delta)");
   VN_CHECK(d->ldq % 8 == 0 && d->ldk % 8 == 0 && d->ldv % 8 == 0 && d->ldo % 8 == 0 && d->lddo % 8 == 0 && d->bsq % 8 == 0 &&
                d->bsk % 8 == 0 && d->bsv % 8 == 0 && d->bso % 8 == 0 && d->bsdo % 8 == 0 && d->lddk % 8 == 0 &&
                d->lddv % 8 == 0 && d->bsdk % 8 == 0 && d->bsdv % 8 == 0 && (!d->dq || (d->lddq % 8 == 0 && d->bsdq % 8 == 0)),
