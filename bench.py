@@ -153,11 +153,13 @@ def profile_categories(plan):
         return orig["conv3x3"](x, Wk, D, **k)
 
     ops.gemm, ops.conv3x3 = gemm, conv3x3
+    ops.set_pdl(False)          # isolate kernels: with PDL a kernel's duration includes waiting for its predecessor
     try:
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             plan.train_step()
             torch.cuda.synchronize()
     finally:
+        ops.set_pdl(True)
         ops.gemm, ops.conv3x3 = orig["gemm"], orig["conv3x3"]
     fam = {"vn_gemm_kernel": "gemm", "attn_": "attn", "gn_": "groupnorm", "ln_kernel": "layernorm", "geglu": "geglu"}
     ms, n = {}, {}
@@ -295,7 +297,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "launches_per_step": cat_n.get("gemm", 0),
         "flops_per_step": gemm_flops, "avg_launch_us": 1e3 * gemm_ms / max(1, cat_n.get("gemm", 0)),
         "share_of_step": gemm_ms / tot_ms if tot_ms else None,
-        "timing": "CUPTI kernel durations of one eager step run right after the timed region (same process, same clocks)",
+        "timing": "CUPTI kernel durations of one eager step (PDL overlap off) run right after the timed region (same process, same clocks)",
         "kernel_ms_per_step": {k: round(v, 4) for k, v in cat_ms.items()},
         "category_launches": cat_n,
         "whole_step": {"gflop_per_image": GFLOP_TRAIN.get(L), "achieved": step_tflops,

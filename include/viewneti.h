@@ -36,6 +36,10 @@ const char* vn_last_error(void);
 /* number of kernels launched by this library since load / since last reset (bench `gpu_launches`). */
 int64_t     vn_launch_count(void);
 void        vn_launch_count_reset(void);
+/* Programmatic dependent launch (on by default): every kernel is launched so that its prologue overlaps the tail of
+ * its predecessor on the stream.  Switch off to time kernels in isolation (per-kernel profiler durations otherwise
+ * include the time a kernel spends waiting for its predecessor). */
+void        vn_set_pdl(int enabled);
 
 /* ------------------------------------------------------------------------------------------------
  * tcgen05 / TMA GEMM and implicit-GEMM 3x3 convolution.

@@ -18,6 +18,8 @@ lat, t, tgt, ctx = make_inputs(SD21, nb, L, L, seed=1)
 plan.latents.copy_(lat); plan.timesteps.copy_(t); plan.target.copy_(tgt)
 for i in range(16):
     plan.ctx[0, i].copy_(ctx[f"CONTEXT_TENSOR_{i}"]); plan.ctx[1, i].copy_(ctx[f"CONTEXT_TENSOR_BYPASS_{i}"])
+from view_neti_b200 import ops as _ops
+_ops.set_pdl(False)
 for _ in range(2):
     plan.train_step()
 torch.cuda.synchronize()

@@ -62,6 +62,7 @@ SIGNATURES = {
     "vn_last_error": (C.c_char_p, []),
     "vn_launch_count": (C.c_int64, []),
     "vn_launch_count_reset": (None, []),
+    "vn_set_pdl": (None, [C.c_int]),
     "vn_gemm_workspace_bytes": (C.c_size_t, [_I, _I]),
     "vn_gemm": (C.c_int, [C.POINTER(GemmDesc), _P]),
     "vn_groupnorm_stats": (C.c_int, [_P, _L, _I, _I, _I, _I, _P, _P]),

@@ -128,6 +128,7 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tST = tmem_base, tdPT = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320;
   const long long sidx = ((long long)b * p.heads + h) * p.nq;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -301,6 +302,7 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdQ = tmem_base + 256;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -406,6 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
                                                                    const __grid_constant__ CUtensorMap tmV,
                                                                    const __grid_constant__ CUtensorMap tmdO,
                                                                    const BwdParams p) {
+  pdl_trigger();
   int id = blockIdx.x;
   if (id < p.n_dkv) {
     const int bx = id % p.ktiles; id /= p.ktiles;
@@ -423,6 +426,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, long long ldo, long long bso,
                                                          const bf16* __restrict__ d_o, long long lddo, long long bsdo,
                                                          float* __restrict__ delta, int nb, int heads, int nq) {
+  pdl_trigger();
+  pdl_wait();
   const long long nvec = (long long)nb * nq * heads * 8;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   float s = 0.f;
@@ -455,6 +460,8 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
 
 // fp64 scratch -> bf16 dk / dv, leaving the scratch zeroed for the next launch
 __global__ void __launch_bounds__(256) attn_dkv_finish_kernel(const BwdParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int C = p.heads * D;
   const long long per = (long long)p.nb * p.nk * C;
   const long long total = per / 2;
@@ -515,9 +522,8 @@ extern "C" int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s) {
     VN_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  attn_delta_kernel<<<(unsigned)vn_cdiv64((long long)d->nb * d->nq * d->heads * 8, 256), 256, 0, st>>>(
+  VN_LAUNCH(attn_delta_kernel, (unsigned)vn_cdiv64((long long)d->nb * d->nq * d->heads * 8, 256), 256, 0, st, 
       (const bf16*)d->o, d->ldo, d->bso, (const bf16*)d->d_o, d->lddo, d->bsdo, d->delta, d->nb, d->heads, d->nq);
-  VN_LAUNCH_OK();
   const int ktiles = vn_cdiv(d->nk, T), qtiles = vn_cdiv(d->nq, T);
   const long long base_ctas = (long long)ktiles * d->heads * d->nb;
   int splits = 1;
@@ -534,16 +540,13 @@ extern "C" int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s) {
   const int n_dq = d->dq ? qtiles * d->heads * d->nb : 0;
   const unsigned grid = (unsigned)(p.n_dkv + n_dq);
   if (splits > 1) {
-    attn_bwd_tc_kernel<true><<<grid, kThreads, SMEM, st>>>(tq, tk, tv, tdo, p);
-    VN_LAUNCH_OK();
+    VN_LAUNCH(attn_bwd_tc_kernel<true>, grid, kThreads, SMEM, st, tq, tk, tv, tdo, p);
     const long long pairs = (long long)d->nb * d->nk * d->heads * D / 2;
     int blocks = (int)vn_cdiv64(pairs, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    attn_dkv_finish_kernel<<<blocks, 256, 0, st>>>(p);
-    VN_LAUNCH_OK();
+    VN_LAUNCH(attn_dkv_finish_kernel, blocks, 256, 0, st, p);
   } else {
-    attn_bwd_tc_kernel<false><<<grid, kThreads, SMEM, st>>>(tq, tk, tv, tdo, p);
-    VN_LAUNCH_OK();
+    VN_LAUNCH(attn_bwd_tc_kernel<false>, grid, kThreads, SMEM, st, tq, tk, tv, tdo, p);
   }
   return 0;
 }

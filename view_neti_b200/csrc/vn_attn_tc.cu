@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
                                                                    const __grid_constant__ CUtensorMap tmK,
                                                                    const __grid_constant__ CUtensorMap tmV,
                                                                    const FwdParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -302,7 +304,6 @@ extern "C" int vn_attention_fwd(const vn_attn_desc* d, vn_stream_t s) {
     configured = true;
   }
   dim3 grid(vn_cdiv(d->nq, BQ), d->heads, d->nb);
-  attn_fwd_tc_kernel<<<grid, kThreads, SMEM_BYTES, (cudaStream_t)s>>>(tq, tk, tv, p);
-  VN_LAUNCH_OK();
+  VN_LAUNCH(attn_fwd_tc_kernel, grid, kThreads, SMEM_BYTES, (cudaStream_t)s, tq, tk, tv, p);
   return 0;
 }

@@ -38,6 +38,37 @@ void vn_count_launch(int n = 1);
     vn_count_launch();                                                                             \
   } while (0)
 
+// Every kernel of the library is launched with programmatic dependent launch (PDL): kernel N+1 may start while kernel N
+// is still running, executes its prologue (barrier init, TMEM allocation, tensor-map prefetch, constant staging) and then
+// blocks in pdl_wait() until kernel N has completed and flushed.  No kernel touches global memory produced by (or still
+// read by) a predecessor before pdl_wait().  The dependency is captured as a programmatic edge inside CUDA graphs.
+bool vn_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t vn_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = vn_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+#define VN_LAUNCH(kernel, grid, block, smem, stream, ...)                                              \
+  do {                                                                                                 \
+    cudaError_t _e = vn_launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__); \
+    if (_e != cudaSuccess) {                                                                           \
+      vn_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__);    \
+      return -3;                                                                                       \
+    }                                                                                                  \
+    vn_count_launch();                                                                                 \
+  } while (0)
+
 static inline int vn_cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t vn_cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -46,6 +77,10 @@ static inline int64_t vn_cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; 
 // ------------------------------------------------------------------------------------------------
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;
+
+// programmatic dependent launch (see vn_launch_pdl)
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -8,7 +8,11 @@
 namespace {
 thread_local char g_err[1024] = "";
 std::atomic<long long> g_launches{0};
+std::atomic<int> g_pdl{1};
 }  // namespace
+
+bool vn_pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
+extern "C" void vn_set_pdl(int enabled) { g_pdl.store(enabled ? 1 : 0); }
 
 void vn_set_error(const char* fmt, ...) {
   va_list ap;
@@ -27,6 +31,8 @@ namespace {
 
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y,
                                                             long long n) {
+  pdl_trigger();
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
     if (i + 4 <= n) {
@@ -43,6 +49,8 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restr
 
 __global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y,
                                                             long long n) {
+  pdl_trigger();
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
     if (i + 4 <= n) {
@@ -59,6 +67,8 @@ __global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const bf16* __restri
 __global__ void __launch_bounds__(256) copy2d_kernel(const bf16* __restrict__ src, long long lds,
                                                      const bf16* __restrict__ add, long long lda,
                                                      bf16* __restrict__ dst, long long ldd, long long rows, int vecs) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = rows * vecs;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -91,8 +101,7 @@ extern "C" int vn_cast_f32_bf16(const float* x, void* y, int64_t n, vn_stream_t 
   VN_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0,
            "vn_cast_f32_bf16: misaligned pointers");
   if (n <= 0) return 0;
-  cast_f32_bf16_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)s>>>(x, (bf16*)y, n);
-  VN_LAUNCH_OK();
+  VN_LAUNCH(cast_f32_bf16_kernel, grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)s, x, (bf16*)y, n);
   return 0;
 }
 
@@ -100,8 +109,7 @@ extern "C" int vn_cast_bf16_f32(const void* x, float* y, int64_t n, vn_stream_t 
   VN_CHECK((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0,
            "vn_cast_bf16_f32: misaligned pointers");
   if (n <= 0) return 0;
-  cast_bf16_f32_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)s>>>((const bf16*)x, y, n);
-  VN_LAUNCH_OK();
+  VN_LAUNCH(cast_bf16_f32_kernel, grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)s, (const bf16*)x, y, n);
   return 0;
 }
 
@@ -111,9 +119,8 @@ extern "C" int vn_copy2d(const void* src, int64_t lds, const void* add, int64_t 
            "vn_copy2d: cols and strides must be multiples of 8");
   if (rows <= 0 || cols <= 0) return 0;
   const int vecs = cols / 8;
-  copy2d_kernel<<<grid_for(rows * vecs, 256), 256, 0, (cudaStream_t)s>>>((const bf16*)src, lds, (const bf16*)add,
+  VN_LAUNCH(copy2d_kernel, grid_for(rows * vecs, 256), 256, 0, (cudaStream_t)s, (const bf16*)src, lds, (const bf16*)add,
                                                                           ldadd, (bf16*)dst, ldd, rows, vecs);
-  VN_LAUNCH_OK();
   return 0;
 }
 

@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
                                                                const __grid_constant__ CUtensorMap tmD,
                                                                const __grid_constant__ CUtensorMap tmR,
                                                                const GemmParams p) {
+  pdl_trigger();
   constexpr int A_BYTES = BM * BK * 2;            // 16 KB
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -204,6 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // everything above overlapped the previous kernel; global memory is touched only from here on
 
   // ---- work assignment ----
   const int num_tiles = p.m_tiles * p.n_tiles;
@@ -519,16 +521,22 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   cfg.attrs = attr;
-  cfg.numAttrs = 0;
-  if (SPLIT) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)p.splits;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.numAttrs = 1;
+  int na = 0;
+  if (vn_pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // PDL, see vn_launch_pdl
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
   }
+  if (SPLIT) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)p.splits;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.numAttrs = na;
   VN_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tr, p));
   vn_count_launch();
   return 0;

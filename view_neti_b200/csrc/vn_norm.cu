@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(512) gn_reduce_kernel(const bf16* __restrict__
                                                          const float* __restrict__ beta, float eps, int silu,
                                                          double* __restrict__ out, int hw, int C, int groups, int k,
                                                          int ppc) {
+  pdl_trigger();
+  pdl_wait();
   // Per-thread partial sums are fp32 in a fixed order; everything that is combined in a scheduling-dependent order
   // (threads of a CTA, CTAs of the grid) is accumulated in fp64, so the statistics are reproducible run to run.
   __shared__ double s_acc[kMaxGroups][2];
@@ -69,20 +71,29 @@ __global__ void __launch_bounds__(512) gn_reduce_kernel(const bf16* __restrict__
   const int c0 = v * 8;
   const int p0 = blockIdx.x * ppc;
   const int p1 = min(hw, p0 + ppc);
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) { s_acc[g][0] = 0.0; s_acc[g][1] = 0.0; }
-  float ga[8], be[8], mean[8], rstd[8];
-  if (MODE == 1) {
-    const double n = (double)cpg * (double)hw;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      ga[j] = gamma[c0 + j]; be[j] = beta[c0 + j];
-      const int g = (c0 + j) / cpg;
+  __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    s_acc[g][0] = 0.0; s_acc[g][1] = 0.0;
+    if (MODE == 1) {                       // the fp64 -> fp32 group constants are computed once per CTA
+      const double n = (double)cpg * (double)hw;
       const double m = stats[(b * groups + g) * 2] / n;
       const double var = fmax(stats[(b * groups + g) * 2 + 1] / n - m * m, 0.0);
-      mean[j] = (float)m; rstd[j] = (float)(1.0 / sqrt(var + (double)eps));
+      s_mean[g] = (float)m; s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
     }
   }
   __syncthreads();
+  float ga[8], be[8], mean[8], rstd[8];
+  if (MODE == 1) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
+    be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c0 + j) / cpg;
+      mean[j] = s_mean[g]; rstd[j] = s_rstd[g];
+    }
+  }
   float a0[8], a1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
@@ -168,6 +179,8 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const bf16* __restrict__ 
                                                         const bf16* __restrict__ add2, long long ld2,
                                                         bf16* __restrict__ y, long long ldy, int hw, int C,
                                                         int groups, int k, int ppc) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int cpg = C / groups;
   const int vecs = C >> 3;
@@ -175,31 +188,41 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const bf16* __restrict__ 
   const int c0 = v * 8;
   const int p0 = blockIdx.x * ppc;
   const int p1 = min(hw, p0 + ppc);
-  const double n = (double)cpg * (double)hw;
-  // per-channel constants:  fwd  y = x*A + B            (A = gamma*rstd, B = beta - mean*A)
-  //                         bwd  xh = x*R + M (R = rstd, M = -mean*rstd), z = xh*G + Bt, dx = R*(dz*G - S1 - xh*S2)
-  float A[8], Bc[8], G[8], S1[8], S2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int g = (c0 + j) / cpg;
+  // group constants once per CTA (fp64 statistics -> fp32), then per-channel constants from shared memory:
+  //   fwd  y = x*A + B            (A = gamma*rstd, B = beta - mean*A)
+  //   bwd  xh = x*R + M (R = rstd, M = -mean*rstd), z = xh*G + Bt, dx = R*(dz*G - S1 - xh*S2)
+  __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups], s_s1[kMaxGroups], s_s2[kMaxGroups];
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    const double n = (double)cpg * (double)hw;
     const double md = stats[(b * groups + g) * 2] / n;
     const double var = fmax(stats[(b * groups + g) * 2 + 1] / n - md * md, 0.0);
-    const float rs = (float)(1.0 / sqrt(var + (double)eps));
-    const float m = (float)md;
-    if (MODE == 0) {
-      A[j] = gamma[c0 + j] * rs;
-      Bc[j] = beta[c0 + j] - m * A[j];
-    } else {
-      A[j] = rs; Bc[j] = -m * rs;
-      G[j] = gamma[c0 + j];
-      S1[j] = (float)(red[(b * groups + g) * 2] / n);
-      S2[j] = (float)(red[(b * groups + g) * 2 + 1] / n);
+    s_mean[g] = (float)md;
+    s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    if (MODE == 1) {
+      s_s1[g] = (float)(red[(b * groups + g) * 2] / n);
+      s_s2[g] = (float)(red[(b * groups + g) * 2 + 1] / n);
     }
   }
-  float Bt[8];
-  if (MODE == 1) {
+  __syncthreads();
+  float A[8], Bc[8], G[8], S1[8], S2[8], Bt[8];
+  {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bet[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) Bt[j] = beta[c0 + j];
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c0 + j) / cpg;
+      const float m = s_mean[g], rs = s_rstd[g];
+      if (MODE == 0) {
+        A[j] = gam[j] * rs;
+        Bc[j] = bet[j] - m * A[j];
+      } else {
+        A[j] = rs; Bc[j] = -m * rs;
+        G[j] = gam[j]; Bt[j] = bet[j];
+        S1[j] = s_s1[g]; S2[j] = s_s2[g];
+      }
+    }
   }
   const bf16* xb = x + (long long)b * hw * ldx + c0;
   const bf16* db = MODE == 1 ? dy + (long long)b * hw * lddy + c0 : nullptr;
@@ -290,6 +313,8 @@ __global__ void __launch_bounds__(256) ln_kernel(const bf16* __restrict__ x, lon
                                                  float eps, float* __restrict__ stats, const bf16* __restrict__ add,
                                                  long long ldadd, bf16* __restrict__ y, long long ldy, int rows,
                                                  int C) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -404,6 +429,8 @@ __global__ void __launch_bounds__(256) geglu_kernel(const bf16* __restrict__ h, 
                                                     const bf16* __restrict__ dy, long long lddy,
                                                     bf16* __restrict__ out, long long ldo, long long total_vecs,
                                                     int F) {
+  pdl_trigger();
+  pdl_wait();
   const int vecs = F >> 3;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vecs;
        i += (long long)gridDim.x * blockDim.x) {
@@ -449,14 +476,13 @@ int ln_launch(const bf16* x, long long ldx, const bf16* dy, long long lddy, cons
   const int grid = vn_cdiv(rows, 8);
 #define VN_LN_CASE(NV)                                                                                              \
   case NV:                                                                                                          \
-    ln_kernel<MODE, NV><<<grid, 256, 0, s>>>(x, ldx, dy, lddy, gamma, beta, eps, stats, add, ldadd, y, ldy, rows, C); \
+    VN_LAUNCH((ln_kernel<MODE, NV>), grid, 256, 0, s, x, ldx, dy, lddy, gamma, beta, eps, stats, add, ldadd, y, ldy, rows, C); \
     break;
   switch (nv) {
     VN_LN_CASE(1) VN_LN_CASE(2) VN_LN_CASE(3) VN_LN_CASE(4) VN_LN_CASE(5) VN_LN_CASE(6) VN_LN_CASE(7) VN_LN_CASE(8)
     default: VN_CHECK(false, "layernorm: C=%d unsupported", C);
   }
 #undef VN_LN_CASE
-  VN_LAUNCH_OK();
   return 0;
 }
 
@@ -467,9 +493,8 @@ extern "C" int vn_groupnorm_stats(const void* x, int64_t ldx, int nb, int hw, in
   if (gn_check(C, groups, ldx)) return -1;
   const GNGeom g = gn_geom(nb, hw, C);
   dim3 grid(g.chunks, nb);
-  gn_reduce_kernel<0><<<grid, g.threads, 0, (cudaStream_t)s>>>((const bf16*)x, ldx, nullptr, 0, nullptr, nullptr,
+  VN_LAUNCH(gn_reduce_kernel<0>, grid, g.threads, 0, (cudaStream_t)s, (const bf16*)x, ldx, nullptr, 0, nullptr, nullptr,
                                                                  nullptr, 0.f, 0, stats, hw, C, groups, g.k, g.ppc);
-  VN_LAUNCH_OK();
   return 0;
 }
 
@@ -480,10 +505,9 @@ extern "C" int vn_groupnorm_apply(const void* x, int64_t ldx, const double* stat
   VN_CHECK(ldy % 8 == 0, "groupnorm: ldy must be a multiple of 8");
   const GNGeom g = gn_geom(nb, hw, C);
   dim3 grid(g.chunks, nb);
-  gn_apply_kernel<0><<<grid, g.threads, 0, (cudaStream_t)s>>>((const bf16*)x, ldx, nullptr, 0, stats, nullptr, gamma,
+  VN_LAUNCH(gn_apply_kernel<0>, grid, g.threads, 0, (cudaStream_t)s, (const bf16*)x, ldx, nullptr, 0, stats, nullptr, gamma,
                                                                 beta, eps, silu, nullptr, 0, nullptr, 0, (bf16*)y, ldy,
                                                                 hw, C, groups, g.k, g.ppc);
-  VN_LAUNCH_OK();
   return 0;
 }
 
@@ -494,9 +518,8 @@ extern "C" int vn_groupnorm_bwd_stats(const void* x, int64_t ldx, const void* dy
   VN_CHECK(lddy % 8 == 0, "groupnorm bwd: strides must be multiples of 8");
   const GNGeom g = gn_geom(nb, hw, C);
   dim3 grid(g.chunks, nb);
-  gn_reduce_kernel<1><<<grid, g.threads, 0, (cudaStream_t)s>>>((const bf16*)x, ldx, (const bf16*)dy, lddy, stats, gamma,
+  VN_LAUNCH(gn_reduce_kernel<1>, grid, g.threads, 0, (cudaStream_t)s, (const bf16*)x, ldx, (const bf16*)dy, lddy, stats, gamma,
                                                                  beta, eps, silu, red, hw, C, groups, g.k, g.ppc);
-  VN_LAUNCH_OK();
   return 0;
 }
 
@@ -508,11 +531,10 @@ extern "C" int vn_groupnorm_bwd_apply(const void* x, int64_t ldx, const void* dy
   VN_CHECK(lddy % 8 == 0 && lddx % 8 == 0 && ldadd1 % 8 == 0 && ldadd2 % 8 == 0, "groupnorm bwd: strides must be multiples of 8");
   const GNGeom g = gn_geom(nb, hw, C);
   dim3 grid(g.chunks, nb);
-  gn_apply_kernel<1><<<grid, g.threads, 0, (cudaStream_t)s>>>((const bf16*)x, ldx, (const bf16*)dy, lddy, stats, red,
+  VN_LAUNCH(gn_apply_kernel<1>, grid, g.threads, 0, (cudaStream_t)s, (const bf16*)x, ldx, (const bf16*)dy, lddy, stats, red,
                                                                 gamma, beta, eps, silu, (const bf16*)add1, ldadd1,
                                                                 (const bf16*)add2, ldadd2, (bf16*)dx, lddx, hw, C, groups,
                                                                 g.k, g.ppc);
-  VN_LAUNCH_OK();
   return 0;
 }
 
@@ -533,8 +555,7 @@ extern "C" int vn_geglu_fwd(const void* h, int64_t ldh, void* y, int64_t ldy, in
   VN_CHECK(F % 8 == 0 && ldh % 8 == 0 && ldy % 8 == 0, "geglu: F and strides must be multiples of 8");
   const long long total = (long long)rows * (F >> 3);
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  geglu_kernel<0><<<blocks, 256, 0, (cudaStream_t)s>>>((const bf16*)h, ldh, nullptr, 0, (bf16*)y, ldy, total, F);
-  VN_LAUNCH_OK();
+  VN_LAUNCH(geglu_kernel<0>, blocks, 256, 0, (cudaStream_t)s, (const bf16*)h, ldh, nullptr, 0, (bf16*)y, ldy, total, F);
   return 0;
 }
 
@@ -543,8 +564,7 @@ extern "C" int vn_geglu_bwd(const void* h, int64_t ldh, const void* dy, int64_t 
   VN_CHECK(F % 8 == 0 && ldh % 8 == 0 && lddy % 8 == 0 && lddh % 8 == 0, "geglu: F and strides must be multiples of 8");
   const long long total = (long long)rows * (F >> 3);
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  geglu_kernel<1><<<blocks, 256, 0, (cudaStream_t)s>>>((const bf16*)h, ldh, (const bf16*)dy, lddy, (bf16*)dh, lddh, total,
+  VN_LAUNCH(geglu_kernel<1>, blocks, 256, 0, (cudaStream_t)s, (const bf16*)h, ldh, (const bf16*)dy, lddy, (bf16*)dh, lddh, total,
                                                          F);
-  VN_LAUNCH_OK();
   return 0;
 }

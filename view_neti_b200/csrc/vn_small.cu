@@ -33,6 +33,8 @@ __device__ __forceinline__ uint4 pack8(const float (&a)[8]) {
 __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const bf16* __restrict__ x, long long ldx,
                                                              bf16* __restrict__ y, long long ldy, int nb, int H, int W,
                                                              int vecs) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)nb * (2 * H) * (2 * W) * vecs;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -50,6 +52,8 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const bf16* __restr
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const bf16* __restrict__ dy, long long lddy,
                                                              bf16* __restrict__ dx, long long lddx, int nb, int H,
                                                              int W, int vecs) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)nb * H * W * vecs;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -78,6 +82,8 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const bf16* __restr
 __global__ void __launch_bounds__(256) im2col_s2_kernel(const bf16* __restrict__ x, long long ldx,
                                                         bf16* __restrict__ col, int nb, int H, int W, int Ho, int Wo,
                                                         int C) {
+  pdl_trigger();
+  pdl_wait();
   const int vecs = C >> 3;
   const long long total = (long long)nb * Ho * Wo * 9 * vecs;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -99,6 +105,8 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const bf16* __restrict__
 __global__ void __launch_bounds__(256) col2im_s2_kernel(const bf16* __restrict__ dcol, const bf16* __restrict__ add,
                                                         long long ldadd, bf16* __restrict__ dx, long long lddx, int nb,
                                                         int H, int W, int Ho, int Wo, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int vecs = C >> 3;
   const long long total = (long long)nb * H * W * vecs;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -144,6 +152,8 @@ __global__ void __launch_bounds__(256) conv_thin_to_wide_kernel(const float* __r
                                                                 const float* __restrict__ wgt,
                                                                 const float* __restrict__ bias, bf16* __restrict__ y,
                                                                 long long ldy, int nb, int Ct, int H, int W, int Cw) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_w[];   // [9 taps][Ct][Cw]: a thread reads its 8 output channels as two 16-byte vectors
   for (int i = threadIdx.x; i < 9 * Ct * Cw; i += blockDim.x) {
     const int cw = i % Cw;
@@ -188,6 +198,8 @@ __global__ void __launch_bounds__(256) conv_wide_to_thin_kernel(const bf16* __re
                                                                 const float* __restrict__ wgt,
                                                                 const float* __restrict__ bias, float* __restrict__ y,
                                                                 int nb, int Cw, int H, int W, int Ct) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_w[];   // [9][Ct][Cw]
   for (int i = threadIdx.x; i < 9 * Ct * Cw; i += blockDim.x) {
     const int cw = i % Cw;
@@ -236,6 +248,8 @@ __global__ void __launch_bounds__(256) conv_wide_to_thin_kernel(const bf16* __re
 // time embedding pieces
 // ---------------------------------------------------------------------------------------------
 __global__ void timestep_sinusoid_kernel(const long long* __restrict__ t, float* __restrict__ out, int nb, int dim) {
+  pdl_trigger();
+  pdl_wait();
   const int half = dim >> 1;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nb * half) return;
@@ -252,6 +266,8 @@ __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, 
                                                    const bf16* __restrict__ Wt, const float* __restrict__ bias,
                                                    float* __restrict__ y, long long ldy, int nb, int N, int K,
                                                    int silu_in) {
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -295,6 +311,8 @@ __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, 
 __global__ void __launch_bounds__(1024) mse_kernel(const float* __restrict__ pred, const float* __restrict__ target,
                                                    long long n, float loss_scale, float* __restrict__ loss,
                                                    float* __restrict__ dpred) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_part[32];
   float acc = 0.f;
   const float g = 2.f * loss_scale / (float)n;
@@ -317,6 +335,8 @@ __global__ void __launch_bounds__(1024) mse_kernel(const float* __restrict__ pre
 __global__ void __launch_bounds__(256) cfg_ddim_kernel(float* __restrict__ latents, const float* __restrict__ eu,
                                                        const float* __restrict__ ec, long long n, float guidance,
                                                        float acp_t, float acp_prev, int vpred) {
+  pdl_trigger();
+  pdl_wait();
   const float sa = sqrtf(acp_t), sb = sqrtf(1.f - acp_t);
   const float pa = sqrtf(acp_prev), pb = sqrtf(1.f - acp_prev);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -348,9 +368,8 @@ extern "C" int vn_upsample2x_fwd(const void* x, int64_t ldx, void* y, int64_t ld
                                  vn_stream_t s) {
   VN_CHECK(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "upsample2x: C and strides must be multiples of 8");
   const long long total = (long long)nb * 4 * H * W * (C / 8);
-  upsample2x_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const bf16*)x, ldx, (bf16*)y, ldy, nb, H, W,
+  VN_LAUNCH(upsample2x_fwd_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)s, (const bf16*)x, ldx, (bf16*)y, ldy, nb, H, W,
                                                                             C / 8);
-  VN_LAUNCH_OK();
   return 0;
 }
 
@@ -358,9 +377,8 @@ extern "C" int vn_upsample2x_bwd(const void* dy, int64_t lddy, void* dx, int64_t
                                  vn_stream_t s) {
   VN_CHECK(C % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0, "upsample2x: C and strides must be multiples of 8");
   const long long total = (long long)nb * H * W * (C / 8);
-  upsample2x_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const bf16*)dy, lddy, (bf16*)dx, lddx, nb, H,
+  VN_LAUNCH(upsample2x_bwd_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)s, (const bf16*)dy, lddy, (bf16*)dx, lddx, nb, H,
                                                                             W, C / 8);
-  VN_LAUNCH_OK();
   return 0;
 }
 
@@ -368,9 +386,8 @@ extern "C" int vn_im2col_s2(const void* x, int64_t ldx, void* col, int nb, int H
   VN_CHECK(C % 8 == 0 && ldx % 8 == 0, "im2col_s2: C and stride must be multiples of 8");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long long total = (long long)nb * Ho * Wo * 9 * (C / 8);
-  im2col_s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const bf16*)x, ldx, (bf16*)col, nb, H, W, Ho, Wo,
+  VN_LAUNCH(im2col_s2_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)s, (const bf16*)x, ldx, (bf16*)col, nb, H, W, Ho, Wo,
                                                                        C);
-  VN_LAUNCH_OK();
   return 0;
 }
 
@@ -379,9 +396,8 @@ extern "C" int vn_col2im_s2(const void* dcol, const void* add, int64_t ldadd, vo
   VN_CHECK(C % 8 == 0 && lddx % 8 == 0 && (!add || ldadd % 8 == 0), "col2im_s2: C and strides must be multiples of 8");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long long total = (long long)nb * H * W * (C / 8);
-  col2im_s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const bf16*)dcol, (const bf16*)add, ldadd,
+  VN_LAUNCH(col2im_s2_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)s, (const bf16*)dcol, (const bf16*)add, ldadd,
                                                                        (bf16*)dx, lddx, nb, H, W, Ho, Wo, C);
-  VN_LAUNCH_OK();
   return 0;
 }
 
@@ -393,8 +409,7 @@ extern "C" int vn_conv_in_fwd(const float* x, const float* w, const float* bias,
   if (thin_smem_config(conv_thin_to_wide_kernel<0>, smem)) return -2;
   int blocks = grid_for(total, 256);
   if (blocks > 148 * 2) blocks = 148 * 2;
-  conv_thin_to_wide_kernel<0><<<blocks, 256, smem, (cudaStream_t)s>>>(x, w, bias, (bf16*)y, ldy, nb, Cin, H, W, Cout);
-  VN_LAUNCH_OK();
+  VN_LAUNCH(conv_thin_to_wide_kernel<0>, blocks, 256, smem, (cudaStream_t)s, x, w, bias, (bf16*)y, ldy, nb, Cin, H, W, Cout);
   return 0;
 }
 
@@ -406,8 +421,7 @@ extern "C" int vn_conv_out_bwd(const float* dy, const float* w, void* dx, int64_
   if (thin_smem_config(conv_thin_to_wide_kernel<1>, smem)) return -2;
   int blocks = grid_for(total, 256);
   if (blocks > 148 * 2) blocks = 148 * 2;
-  conv_thin_to_wide_kernel<1><<<blocks, 256, smem, (cudaStream_t)s>>>(dy, w, nullptr, (bf16*)dx, lddx, nb, Cout, H, W, Cin);
-  VN_LAUNCH_OK();
+  VN_LAUNCH(conv_thin_to_wide_kernel<1>, blocks, 256, smem, (cudaStream_t)s, dy, w, nullptr, (bf16*)dx, lddx, nb, Cout, H, W, Cin);
   return 0;
 }
 
@@ -425,16 +439,14 @@ extern "C" int vn_conv_out_fwd(const void* x, int64_t ldx, const float* w, const
   const long long npix = (long long)nb * H * W;
   int blocks = (int)((npix + 7) / 8);
   if (blocks > 148 * 2) blocks = 148 * 2;
-  conv_wide_to_thin_kernel<<<blocks, 256, smem, (cudaStream_t)s>>>((const bf16*)x, ldx, w, bias, y, nb, Cin, H, W, Cout);
-  VN_LAUNCH_OK();
+  VN_LAUNCH(conv_wide_to_thin_kernel, blocks, 256, smem, (cudaStream_t)s, (const bf16*)x, ldx, w, bias, y, nb, Cin, H, W, Cout);
   return 0;
 }
 
 extern "C" int vn_timestep_sinusoid(const int64_t* t, float* out, int nb, int dim, vn_stream_t s) {
   VN_CHECK(dim % 2 == 0, "timestep_sinusoid: dim must be even");
   const int total = nb * (dim / 2);
-  timestep_sinusoid_kernel<<<vn_cdiv(total, 128), 128, 0, (cudaStream_t)s>>>((const long long*)t, out, nb, dim);
-  VN_LAUNCH_OK();
+  VN_LAUNCH(timestep_sinusoid_kernel, vn_cdiv(total, 128), 128, 0, (cudaStream_t)s, (const long long*)t, out, nb, dim);
   return 0;
 }
 
@@ -442,24 +454,21 @@ extern "C" int vn_gemv(const float* x, int64_t ldx, const void* W, const float* 
                        int N, int K, int silu_in, vn_stream_t s) {
   VN_CHECK(nb >= 1 && nb <= kGemvMaxB, "gemv: batch %d not in [1,%d]", nb, kGemvMaxB);
   VN_CHECK(K % 8 == 0, "gemv: K must be a multiple of 8");
-  gemv_kernel<<<vn_cdiv(N, 8), 256, 0, (cudaStream_t)s>>>(x, ldx, (const bf16*)W, bias, y, ldy, nb, N, K, silu_in);
-  VN_LAUNCH_OK();
+  VN_LAUNCH(gemv_kernel, vn_cdiv(N, 8), 256, 0, (cudaStream_t)s, x, ldx, (const bf16*)W, bias, y, ldy, nb, N, K, silu_in);
   return 0;
 }
 
 extern "C" int vn_mse_loss(const float* pred, const float* target, int64_t n, float loss_scale, float* loss,
                            float* dpred, vn_stream_t s) {
   VN_CHECK(n > 0, "mse: empty input");
-  mse_kernel<<<1, 1024, 0, (cudaStream_t)s>>>(pred, target, n, loss_scale, loss, dpred);
-  VN_LAUNCH_OK();
+  VN_LAUNCH(mse_kernel, 1, 1024, 0, (cudaStream_t)s, pred, target, n, loss_scale, loss, dpred);
   return 0;
 }
 
 extern "C" int vn_cfg_ddim_step(float* latents, const float* eps_uncond, const float* eps_cond, int64_t n,
                                 float guidance, float acp_t, float acp_prev, int vpred, vn_stream_t s) {
   VN_CHECK(n > 0 && acp_t > 0.f, "cfg_ddim_step: bad arguments");
-  cfg_ddim_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)s>>>(latents, eps_uncond, eps_cond, n, guidance, acp_t,
+  VN_LAUNCH(cfg_ddim_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)s, latents, eps_uncond, eps_cond, n, guidance, acp_t,
                                                                   acp_prev, vpred);
-  VN_LAUNCH_OK();
   return 0;
 }

@@ -279,3 +279,8 @@ def launch_count() -> int:
 
 def launch_count_reset() -> None:
     _abi.load().vn_launch_count_reset()
+
+
+def set_pdl(enabled: bool) -> None:
+    """Programmatic dependent launch on/off (off only to time kernels in isolation)."""
+    _abi.load().vn_set_pdl(1 if enabled else 0)
