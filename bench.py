@@ -184,6 +184,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"          # NCCL's version banner goes to stdout; stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     L = args.latent
     cfg = SD21
@@ -245,8 +246,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         loss = F.mse_loss(pred.float(), d_tgt.float(), reduction="mean")   # :211-213
         loss.backward()                                                    # :214
         if world > 1:
-            flat.copy_(torch.cat([d_ctx["CONTEXT_TENSOR_0"].grad.view(-1)[:MAPPER_GRAD_ELEMS // 2],
-                                  d_ctx["CONTEXT_TENSOR_BYPASS_0"].grad.view(-1)[:MAPPER_GRAD_ELEMS // 2]]))
+            flat.copy_(torch.cat([d_ctx[k].grad.view(-1) for k in ("CONTEXT_TENSOR_0", "CONTEXT_TENSOR_BYPASS_0",
+                                                                   "CONTEXT_TENSOR_1", "CONTEXT_TENSOR_BYPASS_1")]
+                                 )[:MAPPER_GRAD_ELEMS])
             dist.all_reduce(flat)
         return float(loss.detach().cpu())                                 # D2H read of the step's result (:257)
 
@@ -305,10 +307,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     }
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample --------------------------------
-    per, n, threads, done_w = oracle_train_step_time(L, steps=1, warmup=0, budget_s=60.0)
-    cpu = {"value": 1.0 / per, "unit": "images/s", "cores": threads, "kind": "port",
-           "sample": f"{n} train image(s) (fwd + MSE + backward to 32 contexts) at {L}x{L} latents, fp32 PyTorch eager, "
-                     f"{threads} threads, no warm-up"}
+    cpu = None
+    if world == 1:
+        per, n, threads, done_w = oracle_train_step_time(L, steps=1, warmup=0, budget_s=60.0)
+        cpu = {"value": 1.0 / per, "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": f"{n} train image(s) (fwd + MSE + backward to 32 contexts) at {L}x{L} latents, fp32 PyTorch "
+                         f"eager, {threads} threads, no warm-up"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
