@@ -67,6 +67,21 @@ __device__ __forceinline__ void mma_kmn(uint32_t tacc, uint32_t a, uint32_t b, u
     umma_bf16(tacc, umma_desc_k_sw128(a + (k >> 2) * TILE_BYTES) + (uint64_t)((k & 3) * 2), desc_mn_sw128(b + k * 2048), id,
               (accumulate || k) ? 1u : 0u);
 }
+// half-tile variants (64 of the 128 columns / k-rows), used to pipeline the tensor pipe against the compute warps:
+// D[128 x 64] = A[128 x 64 k] * B[rows h*64.. of a 128-row K-major tile]^T
+__device__ __forceinline__ void mma_kk_half(uint32_t tacc, uint32_t a, uint32_t b, int h, uint32_t id64) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_bf16(tacc + (uint32_t)(h * 64), umma_desc_k_sw128(a) + (uint64_t)(k * 2),
+              umma_desc_k_sw128(b + h * 64 * 128) + (uint64_t)(k * 2), id64, k ? 1u : 0u);
+}
+// D[128 x 64] (+)= A[block h: 128 x 64 k, K-major] * B[k-rows h*64.. of the MN-major tile]
+__device__ __forceinline__ void mma_kmn_half(uint32_t tacc, uint32_t a, uint32_t b, int h, uint32_t id, bool accumulate) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_bf16(tacc, umma_desc_k_sw128(a + h * TILE_BYTES) + (uint64_t)(k * 2), desc_mn_sw128(b + (h * 4 + k) * 2048), id,
+              (accumulate || k) ? 1u : 0u);
+}
 __device__ __forceinline__ void ld64(uint32_t taddr, uint32_t (&v)[64]) {
   uint32_t(&c0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
   uint32_t(&c1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
@@ -100,10 +115,10 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
   uint64_t* kv_full = bars;
   uint64_t* st_full = bars + 1;                      // [2]
   uint64_t* st_empty = bars + 3;                     // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* acc_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* s_full = bars + 5;                       // [2] per 64-query half
+  uint64_t* p_full = bars + 7;                       // [2]
+  uint64_t* acc_full = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = bx * T, h = by;
@@ -115,9 +130,10 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     mbar_init(kv_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 256);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 256);
+    }
     mbar_init(acc_full, 1);
     mbar_fence_init();
   }
@@ -148,30 +164,41 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t id_s = idesc(T, T, 0);        // 128 x 128, both K-major
+      constexpr uint32_t id_s = idesc(T, 64, 0);       // 128 keys x 64 queries, both K-major
       constexpr uint32_t id_acc = idesc(T, D, 1);      // 128 x 64, B MN-major
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), adS = smem_u32(sdS);
+      // Software pipeline over 64-query halves: while the compute warps turn S^T/dP^T of one half into P^T/dS^T, the
+      // tensor pipe accumulates dV/dK of the other half and produces the next S^T/dP^T.
+      auto issue_sdp = [&](int i, int hh) {            // S^T_h = K Q_h^T, dP^T_h = V dO_h^T of query tile i
+        const uint32_t aQ = smem_u32(sStage + (i & 1) * DKV_STAGE_BYTES), adO = aQ + TILE_BYTES;
+        mma_kk_half(tST, aK, aQ, hh, id_s);
+        mma_kk_half(tdPT, aV, adO, hh, id_s);
+        umma_commit(&s_full[hh]);                      // in-order retirement: also covers dV/dK(i-1, h) -> sP/sdS block h free
+      };
       mbar_wait(kv_full, 0);
+      mbar_wait(&st_full[0], 0);
+      tc_fence_after();
+      issue_sdp(0, 0);
+      issue_sdp(0, 1);
       for (int i = 0; i < nt; ++i) {
-        const int s = i & 1;
-        const uint32_t aQ = smem_u32(sStage + s * DKV_STAGE_BYTES), adO = aQ + TILE_BYTES;
-        mbar_wait(&st_full[s], (i >> 1) & 1);
-        tc_fence_after();
-        // (TMEM S^T / dP^T are free: the compute warps arrived on p_full(i-1) before the accumulations below were issued)
-        mma_kk(tST, aK, aQ, id_s);                     // S^T  = K Q^T
-        mma_kk(tdPT, aV, adO, id_s);                   // dP^T = V dO^T
-        umma_commit(s_full);                           // (in-order retirement: also says dV/dK(i-1) are done -> sP/sdS free)
-        mbar_wait(p_full, i & 1);
-        tc_fence_after();
-        mma_kmn(tdV, aP, adO, id_acc, i > 0);          // dV += P^T dO
-        mma_kmn(tdK, adS, aQ, id_acc, i > 0);          // dK += dS^T Q
-        umma_commit(&st_empty[s]);
+        const uint32_t aQ = smem_u32(sStage + (i & 1) * DKV_STAGE_BYTES), adO = aQ + TILE_BYTES;
+        for (int hh = 0; hh < 2; ++hh) {
+          mbar_wait(&p_full[hh], i & 1);               // P^T_h / dS^T_h in smem; TMEM half h has been read
+          tc_fence_after();
+          mma_kmn_half(tdV, aP, adO, hh, id_acc, i > 0 || hh > 0);     // dV += P^T_h dO_h
+          mma_kmn_half(tdK, adS, aQ, hh, id_acc, i > 0 || hh > 0);     // dK += dS^T_h Q_h
+          if (hh == 1) umma_commit(&st_empty[i & 1]);
+          if (i + 1 < nt) {
+            if (hh == 0) { mbar_wait(&st_full[(i + 1) & 1], ((i + 1) >> 1) & 1); tc_fence_after(); }
+            issue_sdp(i + 1, hh);
+          }
+        }
       }
       umma_commit(acc_full);
     }
     __syncwarp();
   } else {
-    const int qd = warp & 3, hf = (warp - 2) >> 2;
+    const int qd = warp & 3, hf = (warp - 2) >> 2;     // hf: which 32 of the 64 queries of a half (and dV / dK at the end)
     const int r = qd * 32 + lane;                      // key row of the tile
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     const float sl2 = p.scale * kLog2e;
@@ -188,39 +215,43 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
     for (int i = 0; i < nt; ++i) {
       const int s = i & 1;
       const int q0 = (qt_begin + i) * T;
-      const float* lse = reinterpret_cast<const float*>(sStage + s * DKV_STAGE_BYTES + 2 * TILE_BYTES) + hf * 64;
-      const float* dl = lse + T;
       const float next_val = fetch(i + 1);
-      mbar_wait(s_full, i & 1);
-      tc_fence_after();
-      uint32_t sv[64], dp[64];
-      ld64(tST + lane_addr + hf * 64, sv);
-      ld64(tdPT + lane_addr + hf * 64, dp);
-      tmem_ld_wait();
-      const int qvalid = p.nq - q0 - hf * 64;          // queries of this half-tile that exist
-      uint8_t* prow = sP + hf * TILE_BYTES + r * 128;
-      uint8_t* drow = sdS + hf * TILE_BYTES + r * 128;
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        const int cbase = hh * 64 + hf * 32;           // first query column of this thread in the tile
+        const float* lse = reinterpret_cast<const float*>(sStage + s * DKV_STAGE_BYTES + 2 * TILE_BYTES) + cbase;
+        const float* dl = lse + T;
+        mbar_wait(&s_full[hh], i & 1);
+        tc_fence_after();
+        uint32_t sv[32], dp[32];
+        tmem_ld32(tST + lane_addr + cbase, sv);
+        tmem_ld32(tdPT + lane_addr + cbase, dp);
+        tmem_ld_wait();
+        const int qvalid = p.nq - q0 - cbase;          // queries of this slice that exist
+        uint8_t* prow = sP + hh * TILE_BYTES + r * 128;
+        uint8_t* drow = sdS + hh * TILE_BYTES + r * 128;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const float4 l0 = *reinterpret_cast<const float4*>(lse + g * 8), l1 = *reinterpret_cast<const float4*>(lse + g * 8 + 4);
-        const float4 d0 = *reinterpret_cast<const float4*>(dl + g * 8), d1 = *reinterpret_cast<const float4*>(dl + g * 8 + 4);
-        const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-        const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-        float pe[8], de[8];
+        for (int g = 0; g < 4; ++g) {
+          const float4 l0 = *reinterpret_cast<const float4*>(lse + g * 8), l1 = *reinterpret_cast<const float4*>(lse + g * 8 + 4);
+          const float4 d0 = *reinterpret_cast<const float4*>(dl + g * 8), d1 = *reinterpret_cast<const float4*>(dl + g * 8 + 4);
+          const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+          const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+          float pe[8], de[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float pv = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + c]), sl2, -lv[c]));
-          if (g * 8 + c >= qvalid) pv = 0.f;           // padded queries (their lse / delta slots hold stale data)
-          pe[c] = pv;
-          de[c] = pv * (__uint_as_float(dp[g * 8 + c]) - dv[c]) * p.scale;
-          if (g * 8 + c >= qvalid) de[c] = 0.f;
+          for (int c = 0; c < 8; ++c) {
+            float pv = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + c]), sl2, -lv[c]));
+            if (g * 8 + c >= qvalid) pv = 0.f;         // padded queries
+            pe[c] = pv;
+            de[c] = pv * (__uint_as_float(dp[g * 8 + c]) - dv[c]) * p.scale;
+            if (g * 8 + c >= qvalid) de[c] = 0.f;
+          }
+          store_row8(prow, hf * 4 + g, r, pe);
+          store_row8(drow, hf * 4 + g, r, de);
         }
-        store_row8(prow, g, r, pe);
-        store_row8(drow, g, r, de);
+        tc_fence_before();
+        fence_async_smem();
+        mbar_arrive(&p_full[hh]);
       }
-      tc_fence_before();
-      fence_async_smem();
-      mbar_arrive(p_full);
       reinterpret_cast<float*>(sStage + ((i + 1) & 1) * DKV_STAGE_BYTES + 2 * TILE_BYTES)[te] = next_val;
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
@@ -278,10 +309,10 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;                      // [2]
   uint64_t* kv_empty = bars + 3;                     // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* acc_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* s_full = bars + 5;                       // [2] per 64-key half
+  uint64_t* p_full = bars + 7;                       // [2]
+  uint64_t* acc_full = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = bx * T, h = by, b = bz;
@@ -290,9 +321,10 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 256);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 256);
+    }
     mbar_init(acc_full, 1);
     mbar_fence_init();
   }
@@ -320,22 +352,32 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t id_s = idesc(T, T, 0);
+      constexpr uint32_t id_s = idesc(T, 64, 0);       // 128 queries x 64 keys
       constexpr uint32_t id_acc = idesc(T, D, 1);
       const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), adS = smem_u32(sdS);
+      auto issue_sdp = [&](int j, int hh) {            // S_h = Q K_h^T, dP_h = dO V_h^T of key tile j
+        const uint32_t aK = smem_u32(sKV + (j & 1) * 2 * TILE_BYTES), aV = aK + TILE_BYTES;
+        mma_kk_half(tS, aQ, aK, hh, id_s);
+        mma_kk_half(tdP, adO, aV, hh, id_s);
+        umma_commit(&s_full[hh]);
+      };
       mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_sdp(0, 0);
+      issue_sdp(0, 1);
       for (int j = 0; j < nt; ++j) {
-        const int s = j & 1;
-        const uint32_t aK = smem_u32(sKV + s * 2 * TILE_BYTES), aV = aK + TILE_BYTES;
-        mbar_wait(&kv_full[s], (j >> 1) & 1);
-        tc_fence_after();
-        mma_kk(tS, aQ, aK, id_s);                      // S  = Q K^T
-        mma_kk(tdP, adO, aV, id_s);                    // dP = dO V^T
-        umma_commit(s_full);
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        mma_kmn(tdQ, adS, aK, id_acc, j > 0);          // dQ += dS K
-        umma_commit(&kv_empty[s]);
+        const uint32_t aK = smem_u32(sKV + (j & 1) * 2 * TILE_BYTES);
+        for (int hh = 0; hh < 2; ++hh) {
+          mbar_wait(&p_full[hh], j & 1);
+          tc_fence_after();
+          mma_kmn_half(tdQ, adS, aK, hh, id_acc, j > 0 || hh > 0);     // dQ += dS_h K_h
+          if (hh == 1) umma_commit(&kv_empty[j & 1]);
+          if (j + 1 < nt) {
+            if (hh == 0) { mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1); tc_fence_after(); }
+            issue_sdp(j + 1, hh);
+          }
+        }
       }
       umma_commit(acc_full);
     }
@@ -350,27 +392,31 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
     const float lse2 = row < p.nq ? p.lse[sidx + row] * kLog2e : INFINITY;     // padded query rows: P = 0
     const float dl = row < p.nq ? p.delta[sidx + row] : 0.f;
     for (int j = 0; j < nt; ++j) {
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      uint32_t sv[64], dp[64];
-      ld64(tS + lane_addr + hf * 64, sv);
-      ld64(tdP + lane_addr + hf * 64, dp);
-      tmem_ld_wait();
-      const int kvalid = p.nk - j * T - hf * 64;
-      uint8_t* drow = sdS + hf * TILE_BYTES + r * 128;
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        const int cbase = hh * 64 + hf * 32;           // first key column of this thread in the tile
+        mbar_wait(&s_full[hh], j & 1);
+        tc_fence_after();
+        uint32_t sv[32], dp[32];
+        tmem_ld32(tS + lane_addr + cbase, sv);
+        tmem_ld32(tdP + lane_addr + cbase, dp);
+        tmem_ld_wait();
+        const int kvalid = p.nk - j * T - cbase;
+        uint8_t* drow = sdS + hh * TILE_BYTES + r * 128;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        float de[8];
+        for (int g = 0; g < 4; ++g) {
+          float de[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float pv = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + c]), sl2, -lse2));
-          de[c] = (g * 8 + c < kvalid) ? pv * (__uint_as_float(dp[g * 8 + c]) - dl) * p.scale : 0.f;
+          for (int c = 0; c < 8; ++c) {
+            const float pv = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + c]), sl2, -lse2));
+            de[c] = (g * 8 + c < kvalid) ? pv * (__uint_as_float(dp[g * 8 + c]) - dl) * p.scale : 0.f;
+          }
+          store_row8(drow, hf * 4 + g, r, de);
         }
-        store_row8(drow, g, r, de);
+        tc_fence_before();
+        fence_async_smem();
+        mbar_arrive(&p_full[hh]);
       }
-      tc_fence_before();
-      fence_async_smem();
-      mbar_arrive(p_full);
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
