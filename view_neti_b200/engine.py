@@ -183,6 +183,11 @@ class _Plan:
         self.stat_f = self.buf("gn.stats", (n_gn, nb, cfg.norm_num_groups, 2), torch.float64)     # (sum x, sum x^2)
         self.stat_b = self.buf("gn.red", (n_gn, nb, cfg.norm_num_groups, 2), torch.float64)       # backward reductions
         self._stat_slots: Dict[str, int] = {}
+        # side stream: the 32 context projections (forward) and the 32 context-gradient GEMMs (backward) do not sit on
+        # the UNet's dependency chain; they run concurrently with it and are joined by events (captured in the graph)
+        self.side = torch.cuda.Stream(device=self.dev)
+        self.ev_kv = [torch.cuda.Event() for _ in range(self.n_layers)]
+        self.ev_dkv = [torch.cuda.Event() for _ in range(self.n_layers)]
         self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self.launches: Dict[str, int] = {}
         self._saved = False
@@ -205,6 +210,10 @@ class _Plan:
             i = self._stat_slots[name] = len([k for k in self._stat_slots if k.endswith(name[-3:])])
             assert i < arena.shape[0], "statistics arena too small"
         return arena[i]
+
+    def _xf_names(self) -> List[str]:
+        from .sd21 import cross_attn_layer_names
+        return cross_attn_layer_names(self.eng.cfg)
 
     def act_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self.bufs.values())
@@ -289,11 +298,9 @@ class _Plan:
         ops.layernorm_fwd(t1, t.ln[1][0], t.ln[1][1], cfg.ln_eps, n2, self.buf(name + ".ln2", (rows, 2), F32), rows)
         q2 = self.buf(name + ".q2", (nb, hw, c))
         ops.gemm(n2, t.q2f, q2, ws=self.ws)
-        ctxb = self.bufs["ctx.bf16"]
-        k2 = self.buf(name + ".k2", (nb, L, c))
+        k2 = self.buf(name + ".k2", (nb, L, c))           # projected on the side stream at the start of forward()
         v2 = self.buf(name + ".v2", (nb, L, c))
-        ops.gemm(ctxb[0, layer], t.k2f, k2, ws=self.ws)
-        ops.gemm(ctxb[1, layer], t.v2f, v2, ws=self.ws)
+        torch.cuda.current_stream().wait_event(self.ev_kv[layer])
         o2 = self.buf(name + ".o2", (nb, hw, c))
         ops.attention_fwd(q2, k2, v2, o2, self.buf(name + ".lse2", (nb, heads, hw), F32), heads)
         t2 = self.buf(name + ".t2", (nb, hw, c))
@@ -335,8 +342,12 @@ class _Plan:
         dv2 = self.buf(name + ".dv2", (nb, L, c))
         ops.attention_bwd(B[name + ".q2"], B[name + ".k2"], B[name + ".v2"], B[name + ".o2"], B[name + ".lse2"], do2,
                           self.buf(name + ".delta", (nb, heads, hw), F32), dq2, dk2, dv2, heads, dkv_acc=self.ws.dkv)
-        ops.gemm(dk2, t.k2b, self.d_ctx[0, layer], ws=self.ws)          # fp32 out: d CONTEXT_TENSOR_i
-        ops.gemm(dv2, t.v2b, self.d_ctx[1, layer], ws=self.ws)          # fp32 out: d CONTEXT_TENSOR_BYPASS_i
+        # d CONTEXT_TENSOR_l / d CONTEXT_TENSOR_BYPASS_l (fp32 out) leave the chain: side stream, joined in backward()
+        self.ev_dkv[layer].record(torch.cuda.current_stream())
+        self.side.wait_event(self.ev_dkv[layer])
+        with torch.cuda.stream(self.side):
+            ops.gemm(dk2, t.k2b, self.d_ctx[0, layer], ws=self.ws)
+            ops.gemm(dv2, t.v2b, self.d_ctx[1, layer], ws=self.ws)
         if first:
             return                                                       # nothing upstream depends on the contexts
         dn2 = dn3
@@ -374,7 +385,17 @@ class _Plan:
         temb = self.buf("temb.e2", (nb, cfg.time_embed_dim), F32)
         ops.gemv(e1, eng.te2[0], eng.te2[1], temb, silu_in=True)
         ops.gemv(temb, eng.temb_w, eng.temb_b, self.buf("temb.proj", (nb, eng.temb_total), F32), silu_in=True)
-        ops.cast_f32_bf16(self.ctx, self.buf("ctx.bf16", tuple(self.ctx.shape)))
+        ctxb = self.buf("ctx.bf16", tuple(self.ctx.shape))
+        ops.cast_f32_bf16(self.ctx, ctxb)
+        # K = to_k(CONTEXT_TENSOR_l), V = to_v(CONTEXT_TENSOR_BYPASS_l) for all 16 layers (xti_attention_processor.py:38-42)
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            for l, name in enumerate(self._xf_names()):
+                t = eng.xf[name]
+                ops.gemm(ctxb[0, l], t.k2f, self.buf(name + ".k2", (nb, self.L, t.c)), ws=self.ws)
+                ops.gemm(ctxb[1, l], t.v2f, self.buf(name + ".v2", (nb, self.L, t.c)), ws=self.ws)
+                self.ev_kv[l].record(self.side)
 
         # concat buffers of the up path; skip tensors are produced directly into their slices
         cats: Dict[Tuple[int, int], torch.Tensor] = {}
@@ -553,6 +574,7 @@ class _Plan:
                     layer -= 1
                     if first:
                         assert layer == -1
+                        torch.cuda.current_stream().wait_stream(self.side)
                         return self.d_ctx
                     dres = dro
                 else:
@@ -561,6 +583,7 @@ class _Plan:
                 dx = self.buf(f"bwd.skip.{k}", (nb, H * W, xin.shape[-1]))
                 self._res_bwd(name, xin, H, W, dres, dx, extra=dskip(k) if k > 0 else None)
                 dcur = dx
+        torch.cuda.current_stream().wait_stream(self.side)
         return self.d_ctx
 
     # ---- graphs -------------------------------------------------------------------------------------
