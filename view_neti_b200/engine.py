@@ -211,6 +211,14 @@ class _Plan:
             assert i < arena.shape[0], "statistics arena too small"
         return arena[i]
 
+    def _fork(self) -> torch.cuda.Event:
+        """Make the side stream wait for everything enqueued so far on the current stream; returns a fresh event
+        the caller records on the side stream and later waits on (fork / join, capturable)."""
+        e = torch.cuda.Event()
+        e.record(torch.cuda.current_stream())
+        self.side.wait_event(e)
+        return torch.cuda.Event()
+
     def _xf_names(self) -> List[str]:
         from .sd21 import cross_attn_layer_names
         return cross_attn_layer_names(self.eng.cfg)
@@ -244,12 +252,18 @@ class _Plan:
         h1 = self.buf(name + ".h1", (nb, hw, r.cout))
         tp = self.bufs["temb.proj"][:, r.temb_off:r.temb_off + r.cout]
         ops.conv3x3(a1.view(nb, H, W, r.cin), r.c1f, h1.view(nb, H, W, r.cout), bias=r.c1bias, rowbias=tp, ws=self.ws)
-        a2 = self._gn(name + ".gn2", h1, r.n2, eps, True, hw)
         if r.scf is not None:
+            # the 1x1 shortcut only meets the main chain again at conv2's residual input: side stream
             sc = self.buf(name + ".sc", (nb, hw, r.cout))
-            ops.gemm(x, r.scf, sc, bias=r.scbias, ws=self.ws)
+            ev = self._fork()
+            with torch.cuda.stream(self.side):
+                ops.gemm(x, r.scf, sc, bias=r.scbias, ws=self.ws)
+                ev.record(self.side)
         else:
-            sc = x
+            sc, ev = x, None
+        a2 = self._gn(name + ".gn2", h1, r.n2, eps, True, hw)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
         ops.conv3x3(a2.view(nb, H, W, r.cout), r.c2f, out.unflatten(1, (H, W)), bias=r.c2bias,
                     R=sc.unflatten(1, (H, W)), ws=self.ws)
 
@@ -259,17 +273,23 @@ class _Plan:
         nb, hw = self.nb, H * W
         eps = self.eng.cfg.norm_eps
         self.trace_b[name] = dout
+        ev = None
+        if r.scf is not None:                              # shortcut dgrad runs beside the conv2 -> GN2 -> conv1 chain
+            dsc = self.buf(name + ".dsc", (nb, hw, r.cin))
+            ev = self._fork()
+            with torch.cuda.stream(self.side):
+                ops.gemm(dout, r.scb, dsc, ws=self.ws)
+                ev.record(self.side)
+        else:
+            dsc = dout
         da2 = self.buf(name + ".da2", (nb, hw, r.cout))
         ops.conv3x3(dout.unflatten(1, (H, W)), r.c2b, da2.view(nb, H, W, r.cout), ws=self.ws)
         dh1 = self.buf(name + ".dh1", (nb, hw, r.cout))
         self._gn_bwd(name + ".gn2", self.bufs[name + ".h1"], da2, r.n2, eps, True, hw, dh1)
         da1 = self.buf(name + ".da1", (nb, hw, r.cin))
         ops.conv3x3(dh1.view(nb, H, W, r.cout), r.c1b, da1.view(nb, H, W, r.cin), ws=self.ws)
-        if r.scf is not None:
-            dsc = self.buf(name + ".dsc", (nb, hw, r.cin))
-            ops.gemm(dout, r.scb, dsc, ws=self.ws)
-        else:
-            dsc = dout
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
         self._gn_bwd(name + ".gn1", x, da1, r.n1, eps, True, hw, dx, add1=dsc, add2=extra)
 
     def _xf_fwd(self, name, layer, x, H, W, out):
