@@ -232,16 +232,22 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # ---- end to end through the drop-in API, host-resident inputs ------------------------------------------
     pin = lambda x: x.clone().pin_memory()      # noqa: E731
     h_lat, h_t, h_tgt = pin(lat), pin(t), pin(tgt)
-    h_ctx = {k: pin(v) for k, v in ctx.items() if torch.is_tensor(v)}
-    h2d = sum(x.numel() * x.element_size() for x in [h_lat, h_t, h_tgt, *h_ctx.values()])
+    nl = cfg.num_cross_layers
+    # the host keeps the 16 + 16 context tensors of a step in one pinned block (one H2D copy); the dict handed to the
+    # UNet holds per-layer views of it, exactly the reference's {"this_idx", "CONTEXT_TENSOR_i", "..._BYPASS_i"} protocol
+    h_ctx = pin(torch.stack([torch.stack([ctx[f"CONTEXT_TENSOR_{i}"] for i in range(nl)]),
+                             torch.stack([ctx[f"CONTEXT_TENSOR_BYPASS_{i}"] for i in range(nl)])]))
+    h2d = sum(x.numel() * x.element_size() for x in [h_lat, h_t, h_tgt, h_ctx])
 
     def e2e_step():
         d_lat = h_lat.to(dev, non_blocking=True)
         d_t = h_t.to(dev, non_blocking=True)
         d_tgt = h_tgt.to(dev, non_blocking=True)
+        d_all = h_ctx.to(dev, non_blocking=True)                       # stands in for the mapper/CLIP output
         d_ctx = {"this_idx": 0}
-        for k, v in h_ctx.items():
-            d_ctx[k] = v.to(dev, non_blocking=True).requires_grad_(True)
+        for i in range(nl):                                             # leaf tensors (views of the block, no copies)
+            d_ctx[f"CONTEXT_TENSOR_{i}"] = d_all[0, i].detach().requires_grad_(True)
+            d_ctx[f"CONTEXT_TENSOR_BYPASS_{i}"] = d_all[1, i].detach().requires_grad_(True)
         pred = model(d_lat, d_t, d_ctx).sample                       # coach.py:197-198
         loss = F.mse_loss(pred.float(), d_tgt.float(), reduction="mean")   # :211-213
         loss.backward()                                                    # :214

@@ -48,10 +48,9 @@ class _UNetFn(torch.autograd.Function):
         plan = model.engine.plan(nb, h, w)
         plan.latents.copy_(sample)
         plan.timesteps.copy_(timestep)
-        # contexts = K sources for the 16 layers followed by V sources
-        for i in range(n_ctx):
-            plan.ctx[0, i].copy_(contexts[i])
-            plan.ctx[1, i].copy_(contexts[n_ctx + i])
+        # contexts = K sources for the 16 layers followed by V sources; one fused multi-tensor copy into the plan
+        dst = [plan.ctx[0, i] for i in range(n_ctx)] + [plan.ctx[1, i] for i in range(n_ctx)]
+        torch._foreach_copy_(dst, [c.detach() for c in contexts])
         plan.run_forward()
         model._generation += 1
         ctx.plan, ctx.model, ctx.gen, ctx.n_ctx = plan, model, model._generation, n_ctx
@@ -68,10 +67,12 @@ class _UNetFn(torch.autograd.Function):
         plan.run_backward()
         n = ctx.n_ctx
         needs = ctx.needs_input_grad[4:]
+        g = plan.d_ctx.clone()                       # one copy out of the static plan; the grads are views of it
         grads: List[Optional[torch.Tensor]] = []
         for i in range(2 * n):
             if needs[i]:
-                grads.append(plan.d_ctx[i // n, i % n].to(ctx.dtypes[i], copy=True))
+                gi = g[i // n, i % n]
+                grads.append(gi if gi.dtype == ctx.dtypes[i] else gi.to(ctx.dtypes[i]))
             else:
                 grads.append(None)
         return (None, None, None, None, *grads)
