@@ -49,6 +49,25 @@ def test_unet_parity_sd21_256px(sd_model):
     assert r["grad_worst_rel"] < 3e-2
 
 
+def test_unet_parity_sd21_dtu_default_48x64(sd_model):
+    """The reference's DTU preprocessing is 512x384 (training/dataset.py:711-712) => 48x64 latents, N = 3072 tokens."""
+    r = run_parity(SD21, 1, 48, 64, model=sd_model)
+    assert r["eps_mse"] < EPS_MSE_TOL and r["grad_flat_rel"] < GRAD_FLAT_TOL_SD21, (r["eps_mse"], r["grad_flat_rel"])
+
+
+def test_forward_only_cfg_batch_72x96(sd_model):
+    """Inference shape of BASELINE config 5: 768x576 => 72x96 latents, uncond + cond batched as B = 2 (forward only)."""
+    from oracle.unet_sd21 import UNetOracle
+    lat, t, _, ctx = make_inputs(SD21, 2, 72, 96, seed=5)
+    t = torch.full((2,), 481, dtype=torch.int64)
+    unet = UNetOracle(SD21)
+    unet.load_state_dict(init_state_dict(SD21, 0))
+    with torch.no_grad():
+        ref = unet(lat, t, ctx_to(ctx, "cpu", requires_grad=False)).sample
+        out = sd_model(lat.cuda(), t.cuda(), ctx_to(ctx, "cuda", requires_grad=False)).sample
+    assert float(((out.float().cpu() - ref) ** 2).mean()) < EPS_MSE_TOL and rel(out, ref) < 2e-2
+
+
 def test_unet_parity_sd21_no_bypass_keys(sd_model):
     """dict without CONTEXT_TENSOR_BYPASS_i: V falls back to the K context (xti_attention_processor.py:39-42)."""
     r = run_parity(SD21, 1, 16, 16, bypass=False, model=sd_model)

@@ -208,7 +208,7 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
     auto fetch = [&](int i) -> float {
       const int q = (qt_begin + i) * T + (te & 127);
       if (i >= nt || q >= p.nq) return 0.f;
-      return te < 128 ? p.lse[sidx + q] * kLog2e : p.delta[sidx + q];
+      return te < 128 ? -p.lse[sidx + q] * kLog2e : -p.delta[sidx + q] * p.scale;     // pre-negated / pre-scaled
     };
     reinterpret_cast<float*>(sStage + 2 * TILE_BYTES)[te] = fetch(0);
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -230,20 +230,28 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
         const int qvalid = p.nq - q0 - cbase;          // queries of this slice that exist
         uint8_t* prow = sP + hh * TILE_BYTES + r * 128;
         uint8_t* drow = sdS + hh * TILE_BYTES + r * 128;
+        const float2 sl2v = make_float2(sl2, sl2), scv = make_float2(p.scale, p.scale);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
+          // nl = -lse * log2(e), nd = -delta * scale for 8 consecutive queries (packed f32x2 arithmetic, sm_100)
           const float4 l0 = *reinterpret_cast<const float4*>(lse + g * 8), l1 = *reinterpret_cast<const float4*>(lse + g * 8 + 4);
           const float4 d0 = *reinterpret_cast<const float4*>(dl + g * 8), d1 = *reinterpret_cast<const float4*>(dl + g * 8 + 4);
-          const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-          const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+          const float2 nl[4] = {make_float2(l0.x, l0.y), make_float2(l0.z, l0.w), make_float2(l1.x, l1.y), make_float2(l1.z, l1.w)};
+          const float2 nd[4] = {make_float2(d0.x, d0.y), make_float2(d0.z, d0.w), make_float2(d1.x, d1.y), make_float2(d1.z, d1.w)};
           float pe[8], de[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float pv = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + c]), sl2, -lv[c]));
-            if (g * 8 + c >= qvalid) pv = 0.f;         // padded queries
-            pe[c] = pv;
-            de[c] = pv * (__uint_as_float(dp[g * 8 + c]) - dv[c]) * p.scale;
-            if (g * 8 + c >= qvalid) de[c] = 0.f;
+          for (int c = 0; c < 4; ++c) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[g * 8 + 2 * c]), __uint_as_float(sv[g * 8 + 2 * c + 1])), sl2v, nl[c]);
+            const float2 pp = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+            const float2 tt = __ffma2_rn(make_float2(__uint_as_float(dp[g * 8 + 2 * c]), __uint_as_float(dp[g * 8 + 2 * c + 1])), scv, nd[c]);
+            const float2 dd = __fmul2_rn(pp, tt);
+            pe[2 * c] = pp.x; pe[2 * c + 1] = pp.y;
+            de[2 * c] = dd.x; de[2 * c + 1] = dd.y;
+          }
+          if (qvalid < 32) {                           // ragged last query tile: padded queries contribute nothing
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (g * 8 + c >= qvalid) { pe[c] = 0.f; de[c] = 0.f; }
           }
           store_row8(prow, hf * 4 + g, r, pe);
           store_row8(drow, hf * 4 + g, r, de);
@@ -389,8 +397,8 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
     const float sl2 = p.scale * kLog2e;
     const int row = q0 + r;
     const long long sidx = ((long long)b * p.heads + h) * p.nq;
-    const float lse2 = row < p.nq ? p.lse[sidx + row] * kLog2e : INFINITY;     // padded query rows: P = 0
-    const float dl = row < p.nq ? p.delta[sidx + row] : 0.f;
+    const float nlse2 = row < p.nq ? -p.lse[sidx + row] * kLog2e : -INFINITY;  // padded query rows: P = 0
+    const float ndl = row < p.nq ? -p.delta[sidx + row] * p.scale : 0.f;
     for (int j = 0; j < nt; ++j) {
 #pragma unroll 1
       for (int hh = 0; hh < 2; ++hh) {
@@ -403,13 +411,23 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
         tmem_ld_wait();
         const int kvalid = p.nk - j * T - cbase;
         uint8_t* drow = sdS + hh * TILE_BYTES + r * 128;
+        const float2 sl2v = make_float2(sl2, sl2), scv = make_float2(p.scale, p.scale);
+        const float2 nlv = make_float2(nlse2, nlse2), ndv = make_float2(ndl, ndl);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float de[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float pv = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + c]), sl2, -lse2));
-            de[c] = (g * 8 + c < kvalid) ? pv * (__uint_as_float(dp[g * 8 + c]) - dl) * p.scale : 0.f;
+          for (int c = 0; c < 4; ++c) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[g * 8 + 2 * c]), __uint_as_float(sv[g * 8 + 2 * c + 1])), sl2v, nlv);
+            const float2 pp = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+            const float2 tt = __ffma2_rn(make_float2(__uint_as_float(dp[g * 8 + 2 * c]), __uint_as_float(dp[g * 8 + 2 * c + 1])), scv, ndv);
+            const float2 dd = __fmul2_rn(pp, tt);
+            de[2 * c] = dd.x; de[2 * c + 1] = dd.y;
+          }
+          if (kvalid < 32) {                           // ragged last key tile
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (g * 8 + c >= kvalid) de[c] = 0.f;
           }
           store_row8(drow, hf * 4 + g, r, de);
         }

@@ -173,10 +173,12 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
       tmem_ld32(tPV, r0);
       tmem_ld32(tPV + 32, r1);
       tmem_ld_wait();
+      const float2 av = make_float2(alpha, alpha);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        o[i] = fmaf(o[i], alpha, __uint_as_float(r0[i]));
-        o[32 + i] = fmaf(o[32 + i], alpha, __uint_as_float(r1[i]));
+      for (int i = 0; i < 32; i += 2) {                  // packed f32x2 arithmetic (sm_100)
+        const float2 a = __ffma2_rn(make_float2(o[i], o[i + 1]), av, make_float2(__uint_as_float(r0[i]), __uint_as_float(r0[i + 1])));
+        const float2 c = __ffma2_rn(make_float2(o[32 + i], o[33 + i]), av, make_float2(__uint_as_float(r1[i]), __uint_as_float(r1[i + 1])));
+        o[i] = a.x; o[i + 1] = a.y; o[32 + i] = c.x; o[33 + i] = c.y;
       }
     };
 
@@ -208,20 +210,25 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
       const float mref = (mx == -INFINITY) ? 0.f : mx;
       const float alpha = ex2_approx(m_run - mref);    // first tile: ex2(-inf) = 0
       m_run = mx;
-      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+      float2 rsa = make_float2(0.f, 0.f), rsb = make_float2(0.f, 0.f);
+      const float2 sl2v = make_float2(sl2, sl2), nm = make_float2(-mref, -mref);
       uint8_t* prow = sP + ((j & 1) * 2 + hf) * TILE_BYTES + r * 128;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         float e[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(s[g * 8 + i]), sl2, -mref));
-        rs0 += e[0] + e[4]; rs1 += e[1] + e[5]; rs2 += e[2] + e[6]; rs3 += e[3] + e[7];
+        for (int i = 0; i < 8; i += 2) {
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[g * 8 + i]), __uint_as_float(s[g * 8 + i + 1])), sl2v, nm);
+          e[i] = ex2_approx(x.x); e[i + 1] = ex2_approx(x.y);
+        }
+        rsa = __fadd2_rn(rsa, __fadd2_rn(make_float2(e[0], e[1]), make_float2(e[2], e[3])));
+        rsb = __fadd2_rn(rsb, __fadd2_rn(make_float2(e[4], e[5]), make_float2(e[6], e[7])));
         uint4 w;
         w.x = pack_bf162(e[0], e[1]); w.y = pack_bf162(e[2], e[3]);
         w.z = pack_bf162(e[4], e[5]); w.w = pack_bf162(e[6], e[7]);
         *reinterpret_cast<uint4*>(prow + ((g ^ (r & 7)) << 4)) = w;
       }
-      l_run = l_run * alpha + ((rs0 + rs1) + (rs2 + rs3));
+      l_run = l_run * alpha + ((rsa.x + rsa.y) + (rsb.x + rsb.y));
       tc_fence_before();                 // my TMEM reads of S(j) are done
       fence_async_smem();                // my P writes are visible to the tensor core (async proxy)
       mbar_arrive(&p_full[j & 1]);
