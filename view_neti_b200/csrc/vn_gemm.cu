@@ -76,7 +76,6 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -410,7 +409,8 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
         if (lane == 0) mbar_arrive(&tempty_bar[as]);
       }
     }
-    if (tma_epi && threadIdx.x == 64) tma_store_wait_all();   // global writes complete before the CTA exits
+    // (the bulk stores were drained from shared memory by wait_group.read above; their global visibility is ordered by
+    //  grid completion, which is what the next kernel's griddepcontrol.wait / stream order waits for)
   }
 
   if (SPLIT) {
