@@ -321,6 +321,13 @@ def all_checks():
     for bn in (64, 128, 256):
         for sp in (1, 2, 4, 8):
             L.append((check_gemm, dict(M=512, N=640, K=1280, bias=True, rowbias=True, resid=True, force_bn=bn, force_split=sp)))
+    # multicast clusters along M (force_split bits 4..7 = cluster size)
+    for bn in (64, 128, 256):
+        for mc in (1, 2, 4):
+            L.append((check_gemm, dict(M=1536, N=640, K=640, bias=True, resid=True, force_bn=bn, force_split=1 + 16 * mc)))
+    L.append((check_gemm, dict(M=300, N=328, K=192, bias=True, resid=True, force_bn=128, force_split=1 + 16 * 2)))
+    L.append((check_gemm, dict(M=700, N=328, K=192, bias=True, rowbias=True, resid=True, force_bn=64, force_split=1 + 16 * 4)))
+    L.append((check_gemm, dict(M=20000, N=320, K=320, bias=True, resid=True, force_bn=128, force_split=1 + 16 * 4)))
     L.append((check_gemm, dict(M=200, N=328, K=1024, bias=True, resid=True, force_bn=128, force_split=4)))
     L.append((check_gemm, dict(M=77, N=1024, K=1280, out_fp32=True, force_bn=64, force_split=8)))
     L.append((check_gemm, dict(M=6000, N=2560, K=320, bias=True, resid=True, force_bn=256, force_split=1)))
@@ -336,6 +343,9 @@ def all_checks():
     L.append((check_conv, dict(nb=2, H=8, W=8, Cc=1280, N=1280, force_bn=128, force_split=8, rowbias=True, resid=True)))
     L.append((check_conv, dict(nb=3, H=64, W=64, Cc=64, N=192, force_bn=64, force_split=1, rowbias=True, resid=True)))
     L.append((check_conv, dict(nb=1, H=12, W=16, Cc=128, N=128, force_bn=128, force_split=2, rowbias=True, resid=True)))
+    L.append((check_conv, dict(nb=3, H=32, W=32, Cc=64, N=192, force_bn=64, force_split=1 + 16 * 4, rowbias=True, resid=True)))
+    L.append((check_conv, dict(nb=1, H=24, W=16, Cc=128, N=320, force_bn=128, force_split=1 + 16 * 2, rowbias=True, resid=True)))
+    L.append((check_conv, dict(nb=1, H=64, W=64, Cc=320, N=320, force_bn=256, force_split=1 + 16 * 4, rowbias=True, resid=True)))
     for (nb, hw, Cc, silu) in [(1, 4096, 320, True), (2, 1024, 640, False), (1, 64, 2560, True), (1, 256, 1920, True)]:
         L.append((check_groupnorm, dict(nb=nb, hw=hw, Cc=Cc, silu=silu, eps=1e-5 if silu else 1e-6)))
     for (rows, Cc) in [(4096, 320), (1024, 640), (77, 1280)]:

@@ -16,6 +16,10 @@
 //                 stages, so the epilogue of tile i overlaps the main loop of tile i+1.
 //     warps 2-5 : epilogue — tcgen05.ld, + bias / time-embedding row-bias / residual (read from smem), bf16 pack into
 //                 the swizzled staging tile, TMA store (clips the M / N tails).
+//     MC > 1   : thread-block clusters of MC CTAs along M share every B (weight) tile: each CTA loads 1/MC of it and
+//                TMA-MULTICASTS the slice into the shared memory of all CTAs of the cluster, so an SM requests
+//                A + B/MC bytes per k-block instead of A + B (the operand stream out of L2, not the tensor pipe, bounds
+//                these tiles).  A stage is released to the producers by a multicast tcgen05.commit from every CTA.
 //   SPLIT-K (SPLIT = true): for few-tile / long-K problems (deep UNet levels, M = 64..1024).  A thread-block CLUSTER of
 //     S in {2,4,8} CTAs shares one output tile, each CTA accumulates K/S in its own TMEM; partials are exchanged
 //     through DISTRIBUTED SHARED MEMORY (st.shared::cluster), CTA r reduces rows [r*128/S, (r+1)*128/S) and runs
@@ -43,6 +47,7 @@ struct GemmParams {
   const bf16* R; long long ldr;
   int out_fp32;
   int use_tma_epilogue;
+  int nbimg;            // images (conv mode); tiles of a padded cluster slot may decode to img >= nbimg
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -61,6 +66,19 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// arrive on the mbarrier at this offset in every CTA of `mask` once all previously issued tcgen05.mma have completed
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -147,7 +165,7 @@ __device__ __forceinline__ bool tile_row(const GemmParams& p, const TileCoord& c
   return (r < p.rows_a) && (h < p.H) && (w < p.W);
 }
 
-template <int BN, int STAGES, bool SPLIT>
+template <int BN, int STAGES, bool SPLIT, int MC>
 __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmD,
@@ -163,6 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
                           : (ACC_STAGES * BN) <= 256 ? 256 : 512;
   static_assert(STAGE_BYTES % 1024 == 0 && BN % 64 == 0 && ACC_STAGES * BN <= 512, "tile configuration");
   static_assert(!SPLIT || STAGES * STAGE_BYTES >= BM * BN * 4, "exchange buffer must fit in the pipeline stages");
+  static_assert(MC == 1 || (!SPLIT && BN % MC == 0), "multicast clusters only in the persistent schedule");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -189,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MC);                 // every CTA of the multicast cluster must have consumed the stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -201,7 +220,8 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  if (MC > 1) cluster_sync_all();                  // peers' barriers must exist before a multicast can signal them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();          // everything above overlapped the previous kernel; global memory is touched only from here on
@@ -209,9 +229,8 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
   // ---- work assignment ----
   const int num_tiles = p.m_tiles * p.n_tiles;
   int tile_begin, tile_step, kb_begin, nkb;
-  uint32_t crank = 0;
+  uint32_t crank = (SPLIT || MC > 1) ? cluster_ctarank() : 0;
   if (SPLIT) {
-    crank = cluster_ctarank();
     tile_begin = blockIdx.x / p.splits;
     tile_step = num_tiles;                       // exactly one tile per cluster
     kb_begin = (int)crank * p.kb_per_split;
@@ -245,7 +264,14 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
             const int dy = tap / 3, dx = tap - dy * 3;
             tma_load_4d(sa, &tmA, &full_bar[s], cb * BK, c.w0 + dx - 1, c.h0 + dy - 1, c.img);
           }
-          tma_load_2d(sa + A_BYTES, &tmB, &full_bar[s], kb * BK, c.n0);
+          if (MC == 1) {
+            tma_load_2d(sa + A_BYTES, &tmB, &full_bar[s], kb * BK, c.n0);
+          } else {
+            // my 1/MC slice of the B tile goes to every CTA of the cluster (same n-tile, consecutive m-tiles)
+            constexpr int SLICE = BN / MC;
+            tma_load_2d_mc(sa + A_BYTES + (int)crank * SLICE * 128, &tmB, &full_bar[s], kb * BK, c.n0 + (int)crank * SLICE,
+                           (uint16_t)((1u << MC) - 1));
+          }
         }
         if (tma_epi && p.R) {
           // residual tile -> staging, once the previous tile's store has finished reading it
@@ -287,7 +313,8 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
             // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
             umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);            // frees this smem stage when the MMAs above have read it
+          if (MC == 1) umma_commit(&empty_bar[s]);   // frees this smem stage when the MMAs above have read it
+          else umma_commit_mc(&empty_bar[s], (uint16_t)((1u << MC) - 1));
         }
         umma_commit(&tfull_bar[as]);             // accumulator complete
       }
@@ -315,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
         float v = 0.f;
         if (col < BN && c.n0 + col < p.N) {
           if (p.bias) v = __ldg(p.bias + c.n0 + col);
-          if (smem_rowbias) v += __ldg(p.rowbias + (long long)c.img * p.ld_rowbias + c.n0 + col);
+          if (smem_rowbias) v += __ldg(p.rowbias + (long long)min(c.img, p.nbimg - 1) * p.ld_rowbias + c.n0 + col);
         }
         bv[u] = v;
       }
@@ -474,7 +501,8 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (MC > 1) cluster_sync_all();                  // no CTA leaves while a peer may still signal its barriers
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -505,16 +533,34 @@ constexpr int smem_bytes() {
   return STAGES * (BM * BK * 2 + BN * BK * 2) + (SPLIT ? 0 : BM * BN * 2) + BN * 4 + (2 * STAGES + 6) * 8 + 16 + 1024;
 }
 
-template <int BN, int STAGES, bool SPLIT>
+template <int BN, int STAGES, bool SPLIT, int MC = 1>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr,
            const GemmParams& p, int grid_x, cudaStream_t st) {
   static bool configured = false;
+  static int max_clusters = 0;
   constexpr int smem = smem_bytes<BN, STAGES, SPLIT>();
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  auto kern = vn_gemm_kernel<BN, STAGES, SPLIT>;
+  auto kern = vn_gemm_kernel<BN, STAGES, SPLIT, MC>;
   if (!configured) {
     VN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (MC > 1) {
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3((unsigned)(MC * 64), 1, 1);
+      q.blockDim = dim3(kThreads, 1, 1);
+      q.dynamicSmemBytes = smem;
+      cudaLaunchAttribute a[1];
+      a[0].id = cudaLaunchAttributeClusterDimension;
+      a[0].val.clusterDim.x = MC; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
+      q.attrs = a; q.numAttrs = 1;
+      VN_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q));
+      VN_CHECK(max_clusters > 0, "vn_gemm: no cluster of %d CTAs fits on this device", MC);
+    }
     configured = true;
+  }
+  if (MC > 1) {                                  // persistent clusters: never more than can be co-resident
+    int clusters = grid_x / MC;
+    if (clusters > max_clusters) clusters = max_clusters;
+    grid_x = clusters * MC;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid_x, 1, 1);
@@ -529,9 +575,9 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
-  if (SPLIT) {
+  if (SPLIT || MC > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = (unsigned)p.splits;
+    attr[na].val.clusterDim.x = SPLIT ? (unsigned)p.splits : (unsigned)MC;
     attr[na].val.clusterDim.y = 1;
     attr[na].val.clusterDim.z = 1;
     ++na;
@@ -642,8 +688,10 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
 
   int bn = 128, splits = 1;
   choose_tiling(p.m_tiles, d->N, p.kb_total, true, &bn, &splits);
+  // force_split: low 4 bits = split-K cluster size (0 = auto), bits 4..7 = multicast cluster size MC (0 = auto)
+  const int force_s = d->force_split & 15, force_mc = (d->force_split >> 4) & 15;
   if (d->force_bn) bn = d->force_bn;
-  if (d->force_split) splits = d->force_split;
+  if (force_s) splits = force_s;
   VN_CHECK(bn == 64 || bn == 128 || bn == 256, "vn_gemm: unsupported BN %d (64, 128, 256)", bn);
   VN_CHECK(splits == 1 || splits == 2 || splits == 4 || splits == 8, "vn_gemm: unsupported split %d (1, 2, 4, 8)", splits);
   while (splits > 1 && (vn_cdiv(p.kb_total, splits) < 1 || p.kb_total <= (splits - 1) * vn_cdiv(p.kb_total, splits)))
@@ -651,11 +699,23 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
   p.kb_per_split = vn_cdiv(p.kb_total, splits);
   p.splits = splits;
   p.n_tiles = vn_cdiv(d->N, bn);
+  p.nbimg = d->mode == 1 ? d->nb : 1;
+  // multicast clusters along M (persistent schedule only): every CTA of a cluster works on the same n-tile
+  int mc = 1;
+  if (splits == 1) {
+    // Measured on B200 (scripts/gemm_bench.py, FORCE_SPLIT=1+16*MC): multicast does not change the time of any layer
+    // shape - the tiles are bound by the bytes LANDING in an SM per k-block (A + B either way), not by the requests
+    // it issues - so it is opt-in only (force_split bits 4..7) and the default is MC = 1.
+    mc = force_mc ? force_mc : 1;
+    VN_CHECK(mc == 1 || mc == 2 || mc == 4, "vn_gemm: unsupported multicast cluster size %d (1, 2, 4)", mc);
+    if (mc > p.m_tiles) mc = p.m_tiles >= 2 ? 2 : 1;
+    p.m_tiles = vn_cdiv(p.m_tiles, mc) * mc;       // padded slots decode to out-of-range tiles (TMA zero-fill / clipping)
+  }
   const int tiles = p.m_tiles * p.n_tiles;
   {
     cuuint64_t dims[2] = {(cuuint64_t)d->K, (cuuint64_t)d->N};
     cuuint64_t str[1] = {(cuuint64_t)d->ldb * 2};
-    cuuint32_t box[2] = {BK, (cuuint32_t)bn};
+    cuuint32_t box[2] = {BK, (cuuint32_t)(bn / mc)};
     if (make_map(&tb, d->B, 2, dims, str, box)) return -1;
   }
   // staged TMA-store epilogue for bf16 outputs of the persistent schedule
@@ -680,15 +740,22 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
     }
   }
   if (splits == 1) {
-    const int grid = tiles < num_sms() ? tiles : num_sms();
+    int grid = tiles < num_sms() ? tiles : num_sms();
+    grid = (grid / mc) * mc;
+#define VN_GEMM_CASE(BN_, ST_)                                                               \
+  case BN_:                                                                                  \
+    if (mc == 4) return launch<BN_, ST_, false, 4>(ta, tb, td, tr, p, grid, st);             \
+    if (mc == 2) return launch<BN_, ST_, false, 2>(ta, tb, td, tr, p, grid, st);             \
+    return launch<BN_, ST_, false, 1>(ta, tb, td, tr, p, grid, st);
     switch (bn) {
-      case 64: return launch<64, 6, false>(ta, tb, td, tr, p, grid, st);
-      case 128:
-        if (getenv("VN_GEMM_STAGES3")) return launch<128, 3, false>(ta, tb, td, tr, p, grid, st);
-        if (getenv("VN_GEMM_STAGES2")) return launch<128, 2, false>(ta, tb, td, tr, p, grid, st);
-        return launch<128, 5, false>(ta, tb, td, tr, p, grid, st);
-      default: return launch<256, 3, false>(ta, tb, td, tr, p, grid, st);
+      VN_GEMM_CASE(64, 6)
+      VN_GEMM_CASE(128, 5)
+      default:
+        if (mc == 4) return launch<256, 3, false, 4>(ta, tb, td, tr, p, grid, st);
+        if (mc == 2) return launch<256, 3, false, 2>(ta, tb, td, tr, p, grid, st);
+        return launch<256, 3, false, 1>(ta, tb, td, tr, p, grid, st);
     }
+#undef VN_GEMM_CASE
   }
   const int grid = tiles * splits;
   switch (bn) {
