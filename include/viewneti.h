@@ -176,6 +176,28 @@ int vn_cfg_ddim_step(float* latents, const float* eps_uncond, const float* eps_c
                      float guidance, float acp_t, float acp_prev, int vpred, vn_stream_t s);
 int vn_memset_zero(void* p, size_t bytes, vn_stream_t s);
 
+/* ------------------------------------------------------------------------------------------------
+ * NeTI mapper (SURVEY.md 8f "next" #2) - the module the context gradients finally land in.
+ * reference models/neti_mapper.py:165-197,416-438,542-611 (arch_view_net 15) + models/positional_encoding.py:174-195:
+ *   enc = [sin(Wf x) | cos(Wf x)];  a1 = LeakyReLU(LN(W1 enc + b1));  a2 = LeakyReLU(LN(W2 a1 + b2));  y = W3 a2 + b3
+ *   word = normalize(y[:, :dim]) * norm_scale (norm_scale <= 0: no normalisation),  bypass = y[:, dim:]
+ * x [B, nfeat] fp32 = (t, l[, view parameters]) already scaled to [-1, 1];  Wf [32, nfeat] fp32 (not trained).
+ * params / d_params: flat fp32, state_dict order  net.0.{weight[64,64],bias} net.1.{weight,bias} net.3.{weight,bias}
+ * net.4.{weight,bias} output_layer.0.{weight[2*dim,64],bias[2*dim]}  (vn_mapper_param_count(dim) floats).
+ * saved: [B, vn_mapper_saved_floats(dim)] fp32 written by fwd, read by bwd; scratch: [B, 2*dim + 64] fp32.
+ * The backward sums over samples in a fixed order (deterministic) and OVERWRITES d_params.
+ * ------------------------------------------------------------------------------------------------ */
+int vn_mapper_param_count(int dim);
+int vn_mapper_saved_floats(int dim);
+int vn_mapper_fwd(const float* x, const float* Wf, const float* params, float norm_scale, float* word, float* bypass,
+                  float* saved, int B, int nfeat, int dim, vn_stream_t s);
+int vn_mapper_bwd(const float* d_word, const float* d_bypass, const float* params, const float* saved, float norm_scale,
+                  float* d_params, float* scratch, int B, int dim, vn_stream_t s);
+/* torch.optim.AdamW step (coach.py:216, :750-757) on a flat fp32 buffer; grads are multiplied by grad_scale first
+ * (1/world after the all-reduce).  step counts from 1. */
+int vn_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, float grad_scale, vn_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

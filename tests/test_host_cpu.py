@@ -120,3 +120,26 @@ def test_synthetic_conditioning_emits_xti_dict():
     d = c(timesteps=torch.zeros(3, dtype=torch.long))
     assert d["this_idx"] == 0 and len([k for k in d if k.startswith("CONTEXT_TENSOR")]) == 32
     assert d["CONTEXT_TENSOR_BYPASS_15"].shape == (3, 77, 64) and d["CONTEXT_TENSOR_0"].requires_grad
+
+
+def test_neti_mapper_structure_matches_reference():
+    """Parameter names / count and the Fourier matrix of NeTIMapper against the reference-generated golden
+    (tests/golden/make_golden_mapper.py); the arithmetic itself is CUDA-only and tested under -m gpu."""
+    from view_neti_b200._abi import VNError
+    from view_neti_b200.models.neti_mapper import NeTIMapper
+    from view_neti_b200.utils.types import PESigmas
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "neti_mapper.pt"))
+    sig = PESigmas(sigma_t=0.03, sigma_l=2.0, sigma_theta=0.5, sigma_phi=0.5, sigma_r=0.5, sigma_dtu12=0.5)
+    kw = dict(arch_mlp_hidden_dims=64, arch_view_net=15, arch_view_disable_tl=False, use_nested_dropout=False,
+              pe_sigmas=sig, output_bypass=True)
+    mo = NeTIMapper(embedding_type="object", output_dim=1024, **kw)
+    assert sum(p.numel() for p in mo.parameters()) == 141_696                    # SURVEY.md 2.1 row 7
+    assert set(mo.state_dict()) == {k for k in gold["object"]["state"] if k != "encoder.w"}
+    mv = NeTIMapper(embedding_type="view", output_dim=256, placeholder_view_tokens=gold["view"]["tokens"],
+                    placeholder_view_token_ids=gold["view"]["ids"], **kw)
+    assert mv.deg_freedom == "theta-phi" and torch.equal(mv.encoder_w, gold["view"]["w"])
+    assert torch.equal(NeTIMapper(embedding_type="object", output_dim=256, **kw).encoder_w, gold["object"]["w"])
+    x = mv._encode_inputs(torch.tensor([0., 999.]), torch.tensor([0., 15.]), torch.tensor([49408, 49411]))
+    assert torch.allclose(x, torch.tensor([[-1., -1., -1., -1.], [0.998, 0.875, 1., 1.]]))
+    with pytest.raises(VNError):
+        mv(torch.tensor([0.]), torch.tensor([0.]), torch.tensor([49408]))           # CPU: fails loudly, no fallback

@@ -226,3 +226,49 @@ def test_coach_step_trains_the_conditioning(tiny_model):
     losses = coach.train([lat] * 5)
     assert len(losses) == 3 and all(torch.isfinite(l) for l in losses)
     assert float((cond.base.detach() - before).abs().max()) > 0
+
+
+MAPPER_GOLD = os.path.join(os.path.dirname(__file__), "golden", "neti_mapper.pt")
+
+
+@pytest.mark.parametrize("kind", ["object", "view"])
+def test_neti_mapper_matches_reference_golden(kind):
+    """NeTIMapper (fused CUDA fwd / bwd) against outputs and parameter gradients of the reference's own NeTIMapper
+    (tests/golden/make_golden_mapper.py runs /root/reference/models/neti_mapper.py; arch_view_net 15)."""
+    from view_neti_b200.models.neti_mapper import NeTIMapper
+    from view_neti_b200.utils.types import PESigmas
+    gold = torch.load(MAPPER_GOLD)
+    g = gold[kind]
+    sig = PESigmas(sigma_t=0.03, sigma_l=2.0, sigma_theta=0.5, sigma_phi=0.5, sigma_r=0.5, sigma_dtu12=0.5)
+    kw = dict(output_dim=256, arch_mlp_hidden_dims=64, arch_view_net=15, arch_view_disable_tl=False, use_nested_dropout=False, pe_sigmas=sig,
+              output_bypass=True, bypass_unconstrained=True, output_bypass_alpha=0.2, norm_scale=torch.tensor(g["norm_scale"]))
+    if kind == "view":
+        kw.update(placeholder_view_tokens=g["tokens"], placeholder_view_token_ids=g["ids"])
+    m = NeTIMapper(embedding_type=kind, **kw)
+    assert torch.equal(m.encoder_w, g["w"])                      # same Fourier matrix as the reference (seed 0)
+    missing, unexpected = m.load_state_dict({k: v for k, v in g["state"].items() if k != "encoder.w"}, strict=True)
+    assert not missing and not unexpected
+    m = m.cuda()
+    ids = g["input_ids"].cuda() if kind == "view" else None
+    out = m(gold["t"].cuda(), gold["l"].cuda(), ids)
+    assert out.bypass_unconstrained == g["bypass_unconstrained"] and out.output_bypass_alpha == g["output_bypass_alpha"]
+    assert rel(out.word_embedding, g["word"]) < 1e-5 and rel(out.bypass_output, g["bypass"]) < 1e-5
+    loss = (out.word_embedding * g["gw"].cuda()).sum() + (out.bypass_output * g["gb"].cuda()).sum()
+    loss.backward()
+    for name, p in m.named_parameters():
+        assert rel(p.grad, g["grads"][name]) < 2e-4, name
+
+
+def test_adamw_step_matches_torch():
+    from view_neti_b200 import ops
+    torch.manual_seed(0)
+    p = torch.randn(10000, device="cuda")
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        g = torch.randn_like(p)
+        ref.grad = g.clone()
+        opt.step()
+        ops.adamw_step(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, 1e-2, step)
+        assert rel(p, ref.detach()) < 1e-6

@@ -91,6 +91,11 @@ SIGNATURES = {
     "vn_mse_loss": (C.c_int, [_P, _P, _L, _F, _P, _P, _P]),
     "vn_cfg_ddim_step": (C.c_int, [_P, _P, _P, _L, _F, _F, _F, _I, _P]),
     "vn_memset_zero": (C.c_int, [_P, _Z, _P]),
+    "vn_mapper_param_count": (C.c_int, [_I]),
+    "vn_mapper_saved_floats": (C.c_int, [_I]),
+    "vn_mapper_fwd": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _P]),
+    "vn_mapper_bwd": (C.c_int, [_P, _P, _P, _P, _F, _P, _P, _I, _I, _P]),
+    "vn_adamw_step": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
 }
 
 

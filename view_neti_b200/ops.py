@@ -273,6 +273,27 @@ def cfg_ddim_step(latents, eps_u, eps_c, guidance, acp_t, acp_prev, vpred):
                                        int(vpred), stream()), "cfg_ddim")
 
 
+def mapper_param_count(dim: int) -> int:
+    return int(_abi.load().vn_mapper_param_count(dim))
+
+
+def mapper_fwd(x, Wf, params, norm_scale, word, bypass, saved):
+    B, nfeat = x.shape
+    check(_abi.load().vn_mapper_fwd(ptr(x), ptr(Wf), ptr(params), float(norm_scale), ptr(word), ptr(bypass), ptr(saved),
+                                    B, nfeat, word.shape[1], stream()), "mapper_fwd")
+
+
+def mapper_bwd(d_word, d_bypass, params, saved, norm_scale, d_params, scratch):
+    B, dim = d_word.shape
+    check(_abi.load().vn_mapper_bwd(ptr(d_word), ptr(d_bypass), ptr(params), ptr(saved), float(norm_scale), ptr(d_params),
+                                    ptr(scratch), B, dim, stream()), "mapper_bwd")
+
+
+def adamw_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    check(_abi.load().vn_adamw_step(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), params.numel(), lr, beta1,
+                                    beta2, eps, weight_decay, step, grad_scale, stream()), "adamw_step")
+
+
 def launch_count() -> int:
     return int(_abi.load().vn_launch_count())
 
