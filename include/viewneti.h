@@ -71,6 +71,10 @@ typedef struct vn_gemm_desc {
 } vn_gemm_desc;
 
 size_t vn_gemm_workspace_bytes(int max_M, int max_N);
+/* diagnostics (library built with -DVN_TIMELINE only, see scripts/kernel_timeline.py): when non-NULL, every vn_gemm /
+ * fused-GroupNorm CTA writes clock64 stamps of its phases into 16 int64 slots of this device buffer
+ * (>= 16 * 2048 slots).  NULL (default) switches it off; the product build compiles the stamps out. */
+void   vn_set_debug_buffer(void* dev_ptr);
 int    vn_gemm(const vn_gemm_desc* d, vn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -91,6 +95,26 @@ int vn_groupnorm_bwd_apply(const void* x, int64_t ldx, const void* dy, int64_t l
                            const double* red, const float* gamma, const float* beta, float eps, int silu,
                            const void* add1, int64_t ldadd1, const void* add2, int64_t ldadd2,
                            void* dx, int64_t lddx, int nb, int hw, int C, int groups, vn_stream_t s);
+
+/* One-launch forms (statistics + apply fused; what the engine calls).  `partials`: vn_groupnorm_partial_floats(nb)
+ * floats private to this call, EVERY BYTE 0xff on entry (the engine presets one arena for all GroupNorms of a pass
+ * with one memset): the per-CTA partial sums through which the CTAs of the grid exchange their statistics - a word
+ * that is no longer 0xffffffff has been written, so the data is its own flag (no atomics, no counters, deterministic).
+ * stats / red are WRITTEN (not accumulated).  The grid never exceeds one CTA per SM, so all CTAs are co-resident.
+ * partials == NULL, or a shape the fused kernel does not cover (C > 4096, groups > 32, nb > #SMs, < 64 threads), runs
+ * the two-kernel form above (which needs stats / red zero on entry, so callers keep them zeroed); results agree to
+ * fp32 rounding of the statistics.
+ * vn_set_groupnorm_fused(0) (env VN_GN_FUSED=0) forces the two-kernel form. */
+int vn_groupnorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, float eps, int silu,
+                     void* y, int64_t ldy, int nb, int hw, int C, int groups, double* stats,
+                     float* partials, vn_stream_t s);
+int vn_groupnorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, const double* stats,
+                     const float* gamma, const float* beta, float eps, int silu,
+                     const void* add1, int64_t ldadd1, const void* add2, int64_t ldadd2,
+                     void* dx, int64_t lddx, int nb, int hw, int C, int groups, double* red,
+                     float* partials, vn_stream_t s);
+void vn_set_groupnorm_fused(int enabled);
+size_t vn_groupnorm_partial_floats(int nb);
 
 /* LayerNorm over rows of [rows, C] bf16 — diffusers BasicTransformerBlock.norm1/2/3.
  * stats: fp32 [rows,2] = (mean, rstd), written by fwd, read by bwd.  bwd: dx = LN^T(dy) (+ add). */
@@ -175,6 +199,7 @@ int vn_mse_loss(const float* pred, const float* target, int64_t n, float loss_sc
 int vn_cfg_ddim_step(float* latents, const float* eps_uncond, const float* eps_cond, int64_t n,
                      float guidance, float acp_t, float acp_prev, int vpred, vn_stream_t s);
 int vn_memset_zero(void* p, size_t bytes, vn_stream_t s);
+int vn_memset(void* p, int byte_value, size_t bytes, vn_stream_t s);
 
 /* ------------------------------------------------------------------------------------------------
  * NeTI mapper (SURVEY.md 8f "next" #2) - the module the context gradients finally land in.

@@ -123,8 +123,24 @@ def check_groupnorm(nb, hw, Cc, silu, eps=1e-5, groups=32):
     dx = torch.empty_like(x)
     ops.groupnorm_bwd(x, dy, stats, red, gamma, beta, eps, silu, dx, nb, hw, groups, add1=add1)
     lab = f"groupnorm nb{nb} hw{hw} C{Cc} silu{int(silu)}"
+    # one-launch forms (what the engine calls): statistics + grid barrier + apply; must reproduce the two-kernel results
+    stats2 = torch.zeros_like(stats)
+    red2 = torch.zeros_like(red)
+    part = torch.empty(2, ops.groupnorm_partial_floats(nb), device=DEV)
+    ops.memset(part, 0xFF)
+    y2 = torch.empty_like(x)
+    dx2 = torch.empty_like(x)
+    ops.groupnorm_fwd(x, gamma, beta, eps, silu, y2, nb, hw, groups, stats2, part[0])
+    ops.groupnorm_bwd_fused(x, dy, stats2, red2, part[1], gamma, beta, eps, silu, dx2, nb, hw, groups, add1=add1)
     return [(lab + " fwd", rel(y, yr.permute(0, 2, 1)), 6e-3),
-            (lab + " bwd", rel(dx, xr.grad.permute(0, 2, 1) + add1.float()), 8e-3)]
+            (lab + " bwd", rel(dx, xr.grad.permute(0, 2, 1) + add1.float()), 8e-3),
+            (lab + " fused fwd", rel(y2, yr.permute(0, 2, 1)), 6e-3),
+            (lab + " fused bwd", rel(dx2, xr.grad.permute(0, 2, 1) + add1.float()), 8e-3),
+            # (per-thread fp32 partial sums cover different pixel sets in the two geometries: equal up to fp32 rounding)
+            (lab + " fused ~ two-kernel (y)", rel(y2, y), 2e-4),
+            (lab + " fused ~ two-kernel (dx)", rel(dx2, dx), 2e-4),
+            (lab + " fused stats", float((stats2 - stats).norm() / stats.norm()), 1e-5),
+            (lab + " fused red", float((red2 - red).abs().max() / (red.abs().max() + 1e-30)), 1e-3)]
 
 
 def check_layernorm(rows, Cc):
@@ -346,7 +362,9 @@ def all_checks():
     L.append((check_conv, dict(nb=3, H=32, W=32, Cc=64, N=192, force_bn=64, force_split=1 + 16 * 4, rowbias=True, resid=True)))
     L.append((check_conv, dict(nb=1, H=24, W=16, Cc=128, N=320, force_bn=128, force_split=1 + 16 * 2, rowbias=True, resid=True)))
     L.append((check_conv, dict(nb=1, H=64, W=64, Cc=320, N=320, force_bn=256, force_split=1 + 16 * 4, rowbias=True, resid=True)))
-    for (nb, hw, Cc, silu) in [(1, 4096, 320, True), (2, 1024, 640, False), (1, 64, 2560, True), (1, 256, 1920, True)]:
+    for (nb, hw, Cc, silu) in [(1, 4096, 320, True), (2, 1024, 640, False), (1, 64, 2560, True), (1, 256, 1920, True),
+                               (1, 4096, 960, True), (1, 4096, 640, False), (1, 256, 2560, True), (2, 6912, 960, True),
+                               (1, 3072, 320, True), (1, 16, 128, True), (3, 4, 512, False), (1, 1024, 1280, True)]:
         L.append((check_groupnorm, dict(nb=nb, hw=hw, Cc=Cc, silu=silu, eps=1e-5 if silu else 1e-6)))
     for (rows, Cc) in [(4096, 320), (1024, 640), (77, 1280)]:
         L.append((check_layernorm, dict(rows=rows, Cc=Cc)))

@@ -12,7 +12,10 @@ from typing import Optional
 
 import torch
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libviewneti_sm100a.so"
+import os as _os
+
+# VN_LIB_SUFFIX selects an experiment build of the same ABI (see build.py); the default is the product library
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / f"libviewneti_sm100a{_os.environ.get('VN_LIB_SUFFIX', '')}.so"
 _lib: Optional[C.CDLL] = None
 
 
@@ -65,11 +68,17 @@ SIGNATURES = {
     "vn_set_pdl": (None, [C.c_int]),
     "vn_gemm_workspace_bytes": (C.c_size_t, [_I, _I]),
     "vn_gemm": (C.c_int, [C.POINTER(GemmDesc), _P]),
+    "vn_set_debug_buffer": (None, [_P]),
     "vn_groupnorm_stats": (C.c_int, [_P, _L, _I, _I, _I, _I, _P, _P]),
     "vn_groupnorm_apply": (C.c_int, [_P, _L, _P, _P, _P, _F, _I, _P, _L, _I, _I, _I, _I, _P]),
     "vn_groupnorm_bwd_stats": (C.c_int, [_P, _L, _P, _L, _P, _P, _P, _F, _I, _P, _I, _I, _I, _I, _P]),
     "vn_groupnorm_bwd_apply": (C.c_int, [_P, _L, _P, _L, _P, _P, _P, _P, _F, _I, _P, _L, _P, _L, _P, _L,
                                          _I, _I, _I, _I, _P]),
+    "vn_groupnorm_fwd": (C.c_int, [_P, _L, _P, _P, _F, _I, _P, _L, _I, _I, _I, _I, _P, _P, _P]),
+    "vn_groupnorm_bwd": (C.c_int, [_P, _L, _P, _L, _P, _P, _P, _F, _I, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _P, _P,
+                                   _P]),
+    "vn_groupnorm_partial_floats": (C.c_size_t, [_I]),
+    "vn_set_groupnorm_fused": (None, [C.c_int]),
     "vn_layernorm_fwd": (C.c_int, [_P, _L, _P, _P, _F, _P, _L, _P, _I, _I, _P]),
     "vn_layernorm_bwd": (C.c_int, [_P, _L, _P, _L, _P, _P, _P, _L, _P, _L, _I, _I, _P]),
     "vn_geglu_fwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _P]),
@@ -91,6 +100,7 @@ SIGNATURES = {
     "vn_mse_loss": (C.c_int, [_P, _P, _L, _F, _P, _P, _P]),
     "vn_cfg_ddim_step": (C.c_int, [_P, _P, _P, _L, _F, _F, _F, _I, _P]),
     "vn_memset_zero": (C.c_int, [_P, _Z, _P]),
+    "vn_memset": (C.c_int, [_P, _I, _Z, _P]),
     "vn_mapper_param_count": (C.c_int, [_I]),
     "vn_mapper_saved_floats": (C.c_int, [_I]),
     "vn_mapper_fwd": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _P]),

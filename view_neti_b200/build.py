@@ -17,7 +17,11 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 OBJDIR = PKG / "build"
-LIB = LIBDIR / "libviewneti_sm100a.so"
+# experiment builds: VN_LIB_SUFFIX=_x VN_CFLAGS="-DVN_EPI_HALVES=1" python -m view_neti_b200.build --force
+_SUFFIX = os.environ.get("VN_LIB_SUFFIX", "")
+LIB = LIBDIR / f"libviewneti_sm100a{_SUFFIX}.so"
+if _SUFFIX:
+    OBJDIR = PKG / f"build{_SUFFIX}"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -54,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         obj = OBJDIR / (src.stem + ".o")
         if not force and obj.exists() and obj.stat().st_mtime >= max(src.stat().st_mtime, hdr_m):
             return obj
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("VN_CFLAGS", "").split(), "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

@@ -13,6 +13,7 @@
 // ------------------------------------------------------------------------------------------------
 void vn_set_error(const char* fmt, ...);
 void vn_count_launch(int n = 1);
+long long* vn_debug_buffer();      // NULL unless vn_set_debug_buffer() armed the in-kernel timelines
 
 #define VN_CHECK(cond, ...)                                         \
   do {                                                              \
@@ -104,9 +105,11 @@ __device__ __forceinline__ float2 unpack_bf162(uint32_t u) {
   return __bfloat1622float2(t);
 }
 
-__device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
+// sigmoid through ex2.approx + rcp.approx (2 ulp): the IEEE division is a ~10-instruction sequence, and the GroupNorm
+// kernels that evaluate these per element are issue-bound
+__device__ __forceinline__ float silu_f(float z) { return __fdividef(z, 1.f + __expf(-z)); }
 __device__ __forceinline__ float dsilu_f(float z) {
-  float s = 1.f / (1.f + __expf(-z));
+  float s = __fdividef(1.f, 1.f + __expf(-z));
   return s * (1.f + z * (1.f - s));
 }
 

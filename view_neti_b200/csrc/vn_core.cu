@@ -11,6 +11,11 @@ std::atomic<long long> g_launches{0};
 std::atomic<int> g_pdl{1};
 }  // namespace
 
+// in-kernel timelines (scripts/kernel_timeline.py): device buffer of 16 int64 slots per CTA, or NULL (off)
+static long long* g_dbg = nullptr;
+long long* vn_debug_buffer() { return g_dbg; }
+extern "C" void vn_set_debug_buffer(void* p) { g_dbg = reinterpret_cast<long long*>(p); }
+
 bool vn_pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 extern "C" void vn_set_pdl(int enabled) { g_pdl.store(enabled ? 1 : 0); }
 
@@ -121,6 +126,11 @@ extern "C" int vn_copy2d(const void* src, int64_t lds, const void* add, int64_t 
   const int vecs = cols / 8;
   VN_LAUNCH(copy2d_kernel, grid_for(rows * vecs, 256), 256, 0, (cudaStream_t)s, (const bf16*)src, lds, (const bf16*)add,
                                                                           ldadd, (bf16*)dst, ldd, rows, vecs);
+  return 0;
+}
+
+extern "C" int vn_memset(void* p, int byte_value, size_t bytes, vn_stream_t s) {
+  VN_CUDA(cudaMemsetAsync(p, byte_value, bytes, (cudaStream_t)s));
   return 0;
 }
 

@@ -33,7 +33,17 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 192;
+#ifndef VN_EPI_HALVES
+#define VN_EPI_HALVES 2              // epilogue warps per TMEM lane quarter in the persistent schedule (1 or 2)
+#endif
+#ifndef VN_PRODUCERS
+#define VN_PRODUCERS 2               // 2: a second TMA warp (the last warp of the CTA) issues the B loads
+#endif
+constexpr int kEpiHalves = VN_EPI_HALVES;
+constexpr int kProducers = VN_PRODUCERS;
+constexpr int kThreadsSplit = 192 + 32 * (kProducers - 1);   // split-K: TMA warp, MMA warp, 4 epilogue warps (+ B warp)
+constexpr int kThreadsPers = 64 + 128 * kEpiHalves + 32 * (kProducers - 1);   // persistent: TMA, MMA, 4 or 8 epilogue warps
+constexpr int kEpiThreads = 128 * kEpiHalves;
 
 struct GemmParams {
   int M, N;
@@ -48,7 +58,22 @@ struct GemmParams {
   int out_fp32;
   int use_tma_epilogue;
   int nbimg;            // images (conv mode); tiles of a padded cluster slot may decode to img >= nbimg
+  long long* dbg;       // optional in-kernel timeline (vn_set_debug_buffer): 16 slots per CTA, clock64 stamps
 };
+
+__device__ __forceinline__ long long gtimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#ifdef VN_TIMELINE
+#define VN_STAMP(slot)                                                          \
+  do {                                                                          \
+    if (p.dbg) p.dbg[(long long)blockIdx.x * 16 + (slot)] = clock64();          \
+  } while (0)
+#else
+#define VN_STAMP(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -95,7 +120,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
 // Direct (register -> global) finish of 8 consecutive columns of one output row; used by the fp32 and split-K paths.
 __device__ __forceinline__ void store8(const GemmParams& p, float (&o)[8], long long gm, int bidx, int n) {
@@ -166,12 +191,15 @@ __device__ __forceinline__ bool tile_row(const GemmParams& p, const TileCoord& c
 }
 
 template <int BN, int STAGES, bool SPLIT, int MC>
-__global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmD,
                                                                const __grid_constant__ CUtensorMap tmR,
                                                                const GemmParams p) {
   pdl_trigger();
+#ifdef VN_TIMELINE
+  if (p.dbg && threadIdx.x == 0) { p.dbg[(long long)blockIdx.x * 16 + 0] = gtimer_ns(); VN_STAMP(1); }
+#endif
   constexpr int A_BYTES = BM * BK * 2;            // 16 KB
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -212,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], SPLIT ? 4 : 4 * kEpiHalves);      // one arrival per epilogue warp
     }
     mbar_init(rfull_bar, 1);
     mbar_init(sfree_bar, 1);
@@ -224,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();          // everything above overlapped the previous kernel; global memory is touched only from here on
+  if (threadIdx.x == 0) VN_STAMP(2);
 
   // ---- work assignment ----
   const int num_tiles = p.m_tiles * p.n_tiles;
@@ -241,38 +269,51 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
     kb_begin = 0;
     nkb = p.kb_total;
   }
+  pdl_wait();          // everything above overlapped the previous kernel; activations are touched only from here on
+  if (threadIdx.x == 0) VN_STAMP(3);
   const bool tma_epi = !SPLIT && p.use_tma_epilogue;
 
   if (warp == 0) {
     // ================= TMA producer =================
+    // One thread issues every load; its per-k-block instruction chain is on the critical path of the whole main loop
+    // (a stage is re-armed only after this thread has seen it drained), so the loop carries no division or modulo:
+    // stage index / phase and the conv (tap, channel-block) coordinates advance incrementally.
     if (lane == 0) {
       const uint32_t tx_bytes = (uint32_t)(p.rows_a * BK * 2 + B_BYTES);
-      int it = 0, t = 0;
+      int s = 0, t = 0;
+      uint32_t ph = 1;                             // parity to wait for on empty_bar[s]
       for (int tile = tile_begin; tile < num_tiles; tile += tile_step, ++t) {
         const TileCoord c = tile_coord(p, tile, BN);
-        for (int i = 0; i < nkb; ++i, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        int kx = kb_begin * BK;                    // K coordinate (elements) of the next k-block
+        int cb = 0, dx = 0, dy = 0;                // conv: 64-channel block and 3x3 tap of the next k-block
+        if (p.mode == 1) {
+          const int tap = kb_begin / p.cblocks;
+          cb = kb_begin - tap * p.cblocks;
+          dy = tap / 3; dx = tap - dy * 3;
+        }
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait(&empty_bar[s], ph);
           mbar_expect_tx(&full_bar[s], tx_bytes);
           uint8_t* sa = smem + s * STAGE_BYTES;
-          const int kb = kb_begin + i;
           if (p.mode == 0) {
-            tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, c.m0);
+            tma_load_2d(sa, &tmA, &full_bar[s], kx, c.m0);
           } else {
-            const int tap = kb / p.cblocks;
-            const int cb = kb - tap * p.cblocks;
-            const int dy = tap / 3, dx = tap - dy * 3;
             tma_load_4d(sa, &tmA, &full_bar[s], cb * BK, c.w0 + dx - 1, c.h0 + dy - 1, c.img);
+            if (++cb == p.cblocks) { cb = 0; if (++dx == 3) { dx = 0; ++dy; } }
           }
           if (MC == 1) {
-            tma_load_2d(sa + A_BYTES, &tmB, &full_bar[s], kb * BK, c.n0);
+            if (kProducers == 1) tma_load_2d(sa + A_BYTES, &tmB, &full_bar[s], kx, c.n0);
           } else {
             // my 1/MC slice of the B tile goes to every CTA of the cluster (same n-tile, consecutive m-tiles)
             constexpr int SLICE = BN / MC;
-            tma_load_2d_mc(sa + A_BYTES + (int)crank * SLICE * 128, &tmB, &full_bar[s], kb * BK, c.n0 + (int)crank * SLICE,
+            tma_load_2d_mc(sa + A_BYTES + (int)crank * SLICE * 128, &tmB, &full_bar[s], kx, c.n0 + (int)crank * SLICE,
                            (uint16_t)((1u << MC) - 1));
           }
+          kx += BK;
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+          if (i == 0 && t == 0) VN_STAMP(4);
         }
+        if (t == 0) VN_STAMP(5);
         if (tma_epi && p.R) {
           // residual tile -> staging, once the previous tile's store has finished reading it
           mbar_wait(sfree_bar, (t & 1) ^ 1);
@@ -286,10 +327,34 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
       }
     }
     __syncwarp();
+  } else if (kProducers == 2 && MC == 1 && warp == (SPLIT ? 6 : 2 + 4 * kEpiHalves)) {
+    // ================= second TMA producer: the B (weight) tiles =================
+    // Issue latency of the single producer thread bounds the main loop; the B loads of a stage need nothing from the
+    // A producer but the drained stage (same empty barrier) - their complete_tx may land before its expect_tx, the
+    // phase cannot complete until that arrival.
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1;
+      for (int tile = tile_begin; tile < num_tiles; tile += tile_step) {
+        const int n0 = (tile / p.m_tiles) * BN;
+        int kx = kb_begin * BK;
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait(&empty_bar[s], ph);
+          tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &tmB, &full_bar[s], kx, n0);
+          kx += BK;
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      int it = 0, t = 0;
+      int s = 0, t = 0;
+      uint32_t ph = 0;                             // parity to wait for on full_bar[s]
+      const uint64_t desc0 = umma_desc_k_sw128(smem_u32(smem));          // stage 0, A operand
+      constexpr uint64_t kStageStep = (uint64_t)(STAGE_BYTES >> 4);      // descriptor start-address units of 16 B
+      constexpr uint64_t kBOffset = (uint64_t)(A_BYTES >> 4);
       for (int tile = tile_begin; tile < num_tiles; tile += tile_step, ++t) {
         const int n0 = (tile / p.m_tiles) * BN;
         int n_eff = min(BN, p.N - n0);
@@ -301,13 +366,12 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
           tc_fence_after();
         }
         const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
-        for (int i = 0; i < nkb; ++i, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-          const uint64_t adesc = umma_desc_k_sw128(sa);
-          const uint64_t bdesc = umma_desc_k_sw128(sa + A_BYTES);
+          if (i == 0 && t == 0) VN_STAMP(6);
+          const uint64_t adesc = desc0 + (uint64_t)s * kStageStep;
+          const uint64_t bdesc = adesc + kBOffset;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
@@ -315,15 +379,22 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
           }
           if (MC == 1) umma_commit(&empty_bar[s]);   // frees this smem stage when the MMAs above have read it
           else umma_commit_mc(&empty_bar[s], (uint16_t)((1u << MC) - 1));
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         umma_commit(&tfull_bar[as]);             // accumulator complete
+        if (t == 0) VN_STAMP(7);
       }
     }
     __syncwarp();
-  } else if (!SPLIT) {
-    // ================= epilogue (warps 2..5), persistent schedule =================
+  } else if (!SPLIT && warp < 2 + 4 * kEpiHalves) {
+    // ================= epilogue (warps 2..9), persistent schedule =================
+    // Two warps per TMEM lane quarter: warps 2..5 finish the left half of the tile's columns, warps 6..9 the right half
+    // (a lone warp per scheduler cannot hide its own instruction latency, and most launches of a batch-1 step are
+    // single-tile, so the epilogue is on the critical path).  TMEM loads are software-pipelined one chunk ahead.
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                 // tile row == TMEM lane
+    const int half = (warp - 2) >> 2;            // column half of the tile (0 when kEpiHalves == 1)
+    constexpr int NCH = BN / 32 / kEpiHalves;    // 32-column chunks per epilogue warp
     int t = 0;
     for (int tile = tile_begin; tile < num_tiles; tile += tile_step, ++t) {
       const TileCoord c = tile_coord(p, tile, BN);
@@ -334,69 +405,74 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
       // bias (+ the per-image time-embedding row-bias in conv mode) of this tile: global loads are issued before
       // the accumulator wait and parked in shared memory, so no global latency sits on the epilogue's critical path
       const bool smem_rowbias = p.rowbias && p.mode == 1;
-      float bv[BN / 128 > 0 ? BN / 128 : 1];
-      const int te = threadIdx.x - 64;
+      const int te = threadIdx.x - 64;           // 0..kEpiThreads-1
+      constexpr int NBV = (BN + kEpiThreads - 1) / kEpiThreads;
+      float bv[NBV];
 #pragma unroll
-      for (int u = 0; u < (BN + 127) / 128; ++u) {
-        const int col = te + u * 128;
-        float v = 0.f;
+      for (int u = 0; u < NBV; ++u) {
+        const int col = te + u * kEpiThreads;
+        bv[u] = 0.f;
         if (col < BN && c.n0 + col < p.N) {
-          if (p.bias) v = __ldg(p.bias + c.n0 + col);
-          if (smem_rowbias) v += __ldg(p.rowbias + (long long)min(c.img, p.nbimg - 1) * p.ld_rowbias + c.n0 + col);
+          if (p.bias) bv[u] = __ldg(p.bias + c.n0 + col);
+          if (smem_rowbias) bv[u] += __ldg(p.rowbias + (long long)min(c.img, p.nbimg - 1) * p.ld_rowbias + c.n0 + col);
         }
-        bv[u] = v;
       }
       mbar_wait(&tfull_bar[as], (t >> 1) & 1);
       tc_fence_after();
+      if (t == 0 && threadIdx.x == 64) VN_STAMP(8);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
       if (tma_epi) {
+        uint32_t raw[2][32];
+        tmem_ld32(taddr + (half * NCH) * 32, raw[0]);          // in flight across the barrier below
 #pragma unroll
-        for (int u = 0; u < (BN + 127) / 128; ++u)
-          if (te + u * 128 < BN) sbias[te + u * 128] = bv[u];
+        for (int u = 0; u < NBV; ++u)
+          if (te + u * kEpiThreads < BN) sbias[te + u * kEpiThreads] = bv[u];
         epi_bar_sync();
         if (p.R) mbar_wait(rfull_bar, t & 1);
-#pragma unroll 1
-        for (int cc = 0; cc < BN / 32; ++cc) {
-          const int nb0 = c.n0 + cc * 32;
-          if (nb0 >= p.N) break;
-          uint32_t raw[32];
-          tmem_ld32(taddr + cc * 32, raw);
-          tmem_ld_wait();
-          uint8_t* blk = staging + (cc >> 1) * (BM * 128) + r * 128;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = nb0 + g * 8;
-            float o[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(sbias + cc * 32 + g * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(sbias + cc * 32 + g * 8 + 4);
-            o[0] = __uint_as_float(raw[g * 8 + 0]) + b0.x; o[1] = __uint_as_float(raw[g * 8 + 1]) + b0.y;
-            o[2] = __uint_as_float(raw[g * 8 + 2]) + b0.z; o[3] = __uint_as_float(raw[g * 8 + 3]) + b0.w;
-            o[4] = __uint_as_float(raw[g * 8 + 4]) + b1.x; o[5] = __uint_as_float(raw[g * 8 + 5]) + b1.y;
-            o[6] = __uint_as_float(raw[g * 8 + 6]) + b1.z; o[7] = __uint_as_float(raw[g * 8 + 7]) + b1.w;
-            if (p.rowbias && !smem_rowbias && n < p.N && row_ok) {
-              const float* rb = p.rowbias + (long long)bidx * p.ld_rowbias + n;
-              const float4 c0 = __ldg(reinterpret_cast<const float4*>(rb));
-              const float4 c1 = __ldg(reinterpret_cast<const float4*>(rb + 4));
-              o[0] += c0.x; o[1] += c0.y; o[2] += c0.z; o[3] += c0.w;
-              o[4] += c1.x; o[5] += c1.y; o[6] += c1.z; o[7] += c1.w;
+        for (int i = 0; i < NCH; ++i) {
+          const int cc = half * NCH + i;
+          const int nb0 = c.n0 + cc * 32;
+          tmem_ld_wait();
+          if (i + 1 < NCH) tmem_ld32(taddr + (cc + 1) * 32, raw[(i + 1) & 1]);
+          if (nb0 < p.N) {
+            uint8_t* blk = staging + (cc >> 1) * (BM * 128) + r * 128;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int n = nb0 + g * 8;
+              float o[8];
+              const float4 b0 = *reinterpret_cast<const float4*>(sbias + cc * 32 + g * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(sbias + cc * 32 + g * 8 + 4);
+              o[0] = __uint_as_float(raw[i & 1][g * 8 + 0]) + b0.x; o[1] = __uint_as_float(raw[i & 1][g * 8 + 1]) + b0.y;
+              o[2] = __uint_as_float(raw[i & 1][g * 8 + 2]) + b0.z; o[3] = __uint_as_float(raw[i & 1][g * 8 + 3]) + b0.w;
+              o[4] = __uint_as_float(raw[i & 1][g * 8 + 4]) + b1.x; o[5] = __uint_as_float(raw[i & 1][g * 8 + 5]) + b1.y;
+              o[6] = __uint_as_float(raw[i & 1][g * 8 + 6]) + b1.z; o[7] = __uint_as_float(raw[i & 1][g * 8 + 7]) + b1.w;
+              if (p.rowbias && !smem_rowbias && n < p.N && row_ok) {
+                const float* rb = p.rowbias + (long long)bidx * p.ld_rowbias + n;
+                const float4 c0 = __ldg(reinterpret_cast<const float4*>(rb));
+                const float4 c1 = __ldg(reinterpret_cast<const float4*>(rb + 4));
+                o[0] += c0.x; o[1] += c0.y; o[2] += c0.z; o[3] += c0.w;
+                o[4] += c1.x; o[5] += c1.y; o[6] += c1.z; o[7] += c1.w;
+              }
+              uint4* slot = reinterpret_cast<uint4*>(blk + ((((cc & 1) * 4 + g) ^ (r & 7)) << 4));
+              if (p.R && n < p.N) {
+                const uint4 rr = *slot;
+                float2 f;
+                f = unpack_bf162(rr.x); o[0] += f.x; o[1] += f.y;
+                f = unpack_bf162(rr.y); o[2] += f.x; o[3] += f.y;
+                f = unpack_bf162(rr.z); o[4] += f.x; o[5] += f.y;
+                f = unpack_bf162(rr.w); o[6] += f.x; o[7] += f.y;
+              }
+              uint4 w;
+              w.x = pack_bf162(o[0], o[1]); w.y = pack_bf162(o[2], o[3]);
+              w.z = pack_bf162(o[4], o[5]); w.w = pack_bf162(o[6], o[7]);
+              *slot = w;
             }
-            uint4* slot = reinterpret_cast<uint4*>(blk + ((((cc & 1) * 4 + g) ^ (r & 7)) << 4));
-            if (p.R && n < p.N) {
-              const uint4 rr = *slot;
-              float2 f;
-              f = unpack_bf162(rr.x); o[0] += f.x; o[1] += f.y;
-              f = unpack_bf162(rr.y); o[2] += f.x; o[3] += f.y;
-              f = unpack_bf162(rr.z); o[4] += f.x; o[5] += f.y;
-              f = unpack_bf162(rr.w); o[6] += f.x; o[7] += f.y;
-            }
-            uint4 w;
-            w.x = pack_bf162(o[0], o[1]); w.y = pack_bf162(o[2], o[3]);
-            w.z = pack_bf162(o[4], o[5]); w.w = pack_bf162(o[6], o[7]);
-            *slot = w;
           }
         }
         tc_fence_before();
         if (lane == 0) mbar_arrive(&tempty_bar[as]);       // TMEM stage may be overwritten by tile t+2
+        if (t == 0 && threadIdx.x == 64) VN_STAMP(14);
         fence_proxy_async();
         epi_bar_sync();
         if (threadIdx.x == 64) {
@@ -406,6 +482,7 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
             else tma_store_4d(&tmD, staging + j * (BM * 128), c.n0 + j * 64, c.w0, c.h0, c.img);
           }
           tma_store_commit();
+          if (t == 0) VN_STAMP(15);
           tma_store_wait_read();
           mbar_arrive(sfree_bar);
         }
@@ -413,7 +490,7 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
       } else {
         // direct register -> global path (fp32 outputs, odd strides)
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 32; ++cc) {
+        for (int cc = half * NCH; cc < (half + 1) * NCH; ++cc) {
           const int nb0 = c.n0 + cc * 32;
           if (nb0 >= p.N) break;
           uint32_t raw[32];
@@ -436,6 +513,7 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
         if (lane == 0) mbar_arrive(&tempty_bar[as]);
       }
     }
+    if (threadIdx.x == 64) VN_STAMP(9);
     // (the bulk stores were drained from shared memory by wait_group.read above; their global visibility is ordered by
     //  grid completion, which is what the next kernel's griddepcontrol.wait / stream order waits for)
   }
@@ -445,24 +523,29 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
     const int S = p.splits;
     const int rpo = BM / S;                       // rows reduced (and finished) by each CTA of the cluster
     const int cpt = BN / S;                       // columns finished per epilogue thread
-    float* exch = reinterpret_cast<float*>(smem); // [S src][BN col][rpo row] fp32, aliases the pipeline stages
-    if (warp >= 2) {
+    // [S src][BN col][rpo row] fp32, aliases the pipeline stages.  Row-fastest: the 32 lanes of a warp (32 consecutive
+    // tile rows) write one contiguous 128-byte run per remote store - one packet on the SM-to-SM network; a row-major
+    // float4 layout (32 scattered 16-byte pieces per instruction) measured 1.7x slower on B200.
+    float* exch = reinterpret_cast<float*>(smem);
+    const int tile = tile_begin;
+    const TileCoord c = tile_coord(p, tile, BN);
+    if (warp >= 2 && warp < 6) {
       mbar_wait(&tfull_bar[0], 0);                // my accumulator is complete => my stages are no longer read
       tc_fence_after();
+      if (threadIdx.x == 64) VN_STAMP(8);
     }
     __syncwarp();
     cluster_sync_all();                           // every CTA of the cluster is done with its pipeline stages
-    if (warp >= 2) {
+    if (threadIdx.x == 64) VN_STAMP(12);
+    if (warp >= 2 && warp < 6) {
       const int q = warp & 3;
       const int r = q * 32 + lane;
       const uint32_t owner = (uint32_t)(r / rpo);
       const uint32_t remote = mapa_shared(smem_u32(exch), owner) + (uint32_t)(((int)crank * BN * rpo + (r % rpo)) * 4);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-      const int tile = tile_begin;
-      const int n0 = (tile / p.m_tiles) * BN;
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
-        if (n0 + cc * 32 >= p.N) break;
+        if (c.n0 + cc * 32 >= p.N) break;
         uint32_t raw[32];
         tmem_ld32(taddr + cc * 32, raw);
         tmem_ld_wait();
@@ -473,12 +556,11 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
     tc_fence_before();
     __syncwarp();
     cluster_sync_all();                           // all partials have landed (release / acquire at cluster scope)
-    if (warp >= 2) {
+    if (threadIdx.x == 64) VN_STAMP(13);
+    if (warp >= 2 && warp < 6) {
       const int te = threadIdx.x - 64;            // 0..127
       const int rl = te % rpo;
       const int cg = te / rpo;
-      const int tile = tile_begin;
-      const TileCoord c = tile_coord(p, tile, BN);
       long long gm;
       int bidx;
       const bool row_ok = tile_row(p, c, (int)crank * rpo + rl, &gm, &bidx);
@@ -497,6 +579,7 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
           store8(p, o, gm, bidx, n);
         }
       }
+      if (threadIdx.x == 64) VN_STAMP(9);
     }
   }
 
@@ -507,6 +590,9 @@ __global__ void __launch_bounds__(kThreads, 1) vn_gemm_kernel(const __grid_const
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
+#ifdef VN_TIMELINE
+  if (p.dbg && threadIdx.x == 0) { VN_STAMP(10); p.dbg[(long long)blockIdx.x * 16 + 11] = gtimer_ns(); }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -546,7 +632,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
     if (MC > 1) {
       cudaLaunchConfig_t q{};
       q.gridDim = dim3((unsigned)(MC * 64), 1, 1);
-      q.blockDim = dim3(kThreads, 1, 1);
+      q.blockDim = dim3(SPLIT ? kThreadsSplit : kThreadsPers, 1, 1);
       q.dynamicSmemBytes = smem;
       cudaLaunchAttribute a[1];
       a[0].id = cudaLaunchAttributeClusterDimension;
@@ -564,7 +650,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid_x, 1, 1);
-  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.blockDim = dim3(SPLIT ? kThreadsSplit : kThreadsPers, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -700,6 +786,7 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
   p.splits = splits;
   p.n_tiles = vn_cdiv(d->N, bn);
   p.nbimg = d->mode == 1 ? d->nb : 1;
+  p.dbg = vn_debug_buffer();
   // multicast clusters along M (persistent schedule only): every CTA of a cluster works on the same n-tile
   int mc = 1;
   if (splits == 1) {

@@ -304,6 +304,410 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const bf16* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused GroupNorm: statistics + apply in ONE launch.  At per-GPU batch 1 a GroupNorm tensor is 0.2 - 8 MB and both
+// phases are bound by launch / load latency, not bandwidth, so the two-kernel form pays that latency twice (119 x per
+// train step).  Here the grid is at most one CTA per SM and every CTA
+//   1. loads its slab of pixels into REGISTERS (NP vectors per thread; NP == 0: too large, phase 3 re-reads it from L2),
+//   2. reduces it to 64 (group, statistic) fp32 partials - shared memory + T/64 lanes per pair, no atomics,
+//   3. stores them to its slot of `partials` (every word preset to 0xffffffff by the host once per pass) and polls ALL
+//      CTAs' slots until no word is 0xffffffff: the data is its own flag, so there is no fence, no arrival counter
+//      (same-address atomics serialise at ~20 ns each on B200: 148 arrivals cost more than the whole reduction) and
+//      no second hop; every CTA adds the partials up in the same fixed order in fp64,
+//   4. normalises its slab from registers.
+// All CTAs are co-resident by construction (grid <= #SMs, and nothing that waits on this kernel can hold an SM it
+// needs: PDL successors start only after every CTA of this grid has started), which the polling needs; a protocol bug
+// traps instead of hanging.  Shared / global fp64 atomics and in-kernel fp64 div / sqrt, measured at ~2 us per phase
+// (scripts/kernel_timeline.py), are gone; the sums are deterministic by construction.
+//   MODE 0: y = act(GN(x));  acc = (sum x, sum x^2) kept for the backward.
+//   MODE 1: dx = GN^T(dy) (+add1) (+add2);  stats = forward sums, acc = (sum dxhat, sum dxhat*xhat).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_relaxed_v4(const uint4* p) {          // L2 read, never served from a stale L1 line
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+struct GNConst {                                  // per-thread constants of its 8 channels
+  float gam[8], bet[8];
+  float R[8], M[8];                               // MODE 1: xhat = x*R + M
+  float A[8], Bc[8];                              // MODE 0 phase 2: y = x*A + Bc
+  float S1[8], S2[8];                             // MODE 1 phase 2
+};
+
+template <int MODE>
+__device__ __forceinline__ void gn_accumulate(const GNConst& c, int silu, const uint4& xraw, const uint4& draw,
+                                              float (&a0)[8], float (&a1)[8]) {
+  float xf[8];
+  unpack8(xraw, xf);
+  if (MODE == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a0[j] += xf[j]; a1[j] = fmaf(xf[j], xf[j], a1[j]); }
+  } else {
+    float df[8];
+    unpack8(draw, df);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = fmaf(xf[j], c.R[j], c.M[j]);
+      float dz = df[j];
+      if (silu) dz *= dsilu_f(fmaf(xh, c.gam[j], c.bet[j]));
+      const float dh = dz * c.gam[j];
+      a0[j] += dh; a1[j] = fmaf(dh, xh, a1[j]);
+    }
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ uint4 gn_finish(const GNConst& c, int silu, const uint4& xraw, const uint4& draw, bool h1,
+                                           const uint4& r1, bool h2, const uint4& r2) {
+  float xf[8], o[8];
+  unpack8(xraw, xf);
+  if (MODE == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(xf[j], c.A[j], c.Bc[j]);
+      o[j] = silu ? silu_f(z) : z;
+    }
+  } else {
+    float df[8];
+    unpack8(draw, df);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = fmaf(xf[j], c.R[j], c.M[j]);
+      float dz = df[j];
+      if (silu) dz *= dsilu_f(fmaf(xh, c.gam[j], c.bet[j]));
+      o[j] = c.R[j] * (dz * c.gam[j] - c.S1[j] - xh * c.S2[j]);
+    }
+    if (h1) { float t[8]; unpack8(r1, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += t[j]; }
+    if (h2) { float t[8]; unpack8(r2, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += t[j]; }
+  }
+  return pack8(o);
+}
+
+template <int MODE, int NP, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) gn_fused_kernel(const bf16* __restrict__ x, long long ldx,
+                                                           const bf16* __restrict__ dy, long long lddy,
+                                                           const double* __restrict__ stats,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float eps, int silu,
+                                                           double* acc, float* part,
+                                                           const bf16* __restrict__ add1, long long ld1,
+                                                           const bf16* __restrict__ add2, long long ld2,
+                                                           bf16* __restrict__ y, long long ldy, int hw, int C,
+                                                           int groups, int k, int ppc, long long* dbg) {
+  pdl_trigger();
+#ifdef VN_TIMELINE
+#define GN_STAMP(slot)                                                                                     \
+  do {                                                                                                     \
+    if (dbg && threadIdx.x == 0) dbg[((long long)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define GN_STAMP(slot) do { } while (0)
+#endif
+  GN_STAMP(1);
+  constexpr int NR = NP > 0 ? NP : 1;
+  constexpr int kPairs = 64;                       // (group, statistic) pairs per image: groups <= 32
+  __shared__ __align__(16) float s_part[2][MAXT * 8];   // [statistic][thread's 8 channels]; reused as double4[MAXT] later
+  __shared__ double s_tot[kPairs];
+  __shared__ double s_red2[kPairs * 8];
+  __shared__ float s_red[kPairs * 8];
+  __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups], s_s1[kMaxGroups], s_s2[kMaxGroups];
+  const int b = blockIdx.y;
+  const int cpg = C / groups;
+  const int vecs = C >> 3;
+  const int v = threadIdx.x % vecs, slot = threadIdx.x / vecs;
+  const int c0 = v * 8;
+  const int p0 = blockIdx.x * ppc;
+  const int p1 = min(hw, p0 + ppc);
+  const double inv_n = 1.0 / ((double)cpg * (double)hw);
+  GNConst c;
+  {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    c.gam[0] = g0.x; c.gam[1] = g0.y; c.gam[2] = g0.z; c.gam[3] = g0.w; c.gam[4] = g1.x; c.gam[5] = g1.y; c.gam[6] = g1.z; c.gam[7] = g1.w;
+    c.bet[0] = b0.x; c.bet[1] = b0.y; c.bet[2] = b0.z; c.bet[3] = b0.w; c.bet[4] = b1.x; c.bet[5] = b1.y; c.bet[6] = b1.z; c.bet[7] = b1.w;
+  }
+  pdl_wait();          // parameters above are frozen; activations / statistics only from here on
+  GN_STAMP(2);
+  if (MODE == 1) {
+    // E[x^2] - mean^2 in fp64 (cancellation), the reciprocal square root in fp32 (fp64 div / sqrt are long sequences)
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+      const double m = stats[(b * groups + g) * 2] * inv_n;
+      const double var = fmax(fma(-m, m, stats[(b * groups + g) * 2 + 1] * inv_n), 0.0);
+      s_mean[g] = (float)m; s_rstd[g] = 1.0f / sqrtf((float)var + eps);
+    }
+    __syncthreads();
+  }
+  // group of each of the thread's 8 channels: one division, then a running remainder
+  int gj[8];
+  {
+    int g = c0 / cpg, rem = c0 - g * cpg;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (rem == cpg) { rem = 0; ++g; }
+      gj[j] = g;
+      ++rem;
+    }
+  }
+  if (MODE == 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      c.R[j] = s_rstd[gj[j]]; c.M[j] = -s_mean[gj[j]] * s_rstd[gj[j]];
+    }
+  }
+  const bf16* xb = x + (long long)b * hw * ldx + c0;
+  const bf16* db = MODE == 1 ? dy + (long long)b * hw * lddy + c0 : xb;
+
+  // ---- phase 1: partial sums of the CTA's slab ----
+  uint4 xv[NR], dv[NR];
+  float a0[8], a1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+  if (NP > 0) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int p = p0 + slot + i * k;
+      xv[i] = make_uint4(0u, 0u, 0u, 0u);
+      dv[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (p < p1) {
+        xv[i] = ld16(xb + (long long)p * ldx);
+        if (MODE == 1) dv[i] = ld16(db + (long long)p * lddy);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+      if (p0 + slot + i * k < p1) gn_accumulate<MODE>(c, silu, xv[i], dv[i], a0, a1);
+  } else {
+    int p = p0 + slot;
+    for (; p + 3 * k < p1; p += 4 * k) {
+      uint4 xq[4], dq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        xq[u] = ld16(xb + (long long)(p + u * k) * ldx);
+        dq[u] = xq[u];
+        if (MODE == 1) dq[u] = ld16(db + (long long)(p + u * k) * lddy);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) gn_accumulate<MODE>(c, silu, xq[u], dq[u], a0, a1);
+    }
+    for (; p < p1; p += k) {
+      uint4 xq = ld16(xb + (long long)p * ldx), dq = xq;
+      if (MODE == 1) dq = ld16(db + (long long)p * lddy);
+      gn_accumulate<MODE>(c, silu, xq, dq, a0, a1);
+    }
+  }
+  GN_STAMP(3);
+  // ---- CTA reduction without atomics: per-thread channel sums -> shared memory -> T/64 lanes per (group, statistic) ----
+  {
+    float* q0 = &s_part[0][threadIdx.x * 8];
+    float* q1 = &s_part[1][threadIdx.x * 8];
+    *reinterpret_cast<float4*>(q0) = make_float4(a0[0], a0[1], a0[2], a0[3]);
+    *reinterpret_cast<float4*>(q0 + 4) = make_float4(a0[4], a0[5], a0[6], a0[7]);
+    *reinterpret_cast<float4*>(q1) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+    *reinterpret_cast<float4*>(q1 + 4) = make_float4(a1[4], a1[5], a1[6], a1[7]);
+  }
+  __syncthreads();
+  const int T = blockDim.x;
+  const int L = T >> 6;                            // lanes per pair (host guarantees T >= 64), <= 8
+  {
+    // thread (slot, v) wrote channels [v*8, v*8+8) at slot*C: group g of statistic st = k runs of cpg floats
+    if ((int)threadIdx.x < kPairs * L) {
+      const int pr = threadIdx.x / L, sub = threadIdx.x - pr * L;
+      float sum = 0.f;
+      if (pr < 2 * groups) {
+        const int g = pr >> 1, st = pr & 1;
+        const float* src = &s_part[st][g * cpg];
+        for (int sl = 0; sl < k; ++sl, src += C)       // (no integer division: it costs more than the whole loop)
+          for (int ch = sub; ch < cpg; ch += L) sum += src[ch];
+      }
+      s_red[pr * 8 + sub] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x < kPairs) {
+      float v = 0.f;
+      for (int u = 0; u < L; ++u) v += s_red[threadIdx.x * 8 + u];
+      unsigned bits = __float_as_uint(v);
+      if (bits == 0xffffffffu) bits = 0x7fffffffu;             // 0xffffffff is the "not written yet" pattern
+      __stcg(reinterpret_cast<unsigned*>(part) + ((long long)b * gridDim.x + blockIdx.x) * kPairs + threadIdx.x, bits);
+    }
+  }
+  GN_STAMP(4);
+  // ---- exchange: every CTA polls ALL CTAs' partials (preset to 0xffffffff by the host once per pass) until they are
+  // written, and adds them up in the same fixed order (fp64).  No atomics, no arrival counter (same-address atomics
+  // serialise at ~20 ns each: 148 arrivals cost more than the whole reduction), no second hop, deterministic. ----
+  {
+    const uint4* pv = reinterpret_cast<const uint4*>(part + (long long)b * gridDim.x * kPairs);
+    const int nvec = gridDim.x * (kPairs / 4);     // blockDim.x % 16 == 0: a thread always meets the same four pairs
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    for (int base = 0; base < nvec; base += 8 * T) {
+      uint4 f[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + threadIdx.x + u * T;
+        f[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (i < nvec) f[u] = ld_relaxed_v4(pv + i);
+      }
+      long long tstart = 0;
+      for (unsigned spins = 0;; ++spins) {
+        bool ok = true;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = base + threadIdx.x + u * T;
+          if (i < nvec && (f[u].x == 0xffffffffu || f[u].y == 0xffffffffu || f[u].z == 0xffffffffu || f[u].w == 0xffffffffu)) {
+            f[u] = ld_relaxed_v4(pv + i);
+            ok = false;
+          }
+        }
+        if (ok) break;
+        if (spins == 0) tstart = clock64();
+        if ((spins & 0xffu) == 0xffu && (clock64() - tstart) > 4000000000LL) {
+          printf("viewneti: groupnorm partials never arrived (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+          __trap();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        t0 += (double)__uint_as_float(f[u].x); t1 += (double)__uint_as_float(f[u].y);
+        t2 += (double)__uint_as_float(f[u].z); t3 += (double)__uint_as_float(f[u].w);
+      }
+    }
+    GN_STAMP(6);
+    double* red4 = reinterpret_cast<double*>(&s_part[0][0]);        // [thread][4]; s_part is dead (synced above)
+    red4[threadIdx.x * 4 + 0] = t0; red4[threadIdx.x * 4 + 1] = t1;
+    red4[threadIdx.x * 4 + 2] = t2; red4[threadIdx.x * 4 + 3] = t3;
+    __syncthreads();
+    // pair pr lives in component (pr & 3) of the threads j with j % 16 == pr >> 2; L lanes share the T/16 addends
+    if ((int)threadIdx.x < kPairs * L) {
+      const int pr = threadIdx.x / L, sub = threadIdx.x - pr * L;
+      double tot = 0.0;
+      for (int j = (pr >> 2) + 16 * sub; j < T; j += 16 * L) tot += red4[j * 4 + (pr & 3)];
+      s_red2[pr * 8 + sub] = tot;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < 2 * groups) {
+      double tot = 0.0;
+      for (int u = 0; u < L; ++u) tot += s_red2[threadIdx.x * 8 + u];
+      s_tot[threadIdx.x] = tot;
+      if (blockIdx.x == 0) acc[(long long)b * groups * 2 + threadIdx.x] = tot;   // kept for the backward / the caller
+    }
+    __syncthreads();
+  }
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    const double t0 = s_tot[2 * g], t1 = s_tot[2 * g + 1];
+    if (MODE == 0) {
+      const double m = t0 * inv_n;
+      const double var = fmax(fma(-m, m, t1 * inv_n), 0.0);
+      s_mean[g] = (float)m; s_rstd[g] = 1.0f / sqrtf((float)var + eps);
+    } else {
+      s_s1[g] = (float)(t0 * inv_n); s_s2[g] = (float)(t1 * inv_n);
+    }
+  }
+  __syncthreads();
+  GN_STAMP(8);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = gj[j];
+    if (MODE == 0) {
+      c.A[j] = c.gam[j] * s_rstd[g];
+      c.Bc[j] = c.bet[j] - s_mean[g] * c.A[j];
+    } else {
+      c.S1[j] = s_s1[g]; c.S2[j] = s_s2[g];
+    }
+  }
+  const bool h1 = MODE == 1 && add1 != nullptr, h2 = MODE == 1 && add2 != nullptr;
+  const bf16* a1b = h1 ? add1 + (long long)b * hw * ld1 + c0 : xb;
+  const bf16* a2b = h2 ? add2 + (long long)b * hw * ld2 + c0 : xb;
+  bf16* yb = y + (long long)b * hw * ldy + c0;
+  if (NP > 0) {
+    constexpr int U = NR < 4 ? NR : 4;
+#pragma unroll
+    for (int i0 = 0; i0 < NR; i0 += U) {
+      uint4 r1[U], r2[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int p = p0 + slot + (i0 + u) * k;
+        r1[u] = make_uint4(0u, 0u, 0u, 0u);
+        r2[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (MODE == 1 && p < p1) {
+          if (h1) r1[u] = ld16(a1b + (long long)p * ld1);
+          if (h2) r2[u] = ld16(a2b + (long long)p * ld2);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int p = p0 + slot + (i0 + u) * k;
+        if (p < p1)
+          *reinterpret_cast<uint4*>(yb + (long long)p * ldy) = gn_finish<MODE>(c, silu, xv[i0 + u], dv[i0 + u], h1, r1[u], h2, r2[u]);
+      }
+    }
+  } else {
+    constexpr int U = MODE == 0 ? 4 : 2;
+    int p = p0 + slot;
+    for (; p + (U - 1) * k < p1; p += U * k) {
+      uint4 xq[U], dq[U], r1[U], r2[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long pp = p + u * k;
+        xq[u] = ld16(xb + pp * ldx);
+        dq[u] = xq[u]; r1[u] = xq[u]; r2[u] = xq[u];
+        if (MODE == 1) {
+          dq[u] = ld16(db + pp * lddy);
+          if (h1) r1[u] = ld16(a1b + pp * ld1);
+          if (h2) r2[u] = ld16(a2b + pp * ld2);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        *reinterpret_cast<uint4*>(yb + (long long)(p + u * k) * ldy) = gn_finish<MODE>(c, silu, xq[u], dq[u], h1, r1[u], h2, r2[u]);
+    }
+    for (; p < p1; p += k) {
+      uint4 xq = ld16(xb + (long long)p * ldx), dq = xq, r1 = xq, r2 = xq;
+      if (MODE == 1) {
+        dq = ld16(db + (long long)p * lddy);
+        if (h1) r1 = ld16(a1b + (long long)p * ld1);
+        if (h2) r2 = ld16(a2b + (long long)p * ld2);
+      }
+      *reinterpret_cast<uint4*>(yb + (long long)p * ldy) = gn_finish<MODE>(c, silu, xq, dq, h1, r1, h2, r2);
+    }
+  }
+  GN_STAMP(7);
+#undef GN_STAMP
+}
+
+// Geometry of the fused form: at most one CTA per SM over the whole grid (all co-resident, the exchange needs that),
+// up to maxt threads per CTA with threads % 16 == 0 (exchange indexing) and >= 64 (one lane per pair at least).
+bool gn_fused_geom(int nb, int hw, int C, int maxt, GNGeom* out) {
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  const int vecs = C / 8;
+  if (vecs > maxt || nb > sms) return false;
+  GNGeom g;
+  g.k = maxt / vecs;
+  if (g.k > hw) g.k = hw;
+  while (g.k > 1 && (vecs * g.k) % 16 != 0) --g.k;
+  g.threads = vecs * g.k;
+  const int target = sms / nb;                            // CTAs per image
+  g.ppc = (hw + target - 1) / target;
+  g.chunks = (hw + g.ppc - 1) / g.ppc;
+  *out = g;
+  return g.threads >= 64 && g.threads % 16 == 0 && g.chunks * nb <= sms;
+}
+
+static int g_gn_fused = -1;
+bool gn_fused_enabled() {
+  if (g_gn_fused < 0) {
+    const char* e = getenv("VN_GN_FUSED");
+    g_gn_fused = e ? (atoi(e) != 0) : 1;
+  }
+  return g_gn_fused != 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, the row lives in registers as NV 16-byte vectors per lane (C <= 256*NV).
 // ---------------------------------------------------------------------------------------------
 template <int MODE, int NV>
@@ -536,6 +940,65 @@ extern "C" int vn_groupnorm_bwd_apply(const void* x, int64_t ldx, const void* dy
                                                                 (const bf16*)add2, ldadd2, (bf16*)dx, lddx, hw, C, groups,
                                                                 g.k, g.ppc);
   return 0;
+}
+
+extern "C" void vn_set_groupnorm_fused(int enabled) { g_gn_fused = enabled ? 1 : 0; }
+
+// floats of `partials` one GroupNorm call needs for nb images: 64 per CTA, at most one CTA per SM
+extern "C" size_t vn_groupnorm_partial_floats(int nb) {
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  (void)nb;                                       // grid <= #SMs in total, whatever nb is
+  return (size_t)sms * 64;
+}
+
+extern "C" int vn_groupnorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, float eps, int silu,
+                                void* y, int64_t ldy, int nb, int hw, int C, int groups, double* stats,
+                                float* partials, vn_stream_t s) {
+  if (gn_check(C, groups, ldx)) return -1;
+  VN_CHECK(ldy % 8 == 0, "groupnorm: ldy must be a multiple of 8");
+  GNGeom g;
+  if (partials && groups <= 32 && gn_fused_enabled() && gn_fused_geom(nb, hw, C, 512, &g)) {
+    dim3 grid(g.chunks, nb);
+    const int npt = vn_cdiv(g.ppc, g.k);
+#define VN_GN_F(NP)                                                                                                   \
+  VN_LAUNCH((gn_fused_kernel<0, NP, 512>), grid, g.threads, 0, (cudaStream_t)s, (const bf16*)x, ldx, nullptr, 0,      \
+            nullptr, gamma, beta, eps, silu, stats, partials, nullptr, 0, nullptr, 0, (bf16*)y, ldy, hw, C, groups,   \
+            g.k, g.ppc, vn_debug_buffer())
+    if (npt <= 4) { VN_GN_F(4); }
+    else if (npt <= 8) { VN_GN_F(8); }
+    else { VN_GN_F(0); }
+#undef VN_GN_F
+    return 0;
+  }
+  if (vn_groupnorm_stats(x, ldx, nb, hw, C, groups, stats, s)) return -1;
+  return vn_groupnorm_apply(x, ldx, stats, gamma, beta, eps, silu, y, ldy, nb, hw, C, groups, s);
+}
+
+extern "C" int vn_groupnorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, const double* stats,
+                                const float* gamma, const float* beta, float eps, int silu, const void* add1,
+                                int64_t ldadd1, const void* add2, int64_t ldadd2, void* dx, int64_t lddx, int nb, int hw,
+                                int C, int groups, double* red, float* partials, vn_stream_t s) {
+  if (gn_check(C, groups, ldx)) return -1;
+  VN_CHECK(lddy % 8 == 0 && lddx % 8 == 0 && ldadd1 % 8 == 0 && ldadd2 % 8 == 0, "groupnorm bwd: strides must be multiples of 8");
+  GNGeom g;
+  if (partials && groups <= 32 && gn_fused_enabled() && gn_fused_geom(nb, hw, C, 384, &g)) {
+    dim3 grid(g.chunks, nb);
+    const int npt = vn_cdiv(g.ppc, g.k);
+#define VN_GN_B(NP)                                                                                                    \
+  VN_LAUNCH((gn_fused_kernel<1, NP, 384>), grid, g.threads, 0, (cudaStream_t)s, (const bf16*)x, ldx, (const bf16*)dy,  \
+            lddy, stats, gamma, beta, eps, silu, red, partials, (const bf16*)add1, ldadd1, (const bf16*)add2, ldadd2,  \
+            (bf16*)dx, lddx, hw, C, groups, g.k, g.ppc, vn_debug_buffer())
+    if (npt <= 4) { VN_GN_B(4); }
+    else { VN_GN_B(0); }
+#undef VN_GN_B
+    return 0;
+  }
+  if (vn_groupnorm_bwd_stats(x, ldx, dy, lddy, stats, gamma, beta, eps, silu, red, nb, hw, C, groups, s)) return -1;
+  return vn_groupnorm_bwd_apply(x, ldx, dy, lddy, stats, red, gamma, beta, eps, silu, add1, ldadd1, add2, ldadd2, dx,
+                                lddx, nb, hw, C, groups, s);
 }
 
 extern "C" int vn_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y,

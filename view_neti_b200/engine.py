@@ -182,6 +182,11 @@ class _Plan:
         n_gn = 2 * (len(eng.res)) + len(eng.xf) + 1
         self.stat_f = self.buf("gn.stats", (n_gn, nb, cfg.norm_num_groups, 2), torch.float64)     # (sum x, sum x^2)
         self.stat_b = self.buf("gn.red", (n_gn, nb, cfg.norm_num_groups, 2), torch.float64)       # backward reductions
+        # per-CTA partial sums through which the CTAs of a fused GroupNorm exchange statistics: one private slot per
+        # GroupNorm, all bytes preset to 0xff by ONE memset per pass (a written word is its own arrival flag)
+        npf = ops.groupnorm_partial_floats(nb)
+        self.part_f = self.buf("gn.part_f", (n_gn, npf), torch.float32)
+        self.part_b = self.buf("gn.part_b", (n_gn, npf), torch.float32)
         self._stat_slots: Dict[str, int] = {}
         # side stream: the 32 context projections (forward) and the 32 context-gradient GEMMs (backward) do not sit on
         # the UNet's dependency chain; they run concurrently with it and are joined by events (captured in the graph)
@@ -232,15 +237,15 @@ class _Plan:
         G = self.eng.cfg.norm_num_groups
         st = self._stat(name + ".st", self.stat_f)
         y = self.buf(name + ".y", (self.nb, hw, x.shape[-1]))
-        ops.groupnorm_stats(x, self.nb, hw, G, st)
-        ops.groupnorm_apply(x, st, gb[0], gb[1], eps, silu, y, self.nb, hw, G)
+        ops.groupnorm_fwd(x, gb[0], gb[1], eps, silu, y, self.nb, hw, G, st, self.part_f[self._stat_slots[name + ".st"]])
         return y
 
     def _gn_bwd(self, name, x, dy, gb, eps, silu, hw, dx, add1=None, add2=None):
         G = self.eng.cfg.norm_num_groups
         st = self._stat(name + ".st", self.stat_f)
         red = self._stat(name + ".red", self.stat_b)
-        ops.groupnorm_bwd(x, dy, st, red, gb[0], gb[1], eps, silu, dx, self.nb, hw, G, add1=add1, add2=add2)
+        ops.groupnorm_bwd_fused(x, dy, st, red, self.part_b[self._stat_slots[name + ".red"]], gb[0], gb[1], eps, silu, dx,
+                                self.nb, hw, G, add1=add1, add2=add2)
 
     def _res_fwd(self, name, x, H, W, out):
         """diffusers ResnetBlock2D.  x: [nb, hw, cin] view, out: [nb, hw, cout] view."""
@@ -398,6 +403,7 @@ class _Plan:
         B = self.bufs
         # time embedding: sinusoid -> Linear -> SiLU -> Linear, then all ResBlock projections in one launch
         self.stat_f.zero_()
+        ops.memset(self.part_f, 0xFF)
         sin = self.buf("temb.sin", (nb, ch[0]), F32)
         ops.timestep_sinusoid(self.timesteps, sin)
         e1 = self.buf("temb.e1", (nb, cfg.time_embed_dim), F32)
@@ -522,6 +528,7 @@ class _Plan:
         cats = self._cats
         H, W = h, w
         self.stat_b.zero_()
+        ops.memset(self.part_b, 0xFF)
         dy = self.buf("bwd.dy", (nb, H * W, ch[0]))
         ops.conv_out_bwd(self.d_eps, eng.conv_out_w, dy.view(nb, H, W, ch[0]))
         dcur = self.buf(f"bwd.up.{nlev - 1}.out", (nb, H * W, ch[0]))

@@ -149,6 +149,36 @@ def groupnorm_bwd(x, dy, stats, red, gamma, beta, eps, silu, dx, nb, hw, groups,
                                      stream()), "gn_bwd_apply")
 
 
+def groupnorm_partial_floats(nb: int) -> int:
+    """Floats of `partials` one fused GroupNorm call needs (64 per CTA, at most one CTA per SM)."""
+    return int(_abi.load().vn_groupnorm_partial_floats(nb))
+
+
+def groupnorm_fwd(x, gamma, beta, eps, silu, y, nb, hw, groups, stats, partials):
+    """GroupNorm(+SiLU) in one launch.  `partials`: float32 [groupnorm_partial_floats(nb)], every byte 0xff on entry
+    (None -> two-kernel form); `stats` fp64 [nb, groups, 2] is written."""
+    check(_abi.load().vn_groupnorm_fwd(ptr(x), _ld(x), ptr(gamma), ptr(beta), eps, int(silu), ptr(y), _ld(y), nb, hw,
+                                       x.shape[-1], groups, ptr(stats), ptr(partials), stream()), "gn_fwd")
+
+
+def groupnorm_bwd_fused(x, dy, stats, red, partials, gamma, beta, eps, silu, dx, nb, hw, groups, add1=None, add2=None):
+    """dx = GN^T(dy) (+add1) (+add2) in one launch; `partials` as in groupnorm_fwd, `red` is written."""
+    check(_abi.load().vn_groupnorm_bwd(ptr(x), _ld(x), ptr(dy), _ld(dy), ptr(stats), ptr(gamma), ptr(beta), eps,
+                                       int(silu), ptr(add1), _ld(add1) if add1 is not None else 0, ptr(add2),
+                                       _ld(add2) if add2 is not None else 0, ptr(dx), _ld(dx), nb, hw, x.shape[-1],
+                                       groups, ptr(red), ptr(partials), stream()), "gn_bwd")
+
+
+def memset(t: torch.Tensor, byte_value: int) -> None:
+    """Fill a contiguous tensor with one byte value (a memset node when captured in a CUDA graph)."""
+    assert t.is_contiguous()
+    check(_abi.load().vn_memset(ptr(t), int(byte_value), t.numel() * t.element_size(), stream()), "memset")
+
+
+def set_groupnorm_fused(enabled: bool) -> None:
+    _abi.load().vn_set_groupnorm_fused(1 if enabled else 0)
+
+
 def layernorm_fwd(x, gamma, beta, eps, y, stats, rows):
     check(_abi.load().vn_layernorm_fwd(ptr(x), _ld(x), ptr(gamma), ptr(beta), eps, ptr(y), _ld(y), ptr(stats), rows,
                                        x.shape[-1], stream()), "ln_fwd")
