@@ -67,7 +67,10 @@ for key, (kind, M, N, K, geom, has_bias, has_r, f32) in seen.items():
         call = lambda bn, sp: orig_conv(A, Bm, D, bias=bias, R=R, force_bn=bn, force_split=sp)
     bias = torch.randn(N, device="cuda") if has_bias else None
     res = {}
-    for bn, sp in [(0, 0)] + [(b, s) for b in (64, 128, 256) for s in (1, 2, 4, 8)]:
+    # force_split code: low 4 bits split-K cluster size, +256 = CTA pairs (cta_group::2) on, +512 = pairs off
+    cands = [(b, s + 512) for b in (64, 128, 192, 256) for s in (1, 2, 4, 8)] + [(160, 2 + 512), (160, 4 + 512)]
+    cands += [(b, 1 + 256) for b in (128, 192, 256)]
+    for bn, sp in [(0, 0)] + cands:
         try:
             call(bn, sp)
             torch.cuda.synchronize()
@@ -90,7 +93,7 @@ for key, (kind, M, N, K, geom, has_bias, has_r, f32) in seen.items():
     tot_def += d; tot_best += min(best, d)
     if best < 0.97 * d:
         out[key] = [bn, sp, round(best, 2), round(d, 2)]
-    print(f"{key:34s} default {d:7.2f} us  best {best:7.2f} us  bn{bn} s{sp}", flush=True)
+    print(f"{key:34s} default {d:7.2f} us  best {best:7.2f} us  bn{bn} s{sp & 15}{' pair' if sp & 256 else ''}", flush=True)
 print(f"sum over distinct shapes: default {tot_def:.1f} us, tuned {tot_best:.1f} us")
 path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "gemm_tuning.json")
 os.makedirs(os.path.dirname(path), exist_ok=True)

@@ -348,12 +348,28 @@ def all_checks():
     L.append((check_gemm, dict(M=77, N=1024, K=1280, out_fp32=True, force_bn=64, force_split=8)))
     L.append((check_gemm, dict(M=6000, N=2560, K=320, bias=True, resid=True, force_bn=256, force_split=1)))
     L.append((check_gemm, dict(M=20000, N=320, K=320, bias=True, resid=True, force_bn=128, force_split=1)))
+    # CTA pairs (cta_group::2): force_split = 1 (no split-K) + 256 (pairs on)
+    L.append((check_gemm, dict(M=4096, N=320, K=320, bias=True, resid=True, force_bn=128, force_split=257)))
+    L.append((check_gemm, dict(M=20480, N=320, K=320, bias=True, resid=True, force_bn=128, force_split=257)))
+    L.append((check_gemm, dict(M=1024, N=2560, K=640, bias=True, force_bn=256, force_split=257)))
+    L.append((check_gemm, dict(M=512, N=328, K=1024, bias=True, resid=True, force_bn=256, force_split=257)))
+    # BN 160 (split-K only) and BN 192
+    L.append((check_gemm, dict(M=1024, N=640, K=2560, bias=True, resid=True, force_bn=160, force_split=4)))
+    L.append((check_gemm, dict(M=300, N=328, K=1024, bias=True, resid=True, force_bn=160, force_split=2)))
+    L.append((check_gemm, dict(M=1024, N=1920, K=640, bias=True, resid=True, force_bn=192, force_split=1)))
+    L.append((check_gemm, dict(M=1024, N=1920, K=640, bias=True, resid=True, force_bn=192, force_split=257)))
+    L.append((check_gemm, dict(M=256, N=3840, K=1280, bias=True, force_bn=192, force_split=2)))
     L.append((check_gemm, dict(M=300, N=320, K=640, out_fp32=True, strided=True, bias=True)))
     L.append((check_gemm, dict(M=300, N=320, K=640, strided=True, resid=True, force_split=2)))
     for (nb, H, W, Cc, N) in [(1, 64, 64, 320, 320), (1, 32, 32, 640, 640), (1, 16, 16, 1280, 1280),
                               (1, 8, 8, 1280, 1280), (2, 16, 16, 128, 64), (1, 48, 64, 64, 64), (2, 8, 8, 2560, 1280),
                               (1, 64, 64, 960, 320)]:
         L.append((check_conv, dict(nb=nb, H=H, W=W, Cc=Cc, N=N, rowbias=True, resid=True, dgrad=(Cc <= 1280))))
+    L.append((check_conv, dict(nb=1, H=64, W=64, Cc=320, N=320, force_bn=256, force_split=257, rowbias=True, resid=True)))
+    L.append((check_conv, dict(nb=1, H=32, W=32, Cc=640, N=640, force_bn=128, force_split=257, rowbias=True, resid=True)))
+    L.append((check_conv, dict(nb=4, H=64, W=64, Cc=64, N=192, force_bn=128, force_split=257, rowbias=True, resid=True)))
+    L.append((check_conv, dict(nb=1, H=64, W=64, Cc=320, N=320, force_bn=160, force_split=2, rowbias=True, resid=True)))
+    L.append((check_conv, dict(nb=1, H=16, W=16, Cc=1280, N=1280, force_bn=160, force_split=4, rowbias=True, resid=True)))
     L.append((check_conv, dict(nb=1, H=16, W=16, Cc=640, N=320, force_bn=64, force_split=4)))
     L.append((check_conv, dict(nb=1, H=32, W=32, Cc=320, N=320, force_bn=256, force_split=1, rowbias=True, resid=True)))
     L.append((check_conv, dict(nb=2, H=8, W=8, Cc=1280, N=1280, force_bn=128, force_split=8, rowbias=True, resid=True)))

@@ -105,6 +105,49 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
                "h"(mask)
                : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants: loads of both CTAs complete on the LEADER's mbarrier (shared::cluster address),
+// the pair's MMA is issued by the leader and its completion is multicast to the barriers of both CTAs ----
+__device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_cg2(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
@@ -190,7 +233,7 @@ __device__ __forceinline__ bool tile_row(const GemmParams& p, const TileCoord& c
   return (r < p.rows_a) && (h < p.H) && (w < p.W);
 }
 
-template <int BN, int STAGES, bool SPLIT, int MC>
+template <int BN, int STAGES, bool SPLIT, int MC, int CG>
 __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmD,
@@ -201,15 +244,17 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
   if (p.dbg && threadIdx.x == 0) { p.dbg[(long long)blockIdx.x * 16 + 0] = gtimer_ns(); VN_STAMP(1); }
 #endif
   constexpr int A_BYTES = BM * BK * 2;            // 16 KB
-  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int B_BYTES = (BN / CG) * BK * 2;     // CG == 2: each CTA of the pair holds half of the B tile
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int STAGING_BYTES = SPLIT ? 0 : BM * BN * 2;     // BN/64 blocks of [128 rows x 128 B], 128B-swizzled
   constexpr int ACC_STAGES = SPLIT ? 1 : 2;
   constexpr int TMEM_COLS = (ACC_STAGES * BN) <= 32 ? 32 : (ACC_STAGES * BN) <= 64 ? 64 : (ACC_STAGES * BN) <= 128 ? 128
                           : (ACC_STAGES * BN) <= 256 ? 256 : 512;
-  static_assert(STAGE_BYTES % 1024 == 0 && BN % 64 == 0 && ACC_STAGES * BN <= 512, "tile configuration");
+  static_assert(STAGE_BYTES % 1024 == 0 && BN % 32 == 0 && (SPLIT || BN % 64 == 0) && ACC_STAGES * BN <= 512,
+                "tile configuration (the staged epilogue works on 64-column blocks; split-K stores directly)");
   static_assert(!SPLIT || STAGES * STAGE_BYTES >= BM * BN * 4, "exchange buffer must fit in the pipeline stages");
   static_assert(MC == 1 || (!SPLIT && BN % MC == 0), "multicast clusters only in the persistent schedule");
+  static_assert(CG == 1 || (CG == 2 && !SPLIT && MC == 1 && kProducers == 2), "CTA pairs only in the persistent schedule");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -240,32 +285,39 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], SPLIT ? 4 : 4 * kEpiHalves);      // one arrival per epilogue warp
+      mbar_init(&tempty_bar[s], SPLIT ? 4 : 4 * kEpiHalves * CG);      // one arrival per epilogue warp (of the pair)
     }
     mbar_init(rfull_bar, 1);
     mbar_init(sfree_bar, 1);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_cg2<TMEM_COLS>(tmem_slot);      // one warp of EACH CTA of the pair, same slot offset
+    else tmem_alloc<TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
-  if (MC > 1) cluster_sync_all();                  // peers' barriers must exist before a multicast can signal them
+  if (MC > 1 || CG == 2) cluster_sync_all();       // peers' barriers must exist before a multicast can signal them
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) VN_STAMP(2);
 
   // ---- work assignment ----
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  // CG == 2: the work items are PAIR tiles (256 rows x BN): m-tiles 2q and 2q+1 of one n-tile; CTA `crank` of the pair
+  // owns m-tile 2q + crank (its A rows, its half of the accumulator, its D tile) and loads half of the B rows
+  const int num_tiles = (p.m_tiles / CG) * p.n_tiles;
+  const int mh = p.m_tiles / CG;
   int tile_begin, tile_step, kb_begin, nkb;
-  uint32_t crank = (SPLIT || MC > 1) ? cluster_ctarank() : 0;
+  uint32_t crank = (SPLIT || MC > 1 || CG == 2) ? cluster_ctarank() : 0;
+#define VN_TILE_OF(w) (CG == 2 ? (((w) / mh) * p.m_tiles + 2 * ((w) % mh) + (int)crank) : (w))
   if (SPLIT) {
     tile_begin = blockIdx.x / p.splits;
     tile_step = num_tiles;                       // exactly one tile per cluster
     kb_begin = (int)crank * p.kb_per_split;
     nkb = min(p.kb_total, kb_begin + p.kb_per_split) - kb_begin;   // host guarantees >= 1
   } else {
-    tile_begin = blockIdx.x;
-    tile_step = gridDim.x;
+    tile_begin = blockIdx.x / CG;
+    tile_step = gridDim.x / CG;
     kb_begin = 0;
     nkb = p.kb_total;
   }
@@ -279,10 +331,12 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     // (a stage is re-armed only after this thread has seen it drained), so the loop carries no division or modulo:
     // stage index / phase and the conv (tap, channel-block) coordinates advance incrementally.
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)(p.rows_a * BK * 2 + B_BYTES);
+      const uint32_t tx_bytes = (uint32_t)(CG * (p.rows_a * BK * 2 + B_BYTES));      // both CTAs of a pair
+      const uint32_t lead_full = CG == 2 ? mapa_shared(smem_u32(full_bar), 0) : 0;  // leader's full_bar[0]
       int s = 0, t = 0;
       uint32_t ph = 1;                             // parity to wait for on empty_bar[s]
-      for (int tile = tile_begin; tile < num_tiles; tile += tile_step, ++t) {
+      for (int w = tile_begin; w < num_tiles; w += tile_step, ++t) {
+        const int tile = VN_TILE_OF(w);
         const TileCoord c = tile_coord(p, tile, BN);
         int kx = kb_begin * BK;                    // K coordinate (elements) of the next k-block
         int cb = 0, dx = 0, dy = 0;                // conv: 64-channel block and 3x3 tap of the next k-block
@@ -293,9 +347,17 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
         }
         for (int i = 0; i < nkb; ++i) {
           mbar_wait(&empty_bar[s], ph);
-          mbar_expect_tx(&full_bar[s], tx_bytes);
+          if (CG == 1 || crank == 0) mbar_expect_tx(&full_bar[s], tx_bytes);
           uint8_t* sa = smem + s * STAGE_BYTES;
-          if (p.mode == 0) {
+          if (CG == 2) {
+            const uint32_t fb = lead_full + (uint32_t)(s * 8);
+            if (p.mode == 0) {
+              tma_load_2d_cg2(sa, &tmA, fb, kx, c.m0);
+            } else {
+              tma_load_4d_cg2(sa, &tmA, fb, cb * BK, c.w0 + dx - 1, c.h0 + dy - 1, c.img);
+              if (++cb == p.cblocks) { cb = 0; if (++dx == 3) { dx = 0; ++dy; } }
+            }
+          } else if (p.mode == 0) {
             tma_load_2d(sa, &tmA, &full_bar[s], kx, c.m0);
           } else {
             tma_load_4d(sa, &tmA, &full_bar[s], cb * BK, c.w0 + dx - 1, c.h0 + dy - 1, c.img);
@@ -335,12 +397,20 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 1;
-      for (int tile = tile_begin; tile < num_tiles; tile += tile_step) {
-        const int n0 = (tile / p.m_tiles) * BN;
+      const uint32_t lead_full = CG == 2 ? mapa_shared(smem_u32(full_bar), 0) : 0;
+      for (int w = tile_begin; w < num_tiles; w += tile_step) {
+        const int tile = VN_TILE_OF(w);
+        int n0 = (tile / p.m_tiles) * BN;
+        if (CG == 2) {
+          // the pair's MMA takes B rows [0, n/2) from the leader and [n/2, n) from its peer (n = the tile's UMMA N)
+          const int n_eff = (min(BN, p.N - n0) + 15) & ~15;
+          n0 += (int)crank * (n_eff >> 1);
+        }
         int kx = kb_begin * BK;
         for (int i = 0; i < nkb; ++i) {
           mbar_wait(&empty_bar[s], ph);
-          tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &tmB, &full_bar[s], kx, n0);
+          if (CG == 2) tma_load_2d_cg2(smem + s * STAGE_BYTES + A_BYTES, &tmB, lead_full + (uint32_t)(s * 8), kx, n0);
+          else tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &tmB, &full_bar[s], kx, n0);
           kx += BK;
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
@@ -348,18 +418,19 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (CG == 2: the leader CTA issues for the pair) =================
+    if (lane == 0 && (CG == 1 || crank == 0)) {
       int s = 0, t = 0;
       uint32_t ph = 0;                             // parity to wait for on full_bar[s]
       const uint64_t desc0 = umma_desc_k_sw128(smem_u32(smem));          // stage 0, A operand
       constexpr uint64_t kStageStep = (uint64_t)(STAGE_BYTES >> 4);      // descriptor start-address units of 16 B
       constexpr uint64_t kBOffset = (uint64_t)(A_BYTES >> 4);
-      for (int tile = tile_begin; tile < num_tiles; tile += tile_step, ++t) {
+      for (int w = tile_begin; w < num_tiles; w += tile_step, ++t) {
+        const int tile = VN_TILE_OF(w);
         const int n0 = (tile / p.m_tiles) * BN;
         int n_eff = min(BN, p.N - n0);
         n_eff = (n_eff + 15) & ~15;               // UMMA N granularity; B rows beyond N are TMA zero-fill
-        const uint32_t idesc = umma_idesc_bf16(BM, n_eff);
+        const uint32_t idesc = umma_idesc_bf16(BM * CG, n_eff);
         const int as = SPLIT ? 0 : (t & 1);
         if (!SPLIT) {
           mbar_wait(&tempty_bar[as], ((t >> 1) & 1) ^ 1);
@@ -375,13 +446,16 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) ? 1u : 0u);
+            if (CG == 2) umma_bf16_cg2(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) ? 1u : 0u);
+            else umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) ? 1u : 0u);
           }
-          if (MC == 1) umma_commit(&empty_bar[s]);   // frees this smem stage when the MMAs above have read it
+          if (CG == 2) umma_commit_cg2(&empty_bar[s], 3);   // the stage is free in BOTH CTAs of the pair
+          else if (MC == 1) umma_commit(&empty_bar[s]);   // frees this smem stage when the MMAs above have read it
           else umma_commit_mc(&empty_bar[s], (uint16_t)((1u << MC) - 1));
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        umma_commit(&tfull_bar[as]);             // accumulator complete
+        if (CG == 2) umma_commit_cg2(&tfull_bar[as], 3);   // both halves of the pair's accumulator are complete
+        else umma_commit(&tfull_bar[as]);             // accumulator complete
         if (t == 0) VN_STAMP(7);
       }
     }
@@ -396,7 +470,9 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     const int half = (warp - 2) >> 2;            // column half of the tile (0 when kEpiHalves == 1)
     constexpr int NCH = BN / 32 / kEpiHalves;    // 32-column chunks per epilogue warp
     int t = 0;
-    for (int tile = tile_begin; tile < num_tiles; tile += tile_step, ++t) {
+    const uint32_t lead_tempty = CG == 2 ? mapa_shared(smem_u32(tempty_bar), 0) : 0;
+    for (int w = tile_begin; w < num_tiles; w += tile_step, ++t) {
+      const int tile = VN_TILE_OF(w);
       const TileCoord c = tile_coord(p, tile, BN);
       const int as = t & 1;
       long long gm;
@@ -471,7 +547,10 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
           }
         }
         tc_fence_before();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);       // TMEM stage may be overwritten by tile t+2
+        if (lane == 0) {                                   // TMEM stage may be overwritten by tile t+2
+          if (CG == 2) mbar_arrive_cluster(lead_tempty + (uint32_t)(as * 8));
+          else mbar_arrive(&tempty_bar[as]);
+        }
         if (t == 0 && threadIdx.x == 64) VN_STAMP(14);
         fence_proxy_async();
         epi_bar_sync();
@@ -510,7 +589,10 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
           }
         }
         tc_fence_before();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(lead_tempty + (uint32_t)(as * 8));
+          else mbar_arrive(&tempty_bar[as]);
+        }
       }
     }
     if (threadIdx.x == 64) VN_STAMP(9);
@@ -584,12 +666,14 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
   }
 
   tc_fence_before();
-  if (MC > 1) cluster_sync_all();                  // no CTA leaves while a peer may still signal its barriers
+  if (MC > 1 || CG == 2) cluster_sync_all();       // no CTA leaves while a peer may still signal its barriers
   else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (CG == 2) tmem_dealloc_cg2<TMEM_COLS>(tmem_base);
+    else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
+#undef VN_TILE_OF
 #ifdef VN_TIMELINE
   if (p.dbg && threadIdx.x == 0) { VN_STAMP(10); p.dbg[(long long)blockIdx.x * 16 + 11] = gtimer_ns(); }
 #endif
@@ -614,19 +698,19 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int STAGES, bool SPLIT>
+template <int BN, int STAGES, bool SPLIT, int CG = 1>
 constexpr int smem_bytes() {
-  return STAGES * (BM * BK * 2 + BN * BK * 2) + (SPLIT ? 0 : BM * BN * 2) + BN * 4 + (2 * STAGES + 6) * 8 + 16 + 1024;
+  return STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + (SPLIT ? 0 : BM * BN * 2) + BN * 4 + (2 * STAGES + 6) * 8 + 16 + 1024;
 }
 
-template <int BN, int STAGES, bool SPLIT, int MC = 1>
+template <int BN, int STAGES, bool SPLIT, int MC = 1, int CG = 1>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr,
            const GemmParams& p, int grid_x, cudaStream_t st) {
   static bool configured = false;
   static int max_clusters = 0;
-  constexpr int smem = smem_bytes<BN, STAGES, SPLIT>();
+  constexpr int smem = smem_bytes<BN, STAGES, SPLIT, CG>();
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  auto kern = vn_gemm_kernel<BN, STAGES, SPLIT, MC>;
+  auto kern = vn_gemm_kernel<BN, STAGES, SPLIT, MC, CG>;
   if (!configured) {
     VN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (MC > 1) {
@@ -661,9 +745,9 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
-  if (SPLIT || MC > 1) {
+  if (SPLIT || MC > 1 || CG == 2) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = SPLIT ? (unsigned)p.splits : (unsigned)MC;
+    attr[na].val.clusterDim.x = SPLIT ? (unsigned)p.splits : CG == 2 ? 2u : (unsigned)MC;
     attr[na].val.clusterDim.y = 1;
     attr[na].val.clusterDim.z = 1;
     ++na;
@@ -774,12 +858,18 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
 
   int bn = 128, splits = 1;
   choose_tiling(p.m_tiles, d->N, p.kb_total, true, &bn, &splits);
-  // force_split: low 4 bits = split-K cluster size (0 = auto), bits 4..7 = multicast cluster size MC (0 = auto)
-  const int force_s = d->force_split & 15, force_mc = (d->force_split >> 4) & 15;
+  // force_split: low 4 bits = split-K cluster size (0 = auto), bits 4..7 = multicast cluster size MC (0 = auto),
+  // bits 8..9 = CTA pairs (cta_group::2): 1 = on, 2 = off, 0 = auto
+  const int force_s = d->force_split & 15, force_mc = (d->force_split >> 4) & 15, force_cg = (d->force_split >> 8) & 3;
   if (d->force_bn) bn = d->force_bn;
   if (force_s) splits = force_s;
-  VN_CHECK(bn == 64 || bn == 128 || bn == 256, "vn_gemm: unsupported BN %d (64, 128, 256)", bn);
+  VN_CHECK(bn == 64 || bn == 128 || bn == 160 || bn == 192 || bn == 256, "vn_gemm: unsupported BN %d (64, 128, 160, 192, 256)", bn);
   VN_CHECK(splits == 1 || splits == 2 || splits == 4 || splits == 8, "vn_gemm: unsupported split %d (1, 2, 4, 8)", splits);
+  // BN = 160 (= N/2, N/4, N/8 of the 320 / 640 / 1280-wide convolutions: no ragged last n-tile) exists in the split-K
+  // schedule only (the staged epilogue needs 64-column blocks); every finishing thread owns a multiple of 8 columns
+  if (bn == 160 && splits == 1) splits = 2;
+  while (splits > 1 && (bn / splits) % 8 != 0) splits /= 2;
+  VN_CHECK(!(bn == 160 && splits == 1), "vn_gemm: BN 160 needs a split-K cluster of 2 or 4");
   while (splits > 1 && (vn_cdiv(p.kb_total, splits) < 1 || p.kb_total <= (splits - 1) * vn_cdiv(p.kb_total, splits)))
     splits /= 2;
   p.kb_per_split = vn_cdiv(p.kb_total, splits);
@@ -798,11 +888,18 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
     if (mc > p.m_tiles) mc = p.m_tiles >= 2 ? 2 : 1;
     p.m_tiles = vn_cdiv(p.m_tiles, mc) * mc;       // padded slots decode to out-of-range tiles (TMA zero-fill / clipping)
   }
+  // CTA pairs (persistent schedule): two m-tiles of one n-tile share every B tile through cta_group::2 MMAs - each SM
+  // receives A + B/2 per k-block and the pair's tensor cores work on one 256 x BN tile
+  int cg = 1;
+  if (splits == 1 && mc == 1 && bn >= 128 && bn != 160 && p.m_tiles >= 2 && p.m_tiles % 2 == 0 && kProducers == 2) {
+    const bool auto_on = false;
+    cg = force_cg == 1 ? 2 : force_cg == 2 ? 1 : (auto_on ? 2 : 1);
+  }
   const int tiles = p.m_tiles * p.n_tiles;
   {
     cuuint64_t dims[2] = {(cuuint64_t)d->K, (cuuint64_t)d->N};
     cuuint64_t str[1] = {(cuuint64_t)d->ldb * 2};
-    cuuint32_t box[2] = {BK, (cuuint32_t)(bn / mc)};
+    cuuint32_t box[2] = {BK, (cuuint32_t)(bn / mc / cg)};
     if (make_map(&tb, d->B, 2, dims, str, box)) return -1;
   }
   // staged TMA-store epilogue for bf16 outputs of the persistent schedule
@@ -826,6 +923,12 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
       }
     }
   }
+  if (splits == 1 && cg == 2) {
+    const int pairs = tiles / 2 < num_sms() / 2 ? tiles / 2 : num_sms() / 2;
+    if (bn == 256) return launch<256, 5, false, 1, 2>(ta, tb, td, tr, p, 2 * pairs, st);
+    if (bn == 192) return launch<192, 6, false, 1, 2>(ta, tb, td, tr, p, 2 * pairs, st);
+    return launch<128, 7, false, 1, 2>(ta, tb, td, tr, p, 2 * pairs, st);
+  }
   if (splits == 1) {
     int grid = tiles < num_sms() ? tiles : num_sms();
     grid = (grid / mc) * mc;
@@ -834,9 +937,11 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
     if (mc == 4) return launch<BN_, ST_, false, 4>(ta, tb, td, tr, p, grid, st);             \
     if (mc == 2) return launch<BN_, ST_, false, 2>(ta, tb, td, tr, p, grid, st);             \
     return launch<BN_, ST_, false, 1>(ta, tb, td, tr, p, grid, st);
+    if (mc > 1) VN_CHECK(bn != 192, "vn_gemm: multicast clusters exist for BN 64 / 128 / 256 only");
     switch (bn) {
       VN_GEMM_CASE(64, 6)
       VN_GEMM_CASE(128, 5)
+      case 192: return launch<192, 4, false, 1>(ta, tb, td, tr, p, grid, st);
       default:
         if (mc == 4) return launch<256, 3, false, 4>(ta, tb, td, tr, p, grid, st);
         if (mc == 2) return launch<256, 3, false, 2>(ta, tb, td, tr, p, grid, st);
@@ -848,6 +953,8 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
   switch (bn) {
     case 64: return launch<64, 6, true>(ta, tb, td, tr, p, grid, st);
     case 128: return launch<128, 5, true>(ta, tb, td, tr, p, grid, st);
+    case 160: return launch<160, 5, true>(ta, tb, td, tr, p, grid, st);
+    case 192: return launch<192, 4, true>(ta, tb, td, tr, p, grid, st);
     default: return launch<256, 4, true>(ta, tb, td, tr, p, grid, st);
   }
 }
