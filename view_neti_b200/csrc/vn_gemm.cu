@@ -605,9 +605,11 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     const int S = p.splits;
     const int rpo = BM / S;                       // rows reduced (and finished) by each CTA of the cluster
     const int cpt = BN / S;                       // columns finished per epilogue thread
-    // [S src][BN col][rpo row] fp32, aliases the pipeline stages.  Row-fastest: the 32 lanes of a warp (32 consecutive
-    // tile rows) write one contiguous 128-byte run per remote store - one packet on the SM-to-SM network; a row-major
-    // float4 layout (32 scattered 16-byte pieces per instruction) measured 1.7x slower on B200.
+    // [S src][BN/4 column quads][rpo row][4] fp32, aliases the pipeline stages.  The 32 lanes of a warp (32 consecutive
+    // tile rows) write one contiguous 512-byte run per 16-byte remote store - whole 128-byte packets on the SM-to-SM
+    // network with a quarter of the instructions of scalar stores (a row-major float4 layout, 32 scattered 16-byte
+    // pieces per instruction, measured 1.7x slower on B200); the finishing threads read it back with LDS.128,
+    // conflict-free for the same reason.
     float* exch = reinterpret_cast<float*>(smem);
     const int tile = tile_begin;
     const TileCoord c = tile_coord(p, tile, BN);
@@ -623,7 +625,7 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
       const int q = warp & 3;
       const int r = q * 32 + lane;
       const uint32_t owner = (uint32_t)(r / rpo);
-      const uint32_t remote = mapa_shared(smem_u32(exch), owner) + (uint32_t)(((int)crank * BN * rpo + (r % rpo)) * 4);
+      const uint32_t remote = mapa_shared(smem_u32(exch), owner) + (uint32_t)((((int)crank * (BN / 4)) * rpo + (r % rpo)) * 16);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
@@ -632,7 +634,10 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
         tmem_ld32(taddr + cc * 32, raw);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) st_cluster_f32(remote + (uint32_t)((cc * 32 + j) * rpo * 4), __uint_as_float(raw[j]));
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(remote + (uint32_t)((cc * 8 + j) * rpo * 16)),
+                       "r"(raw[4 * j]), "r"(raw[4 * j + 1]), "r"(raw[4 * j + 2]), "r"(raw[4 * j + 3])
+                       : "memory");
       }
     }
     tc_fence_before();
@@ -655,8 +660,10 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = 0.f;
           for (int src = 0; src < S; ++src) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] += exch[((long long)src * BN + col + j) * rpo + rl];
+            const float4* e = reinterpret_cast<const float4*>(exch) + ((long long)src * (BN / 4) + (col >> 2)) * rpo + rl;
+            const float4 v0 = e[0], v1 = e[rpo];
+            o[0] += v0.x; o[1] += v0.y; o[2] += v0.z; o[3] += v0.w;
+            o[4] += v1.x; o[5] += v1.y; o[6] += v1.z; o[7] += v1.w;
           }
           store8(p, o, gm, bidx, n);
         }

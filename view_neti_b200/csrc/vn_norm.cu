@@ -412,8 +412,6 @@ __global__ void __launch_bounds__(MAXT, 1) gn_fused_kernel(const bf16* __restric
   constexpr int kPairs = 64;                       // (group, statistic) pairs per image: groups <= 32
   __shared__ __align__(16) float s_part[2][MAXT * 8];   // [statistic][thread's 8 channels]; reused as double4[MAXT] later
   __shared__ double s_tot[kPairs];
-  __shared__ double s_red2[kPairs * 8];
-  __shared__ float s_red[kPairs * 8];
   __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups], s_s1[kMaxGroups], s_s2[kMaxGroups];
   const int b = blockIdx.y;
   const int cpg = C / groups;
@@ -511,27 +509,35 @@ __global__ void __launch_bounds__(MAXT, 1) gn_fused_kernel(const bf16* __restric
   }
   __syncthreads();
   const int T = blockDim.x;
-  const int L = T >> 6;                            // lanes per pair (host guarantees T >= 64), <= 8
-  {
-    // thread (slot, v) wrote channels [v*8, v*8+8) at slot*C: group g of statistic st = k runs of cpg floats
-    if ((int)threadIdx.x < kPairs * L) {
-      const int pr = threadIdx.x / L, sub = threadIdx.x - pr * L;
-      float sum = 0.f;
-      if (pr < 2 * groups) {
-        const int g = pr >> 1, st = pr & 1;
-        const float* src = &s_part[st][g * cpg];
-        for (int sl = 0; sl < k; ++sl, src += C)       // (no integer division: it costs more than the whole loop)
-          for (int ch = sub; ch < cpg; ch += L) sum += src[ch];
+  // L = 4 / 2 / 1 adjacent lanes per (group, statistic) pair: the first 64*L threads (whole warps) do the reduction
+  const int lsh = T >= 256 ? 2 : T >= 128 ? 1 : 0;
+  const int L = 1 << lsh;
+  if ((int)threadIdx.x < kPairs * L) {
+    // thread (slot, v) wrote channels [v*8, v*8+8) at slot*C: pair (g, st) = k runs of cpg contiguous floats.  A lane
+    // takes whole runs (k >= L) or a segment of one run (k < L); loads are independent, so the loop pipelines.
+    const int pr = threadIdx.x >> lsh, sub = threadIdx.x & (L - 1);
+    float sum = 0.f;
+    if (pr < 2 * groups) {
+      const int g = pr >> 1, st = pr & 1;
+      int sl = sub, sl_step = L, seg = 0, psh = 0;
+      if (k < L) {
+        psh = k == 1 ? lsh : (k == 2 && L == 4) ? 1 : 0;      // parts = L / k rounded down to a power of two
+        while (sl >= k) { sl -= k; ++seg; }
+        sl_step = k;                                           // one run per lane
+        if (seg >= (1 << psh)) sl = k;                         // surplus lane
       }
-      s_red[pr * 8 + sub] = sum;
+      const int c_lo = (seg * cpg) >> psh, c_hi = ((seg + 1) * cpg) >> psh;
+      for (; sl < k; sl += sl_step) {
+        const float* src = &s_part[st][sl * C + g * cpg];
+#pragma unroll 4
+        for (int ch = c_lo; ch < c_hi; ++ch) sum += src[ch];
+      }
     }
-    __syncthreads();
-    if (threadIdx.x < kPairs) {
-      float v = 0.f;
-      for (int u = 0; u < L; ++u) v += s_red[threadIdx.x * 8 + u];
-      unsigned bits = __float_as_uint(v);
+    for (int o = L >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (sub == 0) {
+      unsigned bits = __float_as_uint(sum);
       if (bits == 0xffffffffu) bits = 0x7fffffffu;             // 0xffffffff is the "not written yet" pattern
-      __stcg(reinterpret_cast<unsigned*>(part) + ((long long)b * gridDim.x + blockIdx.x) * kPairs + threadIdx.x, bits);
+      __stcg(reinterpret_cast<unsigned*>(part) + ((long long)b * gridDim.x + blockIdx.x) * kPairs + pr, bits);
     }
   }
   GN_STAMP(4);
@@ -575,23 +581,28 @@ __global__ void __launch_bounds__(MAXT, 1) gn_fused_kernel(const bf16* __restric
       }
     }
     GN_STAMP(6);
-    double* red4 = reinterpret_cast<double*>(&s_part[0][0]);        // [thread][4]; s_part is dead (synced above)
-    red4[threadIdx.x * 4 + 0] = t0; red4[threadIdx.x * 4 + 1] = t1;
-    red4[threadIdx.x * 4 + 2] = t2; red4[threadIdx.x * 4 + 3] = t3;
-    __syncthreads();
-    // pair pr lives in component (pr & 3) of the threads j with j % 16 == pr >> 2; L lanes share the T/16 addends
-    if ((int)threadIdx.x < kPairs * L) {
-      const int pr = threadIdx.x / L, sub = threadIdx.x - pr * L;
-      double tot = 0.0;
-      for (int j = (pr >> 2) + 16 * sub; j < T; j += 16 * L) tot += red4[j * 4 + (pr & 3)];
-      s_red2[pr * 8 + sub] = tot;
+    // thread t holds the sums of pairs 4*(t%16) .. +3 over its CTAs: lanes l and l+16 of a (whole) warp share a quad
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwhole = T >> 5, nw = (T + 31) >> 5;
+    if (wid < nwhole) {
+      t0 += __shfl_xor_sync(0xffffffffu, t0, 16); t1 += __shfl_xor_sync(0xffffffffu, t1, 16);
+      t2 += __shfl_xor_sync(0xffffffffu, t2, 16); t3 += __shfl_xor_sync(0xffffffffu, t3, 16);
+    }
+    double* wq = reinterpret_cast<double*>(&s_part[0][0]);          // [warp][16 quads][4]; s_part is dead (synced above)
+    if (lane < 16) {
+      double* d = wq + (wid * 16 + lane) * 4;
+      d[0] = t0; d[1] = t1; d[2] = t2; d[3] = t3;
     }
     __syncthreads();
-    if ((int)threadIdx.x < 2 * groups) {
+    if ((int)threadIdx.x < kPairs * L) {
+      const int pr = threadIdx.x >> lsh, sub = threadIdx.x & (L - 1);
       double tot = 0.0;
-      for (int u = 0; u < L; ++u) tot += s_red2[threadIdx.x * 8 + u];
-      s_tot[threadIdx.x] = tot;
-      if (blockIdx.x == 0) acc[(long long)b * groups * 2 + threadIdx.x] = tot;   // kept for the backward / the caller
+      for (int w = sub; w < nw; w += L) tot += wq[(w * 16 + (pr >> 2)) * 4 + (pr & 3)];
+      for (int o = L >> 1; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      if (sub == 0 && pr < 2 * groups) {
+        s_tot[pr] = tot;
+        if (blockIdx.x == 0) acc[(long long)b * groups * 2 + pr] = tot;     // kept for the backward / the caller
+      }
     }
     __syncthreads();
   }
