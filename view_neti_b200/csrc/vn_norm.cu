@@ -410,8 +410,9 @@ __global__ void __launch_bounds__(MAXT, 1) gn_fused_kernel(const bf16* __restric
   GN_STAMP(1);
   constexpr int NR = NP > 0 ? NP : 1;
   constexpr int kPairs = 64;                       // (group, statistic) pairs per image: groups <= 32
-  __shared__ __align__(16) float s_part[2][MAXT * 8];   // [statistic][thread's 8 channels]; reused as double4[MAXT] later
+  __shared__ __align__(16) float s_part[2][MAXT * 8];   // [statistic][thread's 8 channels]
   __shared__ double s_tot[kPairs];
+  __shared__ double s_wq[(MAXT / 32) * 16 * 4];
   __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups], s_s1[kMaxGroups], s_s2[kMaxGroups];
   const int b = blockIdx.y;
   const int cpg = C / groups;
@@ -588,7 +589,7 @@ __global__ void __launch_bounds__(MAXT, 1) gn_fused_kernel(const bf16* __restric
       t0 += __shfl_xor_sync(0xffffffffu, t0, 16); t1 += __shfl_xor_sync(0xffffffffu, t1, 16);
       t2 += __shfl_xor_sync(0xffffffffu, t2, 16); t3 += __shfl_xor_sync(0xffffffffu, t3, 16);
     }
-    double* wq = reinterpret_cast<double*>(&s_part[0][0]);          // [warp][16 quads][4]; s_part is dead (synced above)
+    double* wq = s_wq;        // [warp][16 quads][4]; NOT aliased on s_part: its readers are not synchronised with us
     if (lane < 16) {
       double* d = wq + (wid * 16 + lane) * 4;
       d[0] = t0; d[1] = t1; d[2] = t2; d[3] = t3;
