@@ -1,4 +1,5 @@
-"""Aggregate an ncu launch-list CSV (gpu__time_duration.sum) of scripts/profile_step.py: last step only."""
+"""Aggregate an ncu launch-list CSV (gpu__time_duration.sum) of `bench.py --steps 2 --warmup 1`: the last COMPLETE
+train step in the list (a step starts with the statistics memsets just before timestep_sinusoid_kernel)."""
 import collections, csv, sys
 path = sys.argv[1]
 detail = sys.argv[2] if len(sys.argv) > 2 else ""
@@ -7,7 +8,7 @@ with open(path) as f:
 rows = list(csv.DictReader(lines))
 names = [r["Kernel Name"] for r in rows]
 idx = [i for i, x in enumerate(names) if "timestep_sinusoid" in x]
-step = rows[idx[-1] - 1:]       # from the stats memset just before it
+step = rows[idx[-2]:idx[-1]] if len(idx) >= 2 else rows[idx[-1]:]
 agg = collections.defaultdict(lambda: [0, 0.0])
 det = collections.defaultdict(lambda: [0, 0.0])
 for r in step:
