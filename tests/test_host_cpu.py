@@ -143,3 +143,22 @@ def test_neti_mapper_structure_matches_reference():
     assert torch.allclose(x, torch.tensor([[-1., -1., -1., -1.], [0.998, 0.875, 1., 1.]]))
     with pytest.raises(VNError):
         mv(torch.tensor([0.]), torch.tensor([0.]), torch.tensor([49408]))           # CPU: fails loudly, no fallback
+
+
+def test_gemm_tuning_table_is_well_formed():
+    """view_neti_b200/gemm_tuning.json (written by scripts/gemm_autotune.py on B200) only holds choices vn_gemm accepts:
+    BN in {64,128,160,192,256}, split-K cluster in {1,2,4,8} with BN/split a multiple of 8, BN 160 never unsplit,
+    CTA pairs (bit 8) only without split-K and for BN >= 128."""
+    from view_neti_b200 import ops
+    assert len(ops.TUNING) > 50
+    for key, (bn, code) in ops.TUNING.items():
+        mode, M, N, K, H, W = (int(v) for v in key.split(":"))
+        assert mode in (0, 1) and M > 0 and N % 8 == 0 and K % 64 == 0, key
+        split, pair = code & 15, (code >> 8) & 3
+        assert bn in (64, 128, 160, 192, 256), (key, bn)
+        assert split in (1, 2, 4, 8) and (bn // split) % 8 == 0, (key, bn, split)
+        assert not (bn == 160 and split == 1), key
+        if pair == 1:
+            assert split == 1 and bn in (128, 192, 256), (key, bn, code)
+            if mode == 0:                      # (conv m-tiles depend on the spatial tiling; vn_gemm falls back if odd)
+                assert ((M + 127) // 128) % 2 == 0, key

@@ -8,22 +8,28 @@
 //
 // One kernel template, two schedules:
 //   PERSISTENT (SPLIT = false): grid = min(tiles, #SMs), one CTA per SM walks 128 x BN output tiles.
-//     warp 0    : TMA producer — A tile [128 x 64] + B tile [BN x 64] per stage (128B swizzle); conv mode takes A from a
-//                 4-D NHWC tensor map, one (tap, 64-channel) slab per k-block at (c0, w0+dx-1, h0+dy-1, img): TMA
-//                 zero-fills the halo, so padding is free and no im2col buffer exists.  It also prefetches the
-//                 residual tile into the output staging buffer.
+//     warp 0    : TMA producer of the A tiles [128 x 64] (128B swizzle); conv mode takes A from a 4-D NHWC tensor map,
+//                 one (tap, 64-channel) slab per k-block at (c0, w0+dx-1, h0+dy-1, img): TMA zero-fills the halo, so
+//                 padding is free and no im2col buffer exists.  It also prefetches the residual tile into the output
+//                 staging buffer.  The loop carries no division / modulo: one thread's issue latency per k-block
+//                 bounds the whole main loop.
+//     last warp : TMA producer of the B (weight) tiles [BN x 64]: same empty barriers, its own thread.
 //     warp 1    : MMA issuer — one lane issues 4 x tcgen05.mma (K=16) per stage into one of TWO TMEM accumulator
 //                 stages, so the epilogue of tile i overlaps the main loop of tile i+1.
-//     warps 2-5 : epilogue — tcgen05.ld, + bias / time-embedding row-bias / residual (read from smem), bf16 pack into
-//                 the swizzled staging tile, TMA store (clips the M / N tails).
+//     warps 2-9 : epilogue, two warps per TMEM lane quarter (each half of the tile's columns) — tcgen05.ld pipelined one
+//                 chunk ahead, + bias / time-embedding row-bias / residual (read from smem), bf16 pack into the swizzled
+//                 staging tile, TMA store (clips the M / N tails).
+//     CG = 2   : CTA PAIRS (tcgen05.mma.cta_group::2).  Two m-tiles of one n-tile form a 256 x BN tile; each CTA loads
+//                its A rows and HALF of the B rows, every load completes on the LEADER's mbarrier, the leader issues the
+//                MMAs for the pair and multicasts tcgen05.commit to both CTAs; TMEM is allocated with cta_group::2.
 //     MC > 1   : thread-block clusters of MC CTAs along M share every B (weight) tile: each CTA loads 1/MC of it and
-//                TMA-MULTICASTS the slice into the shared memory of all CTAs of the cluster, so an SM requests
-//                A + B/MC bytes per k-block instead of A + B (the operand stream out of L2, not the tensor pipe, bounds
-//                these tiles).  A stage is released to the producers by a multicast tcgen05.commit from every CTA.
-//   SPLIT-K (SPLIT = true): for few-tile / long-K problems (deep UNet levels, M = 64..1024).  A thread-block CLUSTER of
-//     S in {2,4,8} CTAs shares one output tile, each CTA accumulates K/S in its own TMEM; partials are exchanged
-//     through DISTRIBUTED SHARED MEMORY (st.shared::cluster), CTA r reduces rows [r*128/S, (r+1)*128/S) and runs
-//     the epilogue for them.  No global atomics, no workspace, deterministic.
+//                TMA-MULTICASTS the slice into the shared memory of all CTAs of the cluster (opt-in: measured no gain).
+//   SPLIT-K (SPLIT = true): for few-tile / long-K problems (deep UNet levels, M = 64..1024) and for BN = 160.  A
+//     thread-block CLUSTER of S in {2,4,8} CTAs shares one output tile, each CTA accumulates K/S in its own TMEM;
+//     partials are exchanged through DISTRIBUTED SHARED MEMORY (16-byte st.shared::cluster, column-quad-packed), CTA r
+//     reduces rows [r*128/S, (r+1)*128/S) and runs the epilogue for them.  No global atomics, no workspace,
+//     deterministic.
+// scripts/kernel_timeline.py (-DVN_TIMELINE build) shows where the microseconds of one launch go.
 #include "vn_tma.cuh"
 
 #include <stdlib.h>
@@ -61,11 +67,13 @@ struct GemmParams {
   long long* dbg;       // optional in-kernel timeline (vn_set_debug_buffer): 16 slots per CTA, clock64 stamps
 };
 
+#ifdef VN_TIMELINE
 __device__ __forceinline__ long long gtimer_ns() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#endif
 #ifdef VN_TIMELINE
 #define VN_STAMP(slot)                                                          \
   do {                                                                          \
@@ -88,9 +96,6 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
-}
-__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {
   asm volatile(
