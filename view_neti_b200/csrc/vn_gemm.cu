@@ -64,6 +64,7 @@ struct GemmParams {
   int out_fp32;
   int use_tma_epilogue;
   int nbimg;            // images (conv mode); tiles of a padded cluster slot may decode to img >= nbimg
+  int pf_dist;          // weight look-ahead of the B producer in k-blocks (0 = off), see vn_gemm()
   long long* dbg;       // optional in-kernel timeline (vn_set_debug_buffer): 16 slots per CTA, clock64 stamps
 };
 
@@ -152,6 +153,12 @@ __device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst_smem) {
 template <int NCOLS>
 __device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// pull one B box into L2 without landing it anywhere (weight look-ahead of the B producer)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1)
+               : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -326,6 +333,18 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     kb_begin = 0;
     nkb = p.kb_total;
   }
+  // Weight look-ahead (launches that stream a large, cold weight matrix through few CTAs: M <= 256).  With 3-6 stages of
+  // shared memory a CTA keeps ~100 KB of weights in flight, one stage turn-over per DRAM round trip - a third of the
+  // HBM rate over 80 CTAs.  The B producer warp, which has slack, pulls the k-blocks `pf_dist` ahead into L2 with
+  // cp.async.bulk.prefetch.tensor (no shared memory, no barrier); the first ones even before griddepcontrol.wait,
+  // because nothing on the device ever writes the frozen weights.
+  constexpr int kBWarp = SPLIT ? 6 : 2 + 4 * kEpiHalves;
+  if (kProducers == 2 && MC == 1 && p.pf_dist > 0 && warp == kBWarp && lane == 0 && tile_begin < num_tiles) {
+    int n0 = (VN_TILE_OF(tile_begin) / p.m_tiles) * BN;
+    if (CG == 2) n0 += (int)crank * (((min(BN, p.N - n0) + 15) & ~15) >> 1);
+    const int pf_end = min(nkb, p.pf_dist);
+    for (int i = 0; i < pf_end; ++i) tma_prefetch_l2_2d(&tmB, (kb_begin + i) * BK, n0);
+  }
   pdl_wait();          // everything above overlapped the previous kernel; activations are touched only from here on
   if (threadIdx.x == 0) VN_STAMP(3);
   const bool tma_epi = !SPLIT && p.use_tma_epilogue;
@@ -394,7 +413,7 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
       }
     }
     __syncwarp();
-  } else if (kProducers == 2 && MC == 1 && warp == (SPLIT ? 6 : 2 + 4 * kEpiHalves)) {
+  } else if (kProducers == 2 && MC == 1 && warp == kBWarp) {
     // ================= second TMA producer: the B (weight) tiles =================
     // Issue latency of the single producer thread bounds the main loop; the B loads of a stage need nothing from the
     // A producer but the drained stage (same empty barrier) - their complete_tx may land before its expect_tx, the
@@ -413,6 +432,7 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
         }
         int kx = kb_begin * BK;
         for (int i = 0; i < nkb; ++i) {
+          if (p.pf_dist > 0 && i + p.pf_dist < nkb) tma_prefetch_l2_2d(&tmB, kx + p.pf_dist * BK, n0);
           mbar_wait(&empty_bar[s], ph);
           if (CG == 2) tma_load_2d_cg2(smem + s * STAGE_BYTES + A_BYTES, &tmB, lead_full + (uint32_t)(s * 8), kx, n0);
           else tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &tmB, &full_bar[s], kx, n0);
@@ -889,6 +909,16 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
   p.n_tiles = vn_cdiv(d->N, bn);
   p.nbimg = d->mode == 1 ? d->nb : 1;
   p.dbg = vn_debug_buffer();
+  {
+    // weight look-ahead: few m-tiles stream a big weight matrix (>= 4 MB) - keep ~256 KB per CTA requested ahead
+    static int pf_env = -1;
+    if (pf_env < 0) { const char* e = getenv("VN_GEMM_LOOKAHEAD"); pf_env = e ? atoi(e) : 1; }
+    p.pf_dist = 0;
+    if (pf_env && p.m_tiles <= 2 && (long long)d->N * d->K * 2 >= (4ll << 20)) {
+      int dist = 262144 / (bn * BK * 2);
+      p.pf_dist = dist < 8 ? 8 : dist > 48 ? 48 : dist;
+    }
+  }
   // multicast clusters along M (persistent schedule only): every CTA of a cluster works on the same n-tile
   int mc = 1;
   if (splits == 1) {
