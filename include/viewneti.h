@@ -198,6 +198,21 @@ int vn_mse_loss(const float* pred, const float* target, int64_t n, float loss_sc
  * latents fp32 [n] updated in place.  acp_t / acp_prev = alphas_cumprod at t / t_prev; vpred: 0 eps, 1 v. */
 int vn_cfg_ddim_step(float* latents, const float* eps_uncond, const float* eps_cond, int64_t n,
                      float guidance, float acp_t, float acp_prev, int vpred, vn_stream_t s);
+/* ------------------------------------------------------------------------------------------------
+ * CLIP text transformer pieces (the batched conditioning path: reference
+ * models/neti_clip_text_encoder.py:57-225 runs transformers' CLIPEncoder once per UNet layer; here the 16 passes are one batch).
+ * Projections / LayerNorms use vn_gemm / vn_layernorm_*.
+ *   vn_gelu_*            CLIPMLP activation (erf GELU): y = gelu(h);  dh = dy * gelu'(h).
+ *   vn_seq_attention_*   CLIPAttention core for short sequences (nq == nk <= 128, head_dim 64), optional causal mask
+ *                        (CLIPTextTransformer._build_causal_attention_mask); same descriptor as vn_attention_*; lse is
+ *                        the natural-log sum-exp of the scaled logits; bwd needs q,k,v,o,lse,d_o and writes dq,dk,dv.
+ * ------------------------------------------------------------------------------------------------ */
+int vn_gelu_fwd(const void* h, int64_t ldh, void* y, int64_t ldy, int rows, int F, vn_stream_t s);
+int vn_gelu_bwd(const void* h, int64_t ldh, const void* dy, int64_t lddy, void* dh, int64_t lddh, int rows, int F,
+                vn_stream_t s);
+int vn_seq_attention_fwd(const struct vn_attn_desc* d, int causal, vn_stream_t s);
+int vn_seq_attention_bwd(const struct vn_attn_desc* d, int causal, vn_stream_t s);
+
 int vn_memset_zero(void* p, size_t bytes, vn_stream_t s);
 int vn_memset(void* p, int byte_value, size_t bytes, vn_stream_t s);
 

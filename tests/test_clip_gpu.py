@@ -1,0 +1,101 @@
+"""-m gpu: the CLIP text-transformer encoder of the conditioning path through the C-ABI against the
+CPU oracle (oracle/clip_encoder.py, itself pinned to transformers' CLIPEncoder in tests/test_oracle_cpu.py)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert torch.isfinite(a).all()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def test_gelu_fwd_bwd_matches_torch():
+    from view_neti_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    h = (2.0 * torch.randn(1232, 4096, generator=g)).cuda().to(BF)
+    dy = torch.randn(1232, 4096, generator=g).cuda().to(BF)
+    y, dh = torch.empty_like(h), torch.empty_like(h)
+    ops.gelu_fwd(h, y, h.shape[0])
+    ops.gelu_bwd(h, dy, dh, h.shape[0])
+    hr = h.float().requires_grad_(True)
+    yr = F.gelu(hr)
+    yr.backward(dy.float())
+    assert rel(y, yr) < 4e-3 and rel(dh, hr.grad) < 4e-3
+
+
+@pytest.mark.parametrize("nseq,heads,L,causal", [(16, 16, 77, True), (3, 4, 77, False), (2, 2, 32, True), (1, 1, 128, True)])
+def test_seq_attention_matches_torch(nseq, heads, L, causal):
+    from view_neti_b200 import ops
+    C = heads * 64
+    g = torch.Generator().manual_seed(2)
+    qkv = torch.randn(nseq, L, 3 * C, generator=g).cuda().to(BF)      # q / k / v as column slices of one buffer
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    d_o = torch.randn(nseq, L, C, generator=g).cuda().to(BF)
+    o = torch.empty(nseq, L, C, dtype=BF, device="cuda")
+    lse = torch.empty(nseq, heads, L, device="cuda")
+    dqkv = torch.zeros_like(qkv)
+    ops.seq_attention_fwd(q, k, v, o, lse, heads, scale=0.125, causal=causal)
+    ops.seq_attention_bwd(q, k, v, o, lse, d_o, dqkv[..., :C], dqkv[..., C:2 * C], dqkv[..., 2 * C:], heads, scale=0.125,
+                          causal=causal)
+    qr, kr, vr = (t.float().view(nseq, L, heads, 64).transpose(1, 2).detach().requires_grad_(True) for t in (q, k, v))
+    s = (qr @ kr.transpose(-1, -2)) * 0.125
+    if causal:
+        s = s + torch.full((L, L), float("-inf"), device="cuda").triu(1)
+    orf = torch.softmax(s, -1) @ vr
+    orf.backward(d_o.float().view(nseq, L, heads, 64).transpose(1, 2))
+    back = lambda t: t.transpose(1, 2).reshape(nseq, L, C)      # noqa: E731
+    assert rel(o, back(orf)) < 5e-3
+    assert rel(lse, torch.logsumexp(s, -1)) < 1e-4
+    assert rel(dqkv[..., :C], back(qr.grad)) < 8e-3
+    assert rel(dqkv[..., C:2 * C], back(kr.grad)) < 8e-3
+    assert rel(dqkv[..., 2 * C:], back(vr.grad)) < 8e-3
+
+
+@pytest.mark.parametrize("hidden,heads,layers,inter,nseq", [(1024, 16, 3, 4096, 16), (256, 4, 2, 1024, 5)])
+def test_clip_encoder_matches_oracle(hidden, heads, layers, inter, nseq):
+    """SD-2.1 text-encoder width (1024 x 16 heads, 4096 MLP) at 16 stacked per-UNet-layer passes of 77 tokens (B = 1),
+    3 of the 23 layers so the fp32 CPU oracle stays quick: last_hidden_state and d(inputs_embeds)."""
+    from oracle.clip_encoder import encoder_forward, init_state_dict
+    from view_neti_b200.models.clip_encoder import CLIPEncoder, ClipEncoderConfig
+    sd = init_state_dict(hidden, heads, layers, inter, seed=7)
+    cfg = ClipEncoderConfig(hidden_size=hidden, num_attention_heads=heads, num_hidden_layers=layers, intermediate_size=inter)
+    enc = CLIPEncoder(sd, cfg, "cuda")
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(nseq, 77, hidden, generator=g)
+    dy = torch.randn(nseq, 77, hidden, generator=g)
+    xo = x.clone().requires_grad_(True)
+    yo = encoder_forward(sd, xo, heads, layers)
+    yo.backward(dy)
+    for rep in range(3):                       # eager, then two CUDA-graph replays
+        xg = x.cuda().requires_grad_(True)
+        out = enc(inputs_embeds=xg, attention_mask=None, causal_attention_mask=None)
+        y = out[0]
+        y.backward(dy.cuda())
+        assert out.last_hidden_state is y
+        e_y, e_dx = rel(y, yo), rel(xg.grad, xo.grad)
+        assert e_y < 1e-2, (rep, e_y)
+        assert e_dx < 2e-2, (rep, e_dx)
+    # only the rows of a changed token and the rows after it move (causal mask), exactly as in the oracle test
+    x2 = x.clone()
+    x2[:, 50:] += 0.5
+    y2 = enc(inputs_embeds=x2.cuda())[0]
+    assert float((y2[:, :50] - y.detach()[:, :50]).abs().max()) == 0.0
+
+
+def test_clip_encoder_rejects_unsupported_calls():
+    from oracle.clip_encoder import init_state_dict
+    from view_neti_b200._abi import VNError
+    from view_neti_b200.models.clip_encoder import CLIPEncoder, ClipEncoderConfig
+    cfg = ClipEncoderConfig(hidden_size=128, num_attention_heads=2, num_hidden_layers=1, intermediate_size=256)
+    enc = CLIPEncoder(init_state_dict(128, 2, 1, 256), cfg, "cuda")
+    with pytest.raises(VNError):
+        enc(inputs_embeds=torch.zeros(1, 77, 128))                                  # CPU tensor: no fallback
+    with pytest.raises(VNError):
+        enc(inputs_embeds=torch.zeros(1, 77, 128, device="cuda"), attention_mask=torch.ones(1, 77, device="cuda"))

@@ -129,3 +129,29 @@ def test_context_gradient_matches_finite_differences():
             vals.append(torch.nn.functional.mse_loss(e, tgt.double()).item())
         fd = (vals[0] - vals[1]) / (2 * h)
         assert abs(fd - g[key][idx].item()) <= 1e-6 + 1e-3 * abs(fd), (key, fd, g[key][idx].item())
+
+
+def test_clip_encoder_oracle_matches_transformers_clipencoder():
+    """The conditioning path's arithmetic lives in transformers' CLIPEncoder (reference neti_clip_text_encoder.py:53);
+    the restatement in oracle/clip_encoder.py is pinned to that class itself: outputs and input gradients agree to fp32
+    round-off, and the causal mask makes position i independent of later tokens."""
+    import torch
+    from oracle.clip_encoder import encoder_forward, hf_encoder, init_state_dict
+    hidden, heads, layers, inter = 128, 2, 3, 512
+    sd = init_state_dict(hidden, heads, layers, inter, seed=3)
+    run = hf_encoder(sd, hidden, heads, layers, inter)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(3, 77, hidden, generator=g)
+    dy = torch.randn(3, 77, hidden, generator=g)
+    x1 = x.clone().requires_grad_(True)
+    y1 = run(x1)
+    y1.backward(dy)
+    x2 = x.clone().requires_grad_(True)
+    y2 = encoder_forward(sd, x2, heads, layers)
+    y2.backward(dy)
+    assert float((y1 - y2).abs().max()) < 2e-5 * float(y1.abs().max())
+    assert float((x1.grad - x2.grad).abs().max()) < 2e-5 * float(x1.grad.abs().max())
+    xp = x.clone()
+    xp[:, 40:] += 1.0
+    yp = encoder_forward(sd, xp, heads, layers)
+    assert float((yp[:, :40] - y2[:, :40]).abs().max()) == 0.0 and float((yp[:, 40:] - y2[:, 40:]).abs().max()) > 1e-3

@@ -83,6 +83,10 @@ SIGNATURES = {
     "vn_layernorm_bwd": (C.c_int, [_P, _L, _P, _L, _P, _P, _P, _L, _P, _L, _I, _I, _P]),
     "vn_geglu_fwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _P]),
     "vn_geglu_bwd": (C.c_int, [_P, _L, _P, _L, _P, _L, _I, _I, _P]),
+    "vn_gelu_fwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _P]),
+    "vn_gelu_bwd": (C.c_int, [_P, _L, _P, _L, _P, _L, _I, _I, _P]),
+    "vn_seq_attention_fwd": (C.c_int, [C.POINTER(AttnDesc), _I, _P]),
+    "vn_seq_attention_bwd": (C.c_int, [C.POINTER(AttnDesc), _I, _P]),
     "vn_attention_fwd": (C.c_int, [C.POINTER(AttnDesc), _P]),
     "vn_attention_bwd": (C.c_int, [C.POINTER(AttnDesc), _P]),
     "vn_upsample2x_fwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _I, _I, _P]),

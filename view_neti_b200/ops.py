@@ -229,6 +229,30 @@ def attention_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, heads, scale=0.125, d
     check(_abi.load().vn_attention_bwd(C.byref(d), stream()), "attention_bwd")
 
 
+def seq_attention_fwd(q, k, v, o, lse, heads, scale=0.125, causal=True):
+    """Short-sequence (<= 128 tokens) attention, optional causal mask: CLIPAttention core of the text transformer."""
+    d = _attn_desc(q, k, v, o, lse, heads, scale)
+    check(_abi.load().vn_seq_attention_fwd(C.byref(d), int(causal), stream()), "seq_attention_fwd")
+
+
+def seq_attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, heads, scale=0.125, causal=True):
+    d = _attn_desc(q, k, v, o, lse, heads, scale)
+    d.d_o, d.lddo, d.bsdo = ptr(d_o), d_o.stride(1), d_o.stride(0)
+    d.dq, d.lddq, d.bsdq = ptr(dq), dq.stride(1), dq.stride(0)
+    d.dk, d.lddk, d.bsdk = ptr(dk), dk.stride(1), dk.stride(0)
+    d.dv, d.lddv, d.bsdv = ptr(dv), dv.stride(1), dv.stride(0)
+    check(_abi.load().vn_seq_attention_bwd(C.byref(d), int(causal), stream()), "seq_attention_bwd")
+
+
+def gelu_fwd(h, y, rows):
+    check(_abi.load().vn_gelu_fwd(ptr(h), _ld(h), ptr(y), _ld(y), rows, h.shape[-1], stream()), "gelu_fwd")
+
+
+def gelu_bwd(h, dy, dh, rows):
+    check(_abi.load().vn_gelu_bwd(ptr(h), _ld(h), ptr(dy), _ld(dy), ptr(dh), _ld(dh), rows, h.shape[-1], stream()),
+          "gelu_bwd")
+
+
 # ---- resampling / edge convs / glue -------------------------------------------------------------
 def upsample2x_fwd(x, y):
     nb, H, W, Cc = x.shape
