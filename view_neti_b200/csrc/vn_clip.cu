@@ -88,9 +88,9 @@ __device__ __forceinline__ void load_head(float* dst, const bf16* src, long long
 __global__ void __launch_bounds__(128) seq_attn_fwd_kernel(const SeqAttnParams p) {
   pdl_trigger();
   extern __shared__ float sm[];
-  float* sK = sm;
-  float* sV = sm + kMaxL * HD;
   const int h = blockIdx.x, b = blockIdx.y, L = p.L;
+  float* sK = sm;
+  float* sV = sm + L * HD;
   pdl_wait();
   load_head(sK, p.k + (long long)b * p.bsk + h * HD, p.ldk, L);
   load_head(sV, p.v + (long long)b * p.bsv + h * HD, p.ldv, L);
@@ -141,61 +141,79 @@ __global__ void __launch_bounds__(128) seq_attn_fwd_kernel(const SeqAttnParams p
   p.lse[((long long)b * p.heads + h) * L + i] = m + __logf(l);
 }
 
+// Backward: three independent jobs per (sequence, head), one kernel instantiation each (so each gets its own register
+// budget / occupancy): JOB 0: dQ (thread = query row; K, V in shared memory), JOB 1: dV, JOB 2: dK (thread = key row;
+// Q, dO in shared memory).  Every job recomputes the probabilities it needs from q.k and the saved lse; dK / dV are
+// plain per-thread sums over the (causal) query rows: no atomics, deterministic.
+template <int JOB>
 __global__ void __launch_bounds__(128) seq_attn_bwd_kernel(const SeqAttnParams p) {
   pdl_trigger();
   extern __shared__ float sm[];
-  float* sQ = sm;
-  float* sK = sQ + kMaxL * HD;
-  float* sV = sK + kMaxL * HD;
-  float* sdO = sV + kMaxL * HD;
-  float* sLse = sdO + kMaxL * HD;                 // [L]
-  float* sDelta = sLse + kMaxL;                   // [L]  delta_i = dO_i . O_i
+  constexpr int job = JOB;
   const int h = blockIdx.x, b = blockIdx.y, L = p.L;
+  float* sA = sm;                                  // job 0: K      jobs 1, 2: Q
+  float* sB = sA + L * HD;                         // job 0: V      jobs 1, 2: dO
+  float* sLse = sB + L * HD;                       // [L]
+  float* sDelta = sLse + L;                        // [L]  delta_i = dO_i . O_i
   pdl_wait();
-  load_head(sQ, p.q + (long long)b * p.bsq + h * HD, p.ldq, L);
-  load_head(sK, p.k + (long long)b * p.bsk + h * HD, p.ldk, L);
-  load_head(sV, p.v + (long long)b * p.bsv + h * HD, p.ldv, L);
-  load_head(sdO, p.d_o + (long long)b * p.bsdo + h * HD, p.lddo, L);
+  if (job == 0) {
+    load_head(sA, p.k + (long long)b * p.bsk + h * HD, p.ldk, L);
+    load_head(sB, p.v + (long long)b * p.bsv + h * HD, p.ldv, L);
+  } else {
+    load_head(sA, p.q + (long long)b * p.bsq + h * HD, p.ldq, L);
+    load_head(sB, p.d_o + (long long)b * p.bsdo + h * HD, p.lddo, L);
+  }
   const int t = threadIdx.x;
   if (t < L) {
     sLse[t] = p.lse[((long long)b * p.heads + h) * L + t];
-    const bf16* orow = p.o + (long long)b * p.bso + (long long)t * p.ldo + h * HD;
-    const bf16* drow = p.d_o + (long long)b * p.bsdo + (long long)t * p.lddo + h * HD;
-    float d = 0.f;
+    if (job != 1) {
+      const bf16* orow = p.o + (long long)b * p.bso + (long long)t * p.ldo + h * HD;
+      const bf16* drow = p.d_o + (long long)b * p.bsdo + (long long)t * p.lddo + h * HD;
+      float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-    for (int c = 0; c < HD; c += 8) {
-      float a[8], g[8];
-      unpack8f(__ldg(reinterpret_cast<const uint4*>(orow + c)), a);
-      unpack8f(__ldg(reinterpret_cast<const uint4*>(drow + c)), g);
+      for (int c = 0; c < HD; c += 8) {
+        float a[8], g[8];
+        unpack8f(__ldg(reinterpret_cast<const uint4*>(orow + c)), a);
+        unpack8f(__ldg(reinterpret_cast<const uint4*>(drow + c)), g);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) d = fmaf(a[u], g[u], d);
+        for (int u = 0; u < 8; u += 2) { d0 = fmaf(a[u], g[u], d0); d1 = fmaf(a[u + 1], g[u + 1], d1); }
+      }
+      sDelta[t] = d0 + d1;
     }
-    sDelta[t] = d;
   }
   __syncthreads();
   if (t >= L) return;
-  // ---- phase A: thread = query row i: dq_i = scale * sum_j ds_ij k_j,  ds_ij = p_ij (dO_i . v_j - delta_i) ----
-  {
+  if (job == 0) {
+    // ---- dq_i = scale * sum_j ds_ij k_j,  ds_ij = p_ij (dO_i . v_j - delta_i) ----
     const int i = t;
     float q[HD], g[HD], dq[HD];
+    {
+      const bf16* qr = p.q + (long long)b * p.bsq + (long long)i * p.ldq + h * HD;
+      const bf16* gr = p.d_o + (long long)b * p.bsdo + (long long)i * p.lddo + h * HD;
 #pragma unroll
-    for (int c = 0; c < HD; ++c) { q[c] = sQ[i * HD + c] * p.scale; g[c] = sdO[i * HD + c]; dq[c] = 0.f; }
+      for (int c = 0; c < HD; c += 8) {
+        unpack8f(__ldg(reinterpret_cast<const uint4*>(qr + c)), q + c);
+        unpack8f(__ldg(reinterpret_cast<const uint4*>(gr + c)), g + c);
+      }
+#pragma unroll
+      for (int c = 0; c < HD; ++c) { q[c] *= p.scale; dq[c] = 0.f; }
+    }
     const float lse = sLse[i], delta = sDelta[i];
     const int nk = p.causal ? i + 1 : L;
     for (int j = 0; j < nk; ++j) {
-      const float4* kr = reinterpret_cast<const float4*>(sK + j * HD);
-      const float4* vr = reinterpret_cast<const float4*>(sV + j * HD);
-      float s0 = 0.f, s1 = 0.f, e0 = 0.f, e1 = 0.f;
+      const float4* kr = reinterpret_cast<const float4*>(sA + j * HD);
+      const float4* vr = reinterpret_cast<const float4*>(sB + j * HD);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
 #pragma unroll
       for (int c = 0; c < HD / 4; ++c) {
         const float4 kv = kr[c], vv = vr[c];
         s0 = fmaf(q[4 * c], kv.x, s0); s1 = fmaf(q[4 * c + 1], kv.y, s1);
-        s0 = fmaf(q[4 * c + 2], kv.z, s0); s1 = fmaf(q[4 * c + 3], kv.w, s1);
+        s2 = fmaf(q[4 * c + 2], kv.z, s2); s3 = fmaf(q[4 * c + 3], kv.w, s3);
         e0 = fmaf(g[4 * c], vv.x, e0); e1 = fmaf(g[4 * c + 1], vv.y, e1);
-        e0 = fmaf(g[4 * c + 2], vv.z, e0); e1 = fmaf(g[4 * c + 3], vv.w, e1);
+        e2 = fmaf(g[4 * c + 2], vv.z, e2); e3 = fmaf(g[4 * c + 3], vv.w, e3);
       }
-      const float pij = __expf((s0 + s1) - lse);
-      const float ds = pij * ((e0 + e1) - delta) * p.scale;
+      const float pij = __expf(((s0 + s1) + (s2 + s3)) - lse);
+      const float ds = pij * (((e0 + e1) + (e2 + e3)) - delta) * p.scale;
 #pragma unroll
       for (int c = 0; c < HD / 4; ++c) {
         const float4 kv = kr[c];
@@ -206,70 +224,79 @@ __global__ void __launch_bounds__(128) seq_attn_bwd_kernel(const SeqAttnParams p
     bf16* dr = p.dq + (long long)b * p.bsdq + (long long)i * p.lddq + h * HD;
 #pragma unroll
     for (int c = 0; c < HD; c += 8) *reinterpret_cast<uint4*>(dr + c) = pack8f(dq + c);
+    return;
   }
-  // ---- phase B: thread = key row j: dv_j = sum_i p_ij dO_i,  dk_j = scale * sum_i ds_ij q_i  (i >= j when causal).
-  // Two passes over the query rows (dv, then dk) so that a thread never holds more than three 64-float vectors. ----
+  // ---- thread = key row j: dv_j = sum_i p_ij dO_i (job 1),  dk_j = scale * sum_i ds_ij q_i (job 2);  i >= j if causal ----
+  const int j = t;
+  const int i0 = p.causal ? j : 0;
+  float k[HD];
   {
-    const int j = t;
-    const int i0 = p.causal ? j : 0;
-    float k[HD];
+    const bf16* kr = p.k + (long long)b * p.bsk + (long long)j * p.ldk + h * HD;
 #pragma unroll
-    for (int c = 0; c < HD; ++c) k[c] = sK[j * HD + c] * p.scale;
-    {
-      float dv[HD];
+    for (int c = 0; c < HD; c += 8) unpack8f(__ldg(reinterpret_cast<const uint4*>(kr + c)), k + c);
 #pragma unroll
-      for (int c = 0; c < HD; ++c) dv[c] = 0.f;
-      for (int i = i0; i < L; ++i) {
-        const float4* qr = reinterpret_cast<const float4*>(sQ + i * HD);
-        const float4* gr = reinterpret_cast<const float4*>(sdO + i * HD);
-        float s0 = 0.f, s1 = 0.f;
+    for (int c = 0; c < HD; ++c) k[c] *= p.scale;
+  }
+  if (job == 1) {
+    float dv[HD];
 #pragma unroll
-        for (int c = 0; c < HD / 4; ++c) {
-          const float4 qv = qr[c];
-          s0 = fmaf(k[4 * c], qv.x, s0); s1 = fmaf(k[4 * c + 1], qv.y, s1);
-          s0 = fmaf(k[4 * c + 2], qv.z, s0); s1 = fmaf(k[4 * c + 3], qv.w, s1);
-        }
-        const float pij = __expf((s0 + s1) - sLse[i]);
+    for (int c = 0; c < HD; ++c) dv[c] = 0.f;
+    for (int i = 0; i < L; ++i) {            // same row for every thread of the warp: broadcast reads, no bank conflicts
+      if (i < i0) continue;
+      const float4* qr = reinterpret_cast<const float4*>(sA + i * HD);
+      const float4* gr = reinterpret_cast<const float4*>(sB + i * HD);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-        for (int c = 0; c < HD / 4; ++c) {
-          const float4 gv = gr[c];
-          dv[4 * c] = fmaf(pij, gv.x, dv[4 * c]); dv[4 * c + 1] = fmaf(pij, gv.y, dv[4 * c + 1]);
-          dv[4 * c + 2] = fmaf(pij, gv.z, dv[4 * c + 2]); dv[4 * c + 3] = fmaf(pij, gv.w, dv[4 * c + 3]);
-        }
+      for (int c = 0; c < HD / 4; ++c) {
+        const float4 qv = qr[c];
+        s0 = fmaf(k[4 * c], qv.x, s0); s1 = fmaf(k[4 * c + 1], qv.y, s1);
+        s2 = fmaf(k[4 * c + 2], qv.z, s2); s3 = fmaf(k[4 * c + 3], qv.w, s3);
       }
-      bf16* vr = p.dv + (long long)b * p.bsdv + (long long)j * p.lddv + h * HD;
+      const float pij = __expf(((s0 + s1) + (s2 + s3)) - sLse[i]);
 #pragma unroll
-      for (int c = 0; c < HD; c += 8) *reinterpret_cast<uint4*>(vr + c) = pack8f(dv + c);
-    }
-    {
-      float v[HD], dk[HD];
-#pragma unroll
-      for (int c = 0; c < HD; ++c) { v[c] = sV[j * HD + c]; dk[c] = 0.f; }
-      for (int i = i0; i < L; ++i) {
-        const float4* qr = reinterpret_cast<const float4*>(sQ + i * HD);
-        const float4* gr = reinterpret_cast<const float4*>(sdO + i * HD);
-        float s0 = 0.f, s1 = 0.f, e0 = 0.f, e1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < HD / 4; ++c) {
-          const float4 qv = qr[c], gv = gr[c];
-          s0 = fmaf(k[4 * c], qv.x, s0); s1 = fmaf(k[4 * c + 1], qv.y, s1);
-          s0 = fmaf(k[4 * c + 2], qv.z, s0); s1 = fmaf(k[4 * c + 3], qv.w, s1);
-          e0 = fmaf(v[4 * c], gv.x, e0); e1 = fmaf(v[4 * c + 1], gv.y, e1);
-          e0 = fmaf(v[4 * c + 2], gv.z, e0); e1 = fmaf(v[4 * c + 3], gv.w, e1);
-        }
-        const float pij = __expf((s0 + s1) - sLse[i]);
-        const float ds = pij * ((e0 + e1) - sDelta[i]) * p.scale;
-#pragma unroll
-        for (int c = 0; c < HD / 4; ++c) {
-          const float4 qv = qr[c];
-          dk[4 * c] = fmaf(ds, qv.x, dk[4 * c]); dk[4 * c + 1] = fmaf(ds, qv.y, dk[4 * c + 1]);
-          dk[4 * c + 2] = fmaf(ds, qv.z, dk[4 * c + 2]); dk[4 * c + 3] = fmaf(ds, qv.w, dk[4 * c + 3]);
-        }
+      for (int c = 0; c < HD / 4; ++c) {
+        const float4 gv = gr[c];
+        dv[4 * c] = fmaf(pij, gv.x, dv[4 * c]); dv[4 * c + 1] = fmaf(pij, gv.y, dv[4 * c + 1]);
+        dv[4 * c + 2] = fmaf(pij, gv.z, dv[4 * c + 2]); dv[4 * c + 3] = fmaf(pij, gv.w, dv[4 * c + 3]);
       }
-      bf16* kr = p.dk + (long long)b * p.bsdk + (long long)j * p.lddk + h * HD;
-#pragma unroll
-      for (int c = 0; c < HD; c += 8) *reinterpret_cast<uint4*>(kr + c) = pack8f(dk + c);
     }
+    bf16* vr = p.dv + (long long)b * p.bsdv + (long long)j * p.lddv + h * HD;
+#pragma unroll
+    for (int c = 0; c < HD; c += 8) *reinterpret_cast<uint4*>(vr + c) = pack8f(dv + c);
+  } else {
+    float v[HD], dk[HD];
+    {
+      const bf16* vr = p.v + (long long)b * p.bsv + (long long)j * p.ldv + h * HD;
+#pragma unroll
+      for (int c = 0; c < HD; c += 8) unpack8f(__ldg(reinterpret_cast<const uint4*>(vr + c)), v + c);
+#pragma unroll
+      for (int c = 0; c < HD; ++c) dk[c] = 0.f;
+    }
+    for (int i = 0; i < L; ++i) {            // same row for every thread of the warp: broadcast reads, no bank conflicts
+      if (i < i0) continue;
+      const float4* qr = reinterpret_cast<const float4*>(sA + i * HD);
+      const float4* gr = reinterpret_cast<const float4*>(sB + i * HD);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < HD / 4; ++c) {
+        const float4 qv = qr[c], gv = gr[c];
+        s0 = fmaf(k[4 * c], qv.x, s0); s1 = fmaf(k[4 * c + 1], qv.y, s1);
+        s2 = fmaf(k[4 * c + 2], qv.z, s2); s3 = fmaf(k[4 * c + 3], qv.w, s3);
+        e0 = fmaf(v[4 * c], gv.x, e0); e1 = fmaf(v[4 * c + 1], gv.y, e1);
+        e2 = fmaf(v[4 * c + 2], gv.z, e2); e3 = fmaf(v[4 * c + 3], gv.w, e3);
+      }
+      const float pij = __expf(((s0 + s1) + (s2 + s3)) - sLse[i]);
+      const float ds = pij * (((e0 + e1) + (e2 + e3)) - sDelta[i]) * p.scale;
+#pragma unroll
+      for (int c = 0; c < HD / 4; ++c) {
+        const float4 qv = qr[c];
+        dk[4 * c] = fmaf(ds, qv.x, dk[4 * c]); dk[4 * c + 1] = fmaf(ds, qv.y, dk[4 * c + 1]);
+        dk[4 * c + 2] = fmaf(ds, qv.z, dk[4 * c + 2]); dk[4 * c + 3] = fmaf(ds, qv.w, dk[4 * c + 3]);
+      }
+    }
+    bf16* kr = p.dk + (long long)b * p.bsdk + (long long)j * p.lddk + h * HD;
+#pragma unroll
+    for (int c = 0; c < HD; c += 8) *reinterpret_cast<uint4*>(kr + c) = pack8f(dk + c);
   }
 }
 
@@ -326,12 +353,13 @@ extern "C" int vn_gelu_bwd(const void* h, int64_t ldh, const void* dy, int64_t l
 extern "C" int vn_seq_attention_fwd(const vn_attn_desc* d, int causal, vn_stream_t s) {
   if (seq_attn_check(d, false)) return -1;
   const SeqAttnParams p = seq_params(d, causal);
-  constexpr int smem = 2 * kMaxL * HD * (int)sizeof(float);
+  constexpr int smem_max = 2 * kMaxL * HD * (int)sizeof(float);
   static bool configured = false;
   if (!configured) {
-    VN_CUDA(cudaFuncSetAttribute(seq_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VN_CUDA(cudaFuncSetAttribute(seq_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     configured = true;
   }
+  const int smem = 2 * d->nq * HD * (int)sizeof(float);           // sized by the sequence: more CTAs per SM
   VN_LAUNCH(seq_attn_fwd_kernel, dim3(d->heads, d->nb), 128, smem, (cudaStream_t)s, p);
   return 0;
 }
@@ -339,12 +367,17 @@ extern "C" int vn_seq_attention_fwd(const vn_attn_desc* d, int causal, vn_stream
 extern "C" int vn_seq_attention_bwd(const vn_attn_desc* d, int causal, vn_stream_t s) {
   if (seq_attn_check(d, true)) return -1;
   const SeqAttnParams p = seq_params(d, causal);
-  constexpr int smem = (4 * kMaxL * HD + 2 * kMaxL) * (int)sizeof(float);
+  constexpr int smem_max = (2 * kMaxL * HD + 2 * kMaxL) * (int)sizeof(float);
   static bool configured = false;
   if (!configured) {
-    VN_CUDA(cudaFuncSetAttribute(seq_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VN_CUDA(cudaFuncSetAttribute(seq_attn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    VN_CUDA(cudaFuncSetAttribute(seq_attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    VN_CUDA(cudaFuncSetAttribute(seq_attn_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     configured = true;
   }
-  VN_LAUNCH(seq_attn_bwd_kernel, dim3(d->heads, d->nb), 128, smem, (cudaStream_t)s, p);
+  const int smem = (2 * d->nq * HD + 2 * d->nq) * (int)sizeof(float);
+  VN_LAUNCH(seq_attn_bwd_kernel<2>, dim3(d->heads, d->nb), 128, smem, (cudaStream_t)s, p);     // longest job first
+  VN_LAUNCH(seq_attn_bwd_kernel<0>, dim3(d->heads, d->nb), 128, smem, (cudaStream_t)s, p);
+  VN_LAUNCH(seq_attn_bwd_kernel<1>, dim3(d->heads, d->nb), 128, smem, (cudaStream_t)s, p);
   return 0;
 }
