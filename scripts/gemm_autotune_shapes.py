@@ -1,0 +1,57 @@
+"""Autotune vn_gemm (BN, split-K cluster, CTA pair) for explicit linear shapes M:N:K[:bias:resid] (e.g. the CLIP text
+encoder's projections) with the same candidates / timing as scripts/gemm_autotune.py; merges the winners into
+gpurun_out/gemm_tuning_extra.json (copy the entries into view_neti_b200/gemm_tuning.json)."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.getcwd())
+import torch
+
+from view_neti_b200 import ops
+from view_neti_b200._abi import VNError
+
+BF = torch.bfloat16
+REP = 10
+out = {}
+ops.TUNING.clear()
+for spec in sys.argv[1:]:
+    f = [int(v) for v in spec.split(":")]
+    M, N, K = f[:3]
+    has_bias, has_r = (f[3] if len(f) > 3 else 1), (f[4] if len(f) > 4 else 0)
+    A = torch.randn(M, K, device="cuda").to(BF)
+    Bm = torch.randn(N, K, device="cuda").to(BF)
+    D = torch.empty(M, N, dtype=BF, device="cuda")
+    R = torch.randn(M, N, device="cuda").to(BF) if has_r else None
+    bias = torch.randn(N, device="cuda") if has_bias else None
+    cands = [(b, s + 512) for b in (64, 128, 192, 256) for s in (1, 2, 4, 8)] + [(160, 2 + 512), (160, 4 + 512)]
+    cands += [(b, 1 + 256) for b in (128, 192, 256)]
+    res = {}
+    for bn, sp in [(0, 0)] + cands:
+        try:
+            ops.gemm(A, Bm, D, bias=bias, R=R, force_bn=bn, force_split=sp)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(REP):
+                    ops.gemm(A, Bm, D, bias=bias, R=R, force_bn=bn, force_split=sp)
+            ts = []
+            for _ in range(4):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); g.replay(); e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e3 / REP)
+            res[(bn, sp)] = min(ts)
+        except (VNError, RuntimeError) as e:
+            if "CUDA" in str(e) and "vn_gemm" not in str(e):
+                raise
+    d = res.pop((0, 0))
+    (bn, sp), best = min(res.items(), key=lambda kv: kv[1])
+    key = ops.tuning_key(0, M, N, K, 0, 0)
+    if best < 0.97 * d:
+        out[key] = [bn, sp, round(best, 2), round(d, 2)]
+    print(f"{key:28s} default {d:7.2f} us  best {best:7.2f} us  bn{bn} s{sp & 15}{' pair' if sp & 256 else ''}  "
+          f"{2.0 * M * N * K / best / 1e6:6.0f} TFLOP/s", flush=True)
+os.makedirs("gpurun_out", exist_ok=True)
+with open("gpurun_out/gemm_tuning_extra.json", "w") as f:
+    json.dump(out, f, indent=0, sort_keys=True)
