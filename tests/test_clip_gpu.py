@@ -99,3 +99,48 @@ def test_clip_encoder_rejects_unsupported_calls():
         enc(inputs_embeds=torch.zeros(1, 77, 128))                                  # CPU tensor: no fallback
     with pytest.raises(VNError):
         enc(inputs_embeds=torch.zeros(1, 77, 128, device="cuda"), attention_mask=torch.ones(1, 77, device="cuda"))
+
+
+@pytest.mark.parametrize("case", ["bypass_unconstrained", "bypass_matched_norm"])
+def test_batched_conditioning_matches_reference_golden(case):
+    """The whole conditioning path (CUDA mappers -> embedding overwrite -> CUDA CLIP encoder -> bypass injection -> final
+    LayerNorm), batched over the 16 UNet layers, against the outputs AND mapper-parameter gradients of the reference's own
+    modules run layer by layer (tests/golden/make_golden_conditioning.py)."""
+    import os
+    from view_neti_b200.models.clip_encoder import CLIPEncoder, ClipEncoderConfig
+    from view_neti_b200.models.neti_conditioning import NeTIConditioning
+    from view_neti_b200.models.neti_mapper import NeTIMapper
+    from view_neti_b200.utils.types import PESigmas
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "neti_conditioning.pt"), weights_only=False)
+    cfg, c = G["config"], G["cases"][case]
+    enc = CLIPEncoder(G["encoder_state"], ClipEncoderConfig(hidden_size=cfg["hidden"], num_attention_heads=cfg["heads"],
+                                                            num_hidden_layers=cfg["layers"], intermediate_size=cfg["inter"]), "cuda")
+    sig = PESigmas(sigma_t=0.03, sigma_l=2.0, sigma_theta=0.5, sigma_phi=0.5, sigma_r=0.5, sigma_dtu12=0.5)
+    kw = dict(output_dim=cfg["hidden"], arch_mlp_hidden_dims=64, arch_view_net=15, arch_view_disable_tl=False,
+              use_nested_dropout=False, pe_sigmas=sig, output_bypass=True, bypass_unconstrained=c["bypass_unconstrained"],
+              output_bypass_alpha=c["output_bypass_alpha"])
+    mo = NeTIMapper(embedding_type="object", norm_scale=torch.tensor(0.3714), placeholder_object_token="<statue>", **kw)
+    mv = NeTIMapper(embedding_type="view", norm_scale=torch.tensor(0.4102), placeholder_view_tokens=list(G["view_tokens"]),
+                    placeholder_view_token_ids=list(G["view_ids"]), **kw)
+    for m, key in ((mo, "object"), (mv, "view")):
+        assert torch.equal(m.encoder_w, c[key + "_w"])
+        m.load_state_dict({k: v for k, v in c[key + "_state"].items() if k != "encoder.w"}, strict=True)
+        m.cuda()
+    cond = NeTIConditioning(G["token_embedding"], G["position_embedding"], G["final_ln"], enc, {G["obj_id"]: mo}, mv)
+    assert len(list(cond.parameters())) == 20          # both mappers are visible to the optimizer / the all-reduce
+    hs = cond(input_ids=c["input_ids"], timesteps=c["timesteps"], input_ids_placeholder_object=c["ph_obj"],
+              input_ids_placeholder_view=c["ph_view"])
+    assert hs["this_idx"] == 0
+    for j, layer in enumerate(c["layers_kept"]):
+        assert rel(hs[f"CONTEXT_TENSOR_{layer}"], c["hs"][j]) < 1.5e-2, layer
+        assert rel(hs[f"CONTEXT_TENSOR_BYPASS_{layer}"], c["hs_bypass"][j]) < 1.5e-2, layer
+    if len(c["layers_kept"]) == 16:
+        gg = torch.Generator().manual_seed(c["cotangent_seed"])
+        shape = (16, *c["hs"].shape[1:])
+        gk, gv = torch.randn(shape, generator=gg).cuda(), torch.randn(shape, generator=gg).cuda()
+        loss = sum((hs[f"CONTEXT_TENSOR_{i}"] * gk[i]).sum() + (hs[f"CONTEXT_TENSOR_BYPASS_{i}"] * gv[i]).sum() for i in range(16))
+        loss.backward()
+        flat = torch.cat([p.grad.reshape(-1) for mname, m in (("object", mo), ("view", mv)) for n, p in m.named_parameters()])
+        gold = torch.cat([c["grads"][f"{mname}.{n}"].reshape(-1) for mname, m in (("object", mo), ("view", mv))
+                          for n, p in m.named_parameters()])
+        assert rel(flat, gold) < 3e-2          # relative L2 of the flat mapper gradient (north_star: < 1e-2 at fp16 tolerance)

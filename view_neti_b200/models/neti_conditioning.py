@@ -1,0 +1,122 @@
+"""The conditioning path of one train step, batched: reference training/coach.py:276-311 runs the NeTI text encoder once
+per UNet layer (16 passes); here the 16 passes are ONE [16*B, 77, C] pass.
+
+    mapper outputs for all (timestep_b, layer) pairs         one fused launch per mapper   (models/neti_mapper.py)
+    -> overwrite the placeholder rows of the token embeddings   net_clip_text_embedding.py:61-131
+    -> + position embeddings -> CLIP encoder                    models/clip_encoder.py (vn_gemm / LayerNorm / GELU / attention)
+    -> bypass injection at the placeholder rows                 neti_clip_text_encoder.py:118-178
+    -> final LayerNorm of the plain and the bypass states       :180-182
+    -> {"this_idx": 0, "CONTEXT_TENSOR_i", "CONTEXT_TENSOR_BYPASS_i"}   coach.py:287-305
+
+The embedding scatter, the bypass arithmetic on 16*B rows and the final LayerNorm are a handful of small torch ops
+(autograd carries the gradient between the CUDA encoder and the CUDA mappers); everything with FLOPs in it is the
+library.  `NeTIConditioning` plugs into `Coach(cfg, unet, conditioning=...)` and is called exactly like
+`Coach.get_text_conditioning`.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from .._abi import VNError
+from ..constants import UNET_LAYERS
+from .clip_encoder import CLIPEncoder
+from .neti_mapper import NeTIMapper
+
+
+class NeTIConditioning(torch.nn.Module):
+
+    def __init__(self, token_embedding: torch.Tensor, position_embedding: torch.Tensor,
+                 final_layer_norm: Tuple[torch.Tensor, torch.Tensor], encoder: CLIPEncoder,
+                 mapper_object_lookup: Optional[Dict[int, NeTIMapper]], mapper_view: Optional[NeTIMapper],
+                 n_layers: int = len(UNET_LAYERS), layer_norm_eps: float = 1e-5, weight_dtype: torch.dtype = torch.float32):
+        super().__init__()
+        dev = encoder.engine.dev
+        # frozen text-model pieces (coach.py:649-652 freezes the text encoder except the mappers)
+        self.register_buffer("token_embedding", token_embedding.to(dev, torch.float32), persistent=False)
+        self.register_buffer("position_embedding", position_embedding.to(dev, torch.float32), persistent=False)
+        self.register_buffer("final_ln_weight", final_layer_norm[0].to(dev, torch.float32), persistent=False)
+        self.register_buffer("final_ln_bias", final_layer_norm[1].to(dev, torch.float32), persistent=False)
+        self.encoder = encoder
+        self.n_layers = n_layers
+        self.eps = layer_norm_eps
+        self.weight_dtype = weight_dtype
+        # like net_clip_text_embedding.py:25-32 the object mappers live in a dict keyed by placeholder token id; registering
+        # them in a ModuleDict makes them visible to .parameters() (the reference's plain dict hides them from DDP)
+        self.mapper_object_lookup = torch.nn.ModuleDict({str(k): v for k, v in (mapper_object_lookup or {}).items()})
+        self.mapper_view = mapper_view
+
+    @staticmethod
+    def _positions(input_ids: torch.Tensor, placeholder: torch.Tensor) -> torch.Tensor:
+        locs = input_ids == placeholder.unsqueeze(1)
+        if not bool((locs.sum(1) == 1).all()):
+            raise VNError("every prompt must hold its placeholder token exactly once (net_clip_text_embedding.py:99,130)")
+        return locs.float().argmax(1)
+
+    @staticmethod
+    def _inject_bypass(state, rows, pos, bypass, unconstrained: bool, alpha: float):
+        existing = state[rows, pos]
+        if not unconstrained:
+            b = bypass / bypass.norm(dim=1, keepdim=True) * existing.norm(dim=1, keepdim=True)
+            new = existing + alpha * b
+        else:
+            normalizing = state.norm(dim=-1).mean(-1).detach()
+            new = bypass / bypass.norm(dim=1, keepdim=True) * normalizing.unsqueeze(1)
+        out = state.clone()
+        out[rows, pos] = new.to(state.dtype)
+        return out
+
+    def forward(self, input_ids: torch.Tensor = None, timesteps: torch.Tensor = None,
+                input_ids_placeholder_object=None, input_ids_placeholder_view=None, device=None,
+                original_ti: bool = False, **_) -> Dict:
+        dev = self.token_embedding.device
+        input_ids = torch.as_tensor(input_ids, device=dev)
+        timesteps = torch.as_tensor(timesteps, device=dev)
+        B, L = input_ids.shape
+        nl = 1 if original_ti else self.n_layers
+        N = nl * B
+        C = self.token_embedding.shape[1]
+        t_rep = timesteps.float().repeat(nl)                                   # layer-major: row = layer * B + b
+        l_rep = torch.arange(nl, device=dev).repeat_interleave(B).float()
+        rows = torch.arange(N, device=dev)
+        emb = self.token_embedding[input_ids].repeat(nl, 1, 1)                 # [N, L, C] (a fresh tensor: written below)
+        obj = view = None
+        if len(self.mapper_object_lookup) > 0 and input_ids_placeholder_object is not None:
+            ph_o = torch.as_tensor(input_ids_placeholder_object, device=dev)
+            if not bool((ph_o == ph_o[0]).all()):
+                raise VNError("one object per batch (net_clip_text_embedding.py:67-68)")
+            mapper = self.mapper_object_lookup[str(int(ph_o[0]))]
+            out = mapper(timestep=t_rep, unet_layer=l_rep, input_ids_placeholder_view=None, truncation_idx=None)
+            pos_o = self._positions(input_ids, ph_o).repeat(nl)
+            emb[rows, pos_o] = out.word_embedding.to(emb.dtype)
+            obj = (out, pos_o)
+        if self.mapper_view is not None and input_ids_placeholder_view is not None:
+            ph_v = torch.as_tensor(input_ids_placeholder_view, device=dev)
+            if not bool((ph_v == -1).all()):                                   # net_clip_text_embedding.py:105-106
+                out = self.mapper_view(timestep=t_rep, unet_layer=l_rep, input_ids_placeholder_view=ph_v.repeat(nl),
+                                       truncation_idx=None)
+                pos_v = self._positions(input_ids, ph_v).repeat(nl)
+                emb[rows, pos_v] = out.word_embedding.to(emb.dtype)
+                view = (out, pos_v)
+        x = emb + self.position_embedding[:L]
+        last = self.encoder(inputs_embeds=x)[0]
+        with_bypass = None
+        for item in (obj, view):                                               # object first, then view (:127-178)
+            if item is not None and item[0].bypass_output is not None:
+                out, pos = item
+                base = last if with_bypass is None else with_bypass
+                with_bypass = self._inject_bypass(base, rows, pos, out.bypass_output.to(last.dtype), out.bypass_unconstrained,
+                                                  out.output_bypass_alpha)
+        ln = lambda s: F.layer_norm(s, (C,), self.final_ln_weight, self.final_ln_bias, self.eps).to(self.weight_dtype)   # noqa: E731
+        last_n = ln(last)
+        if original_ti:
+            return last_n[:B]                                                  # coach.py:307-309
+        hs: Dict = {"this_idx": 0}
+        bypass_n = ln(with_bypass) if with_bypass is not None else None
+        for i in range(nl):
+            hs[f"CONTEXT_TENSOR_{i}"] = last_n[i * B:(i + 1) * B]
+            if bypass_n is not None:
+                hs[f"CONTEXT_TENSOR_BYPASS_{i}"] = bypass_n[i * B:(i + 1) * B]
+        return hs
