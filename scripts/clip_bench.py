@@ -7,13 +7,12 @@ import sys
 sys.path.insert(0, os.getcwd())
 import torch
 
-from oracle.clip_encoder import init_state_dict
-from view_neti_b200.models.clip_encoder import SD21_TEXT, ClipEncoderEngine
+from view_neti_b200.models.clip_encoder import SD21_TEXT, ClipEncoderEngine, init_state_dict
 
 cfg = SD21_TEXT
 B = int(os.environ.get("B", 1))
 steps = int(os.environ.get("STEPS", 20))
-eng = ClipEncoderEngine(init_state_dict(cfg.hidden_size, cfg.num_attention_heads, cfg.num_hidden_layers, cfg.intermediate_size, 0), cfg)
+eng = ClipEncoderEngine(init_state_dict(cfg, 0), cfg)
 plan = eng.plan(16 * B, 77)
 plan.x_in.normal_()
 plan.dy_in.normal_()

@@ -43,6 +43,32 @@ class ClipEncoderConfig:
 SD21_TEXT = ClipEncoderConfig()
 
 
+def init_state_dict(cfg: ClipEncoderConfig = SD21_TEXT, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Seeded random weights under transformers' CLIPEncoder key names at the configured shapes (no checkpoints exist
+    offline; a real text encoder's `text_model.encoder.state_dict()` loads the same way).  Residual branches are damped
+    by (2*layers)**-0.5 so the stream stays O(1) through all layers."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    C, I, nl = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers
+    damp = (2 * nl) ** -0.5
+    sd: Dict[str, torch.Tensor] = {}
+    for i in range(nl):
+        p = f"layers.{i}."
+        for n in ("q", "k", "v"):
+            sd[p + f"self_attn.{n}_proj.weight"] = torch.randn(C, C, generator=g) / math.sqrt(C)
+            sd[p + f"self_attn.{n}_proj.bias"] = 0.1 * torch.randn(C, generator=g)
+        sd[p + "self_attn.out_proj.weight"] = torch.randn(C, C, generator=g) * damp / math.sqrt(C)
+        sd[p + "self_attn.out_proj.bias"] = 0.05 * torch.randn(C, generator=g)
+        sd[p + "mlp.fc1.weight"] = torch.randn(I, C, generator=g) / math.sqrt(C)
+        sd[p + "mlp.fc1.bias"] = 0.1 * torch.randn(I, generator=g)
+        sd[p + "mlp.fc2.weight"] = torch.randn(C, I, generator=g) * damp / math.sqrt(I)
+        sd[p + "mlp.fc2.bias"] = 0.05 * torch.randn(C, generator=g)
+        for n in ("layer_norm1", "layer_norm2"):
+            sd[p + n + ".weight"] = 1 + 0.1 * torch.randn(C, generator=g)
+            sd[p + n + ".bias"] = 0.05 * torch.randn(C, generator=g)
+    return sd
+
+
 class _Layer:
     pass
 
