@@ -182,3 +182,47 @@ def test_complete_train_steps_through_coach():
     moved = [float((p.detach() - b).abs().max()) for p, b in zip(cond.parameters(), before)]
     assert len(moved) == 20 and min(moved) > 0, moved          # every tensor of both mappers received gradient
     assert l1 < l0, (l0, l1)
+
+
+def test_prompt_manager_batches_timesteps_and_matches_reference_golden():
+    """PromptManager.embed_prompt (reference prompt_manager.py:44-101): all timesteps of a prompt in batched inference
+    passes.  The entry of timestep 17 for prompt 0 / 731 for prompt 1 must equal the reference's own outputs for those
+    (prompt, timestep) pairs in tests/golden/neti_conditioning.pt; the other entries must equal the training-mode path."""
+    import os
+    from view_neti_b200.models.clip_encoder import CLIPEncoder, ClipEncoderConfig
+    from view_neti_b200.models.neti_conditioning import NeTIConditioning
+    from view_neti_b200.models.neti_mapper import NeTIMapper
+    from view_neti_b200.prompt_manager import PromptManager
+    from view_neti_b200.utils.types import PESigmas
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "neti_conditioning.pt"), weights_only=False)
+    cfg, c = G["config"], G["cases"]["bypass_unconstrained"]
+    enc = CLIPEncoder(G["encoder_state"], ClipEncoderConfig(hidden_size=cfg["hidden"], num_attention_heads=cfg["heads"],
+                                                            num_hidden_layers=cfg["layers"], intermediate_size=cfg["inter"]), "cuda")
+    sig = PESigmas(sigma_t=0.03, sigma_l=2.0, sigma_theta=0.5, sigma_phi=0.5, sigma_r=0.5, sigma_dtu12=0.5)
+    kw = dict(output_dim=cfg["hidden"], arch_mlp_hidden_dims=64, arch_view_net=15, arch_view_disable_tl=False,
+              use_nested_dropout=False, pe_sigmas=sig, output_bypass=True, bypass_unconstrained=True, output_bypass_alpha=0.2)
+    mo = NeTIMapper(embedding_type="object", norm_scale=torch.tensor(0.3714), placeholder_object_token="<statue>", **kw)
+    mv = NeTIMapper(embedding_type="view", norm_scale=torch.tensor(0.4102), placeholder_view_tokens=list(G["view_tokens"]),
+                    placeholder_view_token_ids=list(G["view_ids"]), **kw)
+    for m, key in ((mo, "object"), (mv, "view")):
+        m.load_state_dict({k: v for k, v in c[key + "_state"].items() if k != "encoder.w"}, strict=True)
+        m.cuda()
+    cond = NeTIConditioning(G["token_embedding"], G["position_embedding"], G["final_ln"], enc, {G["obj_id"]: mo}, mv)
+    timesteps = [999, 17, 500, 731, 20]
+    pm = PromptManager(tokenizer=None, text_encoder=cond, timesteps=timesteps, placeholder_view_token_ids=G["view_ids"],
+                       placeholder_object_token_ids=[G["obj_id"]], chunk=2)
+    for prompt, t_gold in ((0, 17), (1, 731)):
+        embeds = pm.embed_prompt(c["input_ids"][prompt:prompt + 1], num_images_per_prompt=3)
+        assert len(embeds) == len(timesteps) and embeds[0]["this_idx"] == 0
+        e = embeds[timesteps.index(t_gold)]
+        assert e["CONTEXT_TENSOR_0"].shape == (3, 77, cfg["hidden"])
+        for layer in (0, 7, 15):
+            assert rel(e[f"CONTEXT_TENSOR_{layer}"][0], c["hs"][layer][prompt]) < 1.5e-2
+            assert rel(e[f"CONTEXT_TENSOR_BYPASS_{layer}"][2], c["hs_bypass"][layer][prompt]) < 1.5e-2
+        # batched inference pass == training-mode path, timestep by timestep
+        t_other = 500
+        ref = cond(input_ids=c["input_ids"][prompt:prompt + 1].cuda(), timesteps=torch.tensor([t_other]).cuda(),
+                   input_ids_placeholder_object=c["ph_obj"][prompt:prompt + 1], input_ids_placeholder_view=c["ph_view"][prompt:prompt + 1])
+        got = embeds[timesteps.index(t_other)]
+        assert rel(got["CONTEXT_TENSOR_9"][1], ref["CONTEXT_TENSOR_9"][0]) < 1e-5
+        assert rel(got["CONTEXT_TENSOR_BYPASS_9"][1], ref["CONTEXT_TENSOR_BYPASS_9"][0]) < 1e-5

@@ -107,19 +107,19 @@ class ClipEncoderEngine:
             self.layers.append(l)
         self._plans: Dict[Tuple[int, int], "_ClipPlan"] = {}
 
-    def plan(self, nseq: int, L: int) -> "_ClipPlan":
-        key = (nseq, L)
+    def plan(self, nseq: int, L: int, train: bool = True) -> "_ClipPlan":
+        key = (nseq, L, train)
         if key not in self._plans:
-            self._plans[key] = _ClipPlan(self, nseq, L)
+            self._plans[key] = _ClipPlan(self, nseq, L, train)
         return self._plans[key]
 
 
 class _ClipPlan:
     """Static buffers + launch order for [nseq, L, hidden]; forward / backward are CUDA-graph capturable."""
 
-    def __init__(self, eng: ClipEncoderEngine, nseq: int, L: int):
+    def __init__(self, eng: ClipEncoderEngine, nseq: int, L: int, train: bool = True):
         cfg = eng.cfg
-        self.eng, self.nseq, self.L = eng, nseq, L
+        self.eng, self.nseq, self.L, self.train = eng, nseq, L, train
         dev, C, I, nl = eng.dev, cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers
         z = lambda *s, dt=BF: torch.zeros(*s, dtype=dt, device=dev)      # noqa: E731
         rows = nseq * L
@@ -129,22 +129,29 @@ class _ClipPlan:
         self.y_out = z(nseq, L, C, dt=F32)
         self.dy_in = z(nseq, L, C, dt=F32)
         self.dx_out = z(nseq, L, C, dt=F32)
-        # kept per layer for the backward: both LayerNorm inputs + statistics, q/k/v, attention output, lse, fc1 output
-        self.x = [z(nseq, L, C) for _ in range(nl + 1)]
-        self.xm = [z(nseq, L, C) for _ in range(nl)]
-        self.st1 = [z(rows, 2, dt=F32) for _ in range(nl)]
-        self.st2 = [z(rows, 2, dt=F32) for _ in range(nl)]
-        self.qkv = [z(nseq, L, 3 * C) for _ in range(nl)]
-        self.o = [z(nseq, L, C) for _ in range(nl)]
-        self.lse = [z(nseq, cfg.num_attention_heads, L, dt=F32) for _ in range(nl)]
-        self.h1 = [z(nseq, L, I) for _ in range(nl)]
+        # train: kept per layer for the backward (both LayerNorm inputs + statistics, q/k/v, attention output, lse, fc1
+        # output).  inference (no gradient wanted): every layer reuses ONE set of buffers, the stream ping-pongs between two.
+        per = (lambda mk, n: [mk() for _ in range(n)]) if train else (lambda mk, n: [mk()] * n)      # noqa: E731
+        if train:
+            self.x = [z(nseq, L, C) for _ in range(nl + 1)]
+        else:
+            pp = [z(nseq, L, C), z(nseq, L, C)]
+            self.x = [pp[i % 2] for i in range(nl + 1)]
+        self.xm = per(lambda: z(nseq, L, C), nl)
+        self.st1 = per(lambda: z(rows, 2, dt=F32), nl)
+        self.st2 = per(lambda: z(rows, 2, dt=F32), nl)
+        self.qkv = per(lambda: z(nseq, L, 3 * C), nl)
+        self.o = per(lambda: z(nseq, L, C), nl)
+        self.lse = per(lambda: z(nseq, cfg.num_attention_heads, L, dt=F32), nl)
+        self.h1 = per(lambda: z(nseq, L, I), nl)
         # scratch shared by all layers
         self.n = z(nseq, L, C)
         self.g = z(nseq, L, I)
-        self.dq = z(nseq, L, 3 * C)
-        self.da = z(nseq, L, C)
-        self.db = z(nseq, L, C)
-        self.dc = z(nseq, L, C)
+        if train:
+            self.dq = z(nseq, L, 3 * C)
+            self.da = z(nseq, L, C)
+            self.db = z(nseq, L, C)
+            self.dc = z(nseq, L, C)
         self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self._saved = False
 
@@ -171,6 +178,7 @@ class _ClipPlan:
 
     def backward(self) -> torch.Tensor:
         """dx_out = d<y_out, dy_in> / d x_in for the activations of the last forward (data gradients only)."""
+        assert self.train, "this plan was built for inference (no activations kept)"
         assert self._saved, "backward() needs a forward() on this plan first"
         eng, cfg = self.eng, self.eng.cfg
         C, heads, rows = cfg.hidden_size, cfg.num_attention_heads, self.rows
@@ -209,7 +217,9 @@ class _ClipPlan:
             self._saved = True
             return self.y_out
         out = self.forward()                       # first call: eager (sets kernel attributes, allocates nothing new)
-        if use_graphs:
+        if use_graphs and not self.train:
+            self._capture("fwd")
+        elif use_graphs:
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
@@ -278,6 +288,10 @@ class CLIPEncoder(torch.nn.Module):
             raise ops._abi.VNError("CLIPEncoder needs CUDA tensors (no CPU fallback)")
         nseq, L, C = inputs_embeds.shape
         assert C == self.config.hidden_size
+        if not (torch.is_grad_enabled() and inputs_embeds.requires_grad):
+            plan = self.engine.plan(nseq, L, train=False)          # inference: one set of layer buffers, forward graph only
+            plan.x_in.copy_(inputs_embeds)
+            return _EncoderOutput(plan.run_forward(self.use_graphs).to(inputs_embeds.dtype, copy=True))
         plan = self.engine.plan(nseq, L)
         y = _ClipEncoderFn.apply(inputs_embeds, plan, self.use_graphs)
         return _EncoderOutput(y)
