@@ -644,16 +644,21 @@ class _Plan:
         return self.graphs[what]
 
     def run_forward(self) -> torch.Tensor:
-        """Used by the drop-in UNet: eager on the first call, CUDA-graph replay afterwards."""
-        if "fwd" in self.graphs:
+        """Used by the drop-in UNet: eager on the first call, CUDA-graph replay afterwards.  Forward-only users (the
+        denoise loop of sd_pipeline_call) get the forward graph after one eager pass; the backward graph is captured as
+        soon as a backward has run once (both captures happen here, on the caller's thread: the autograd thread only
+        ever replays)."""
+        if self.eng.use_graphs and "fwd" in self.graphs:
+            if "bwd" not in self.graphs and "bwd.dy" in self.bufs:
+                self.capture("bwd")
             self.graphs["fwd"].replay()
             self._saved = True
             return self.eps
         out = self.forward()
-        if self.eng.use_graphs and "bwd.dy" in self.bufs:
-            # both graphs are captured here (caller's thread), the autograd thread only ever replays
+        if self.eng.use_graphs:
             self.capture("fwd")
-            self.capture("bwd")
+            if "bwd.dy" in self.bufs:
+                self.capture("bwd")
         return out
 
     def run_backward(self) -> torch.Tensor:
