@@ -226,3 +226,39 @@ def test_prompt_manager_batches_timesteps_and_matches_reference_golden():
         got = embeds[timesteps.index(t_other)]
         assert rel(got["CONTEXT_TENSOR_9"][1], ref["CONTEXT_TENSOR_9"][0]) < 1e-5
         assert rel(got["CONTEXT_TENSOR_BYPASS_9"][1], ref["CONTEXT_TENSOR_BYPASS_9"][0]) < 1e-5
+
+
+def test_object_only_conditioning_is_mode0_textual_inversion():
+    """BASELINE config 0 (mode 0: object-only TI, no view mapper): prompts without a view token
+    (input_ids_placeholder_view == -1, net_clip_text_embedding.py:105-106) still yield the 16 + 16 context tensors, only the
+    object mapper receives gradient, and `original_ti` returns the first layer's plain tensor (coach.py:307-309)."""
+    from view_neti_b200.models.clip_encoder import CLIPEncoder, ClipEncoderConfig, init_state_dict
+    from view_neti_b200.models.neti_conditioning import NeTIConditioning
+    from view_neti_b200.models.neti_mapper import NeTIMapper
+    from view_neti_b200.utils.types import PESigmas
+    cfg = ClipEncoderConfig(hidden_size=128, num_attention_heads=2, num_hidden_layers=2, intermediate_size=256)
+    enc = CLIPEncoder(init_state_dict(cfg, 1), cfg, "cuda")
+    g = torch.Generator().manual_seed(2)
+    mo = NeTIMapper(embedding_type="object", output_dim=128, arch_mlp_hidden_dims=64, arch_view_net=15, arch_view_disable_tl=False,
+                    use_nested_dropout=False, pe_sigmas=PESigmas(sigma_t=0.03, sigma_l=2.0), output_bypass=True,
+                    bypass_unconstrained=True, output_bypass_alpha=0.2, norm_scale=torch.tensor(0.37),
+                    placeholder_object_token="<teapot>").cuda()
+    cond = NeTIConditioning(torch.randn(200, 128, generator=g) * 0.1, torch.randn(77, 128, generator=g) * 0.05,
+                            (torch.ones(128), torch.zeros(128)), enc, {150: mo}, None)
+    ids = torch.randint(1, 100, (2, 77), generator=g)
+    ids[:, 4] = 150
+    kw = dict(input_ids=ids.cuda(), timesteps=torch.tensor([10, 900]).cuda(), input_ids_placeholder_object=torch.tensor([150, 150]),
+              input_ids_placeholder_view=torch.tensor([-1, -1]))
+    hs = cond(**kw)
+    assert sorted(k for k in hs if k != "this_idx") == sorted([f"CONTEXT_TENSOR_{i}" for i in range(16)] +
+                                                              [f"CONTEXT_TENSOR_BYPASS_{i}" for i in range(16)])
+    assert hs["CONTEXT_TENSOR_3"].shape == (2, 77, 128)
+    sum((v ** 2).sum() for k, v in hs.items() if k != "this_idx").backward()
+    assert all(p.grad is not None and float(p.grad.abs().max()) > 0 for p in mo.parameters())
+    # rows before the placeholder do not depend on the mapper (causal mask): identical across the 16 layers
+    a, b = hs["CONTEXT_TENSOR_0"].detach(), hs["CONTEXT_TENSOR_11"].detach()
+    assert float((a[:, :4] - b[:, :4]).abs().max()) == 0.0
+    assert float((a[:, 4:] - b[:, 4:]).abs().max()) > 0.0
+    first = cond(original_ti=True, **kw)
+    assert torch.is_tensor(first) and first.shape == (2, 77, 128)
+    assert rel(first, hs["CONTEXT_TENSOR_0"]) < 1e-6
