@@ -155,6 +155,7 @@ typedef struct vn_attn_desc {
   void* dk; int64_t lddk, bsdk;
   void* dv; int64_t lddv, bsdv;
   double* dkv_acc;                        /* NULL or zeroed scratch, see above */
+  int32_t causal;                         /* 1: key j is visible to query i only if j <= i (CLIP text encoder) */
 } vn_attn_desc;
 int vn_attention_fwd(const vn_attn_desc* d, vn_stream_t s);
 int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s);

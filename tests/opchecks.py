@@ -174,19 +174,21 @@ def check_geglu(rows, Fd):
     return [(f"geglu {rows}x{Fd} fwd", rel(y, yr), 6e-3), (f"geglu {rows}x{Fd} bwd", rel(dh, hr.grad), 8e-3)]
 
 
-def attn_ref(q, k, v, heads, scale):
+def attn_ref(q, k, v, heads, scale, causal=False):
     nb, nq, Cc = q.shape
     nk = k.shape[1]
     qh = q.float().reshape(nb, nq, heads, 64).transpose(1, 2)
     kh = k.float().reshape(nb, nk, heads, 64).transpose(1, 2)
     vh = v.float().reshape(nb, nk, heads, 64).transpose(1, 2)
     s = (qh @ kh.transpose(-1, -2)) * scale
+    if causal:
+        s = s + torch.full((nq, nk), float("-inf"), device=s.device).triu(1)
     p = s.softmax(-1)
     o = (p @ vh).transpose(1, 2).reshape(nb, nq, Cc)
     return o, torch.logsumexp(s, -1)
 
 
-def check_attention(nb, heads, nq, nk, bwd=True, use_acc=False, strided=False):
+def check_attention(nb, heads, nq, nk, bwd=True, use_acc=False, strided=False, causal=False):
     Cc = heads * 64
     if strided:   # q/k/v as slices of one fused [nb, n, 3C] buffer (self-attention layout)
         assert nq == nk
@@ -198,10 +200,10 @@ def check_attention(nb, heads, nq, nk, bwd=True, use_acc=False, strided=False):
         v = rnd(nb, nk, Cc, seed=27).to(BF)
     o = torch.empty(nb, nq, Cc, dtype=BF, device=DEV)
     lse = torch.empty(nb, heads, nq, device=DEV)
-    ops.attention_fwd(q, k, v, o, lse, heads)
+    ops.attention_fwd(q, k, v, o, lse, heads, causal=causal)
     qr, kr, vr = (t.float().detach().clone().requires_grad_(True) for t in (q, k, v))
-    oref, lseref = attn_ref(qr, kr, vr, heads, 0.125)
-    lab = f"attn nb{nb} h{heads} nq{nq} nk{nk} acc{int(use_acc)} st{int(strided)}"
+    oref, lseref = attn_ref(qr, kr, vr, heads, 0.125, causal=causal)
+    lab = f"attn nb{nb} h{heads} nq{nq} nk{nk} acc{int(use_acc)} st{int(strided)} causal{int(causal)}"
     out = [(lab + " o", rel(o, oref), 8e-3), (lab + " lse", rel(lse, lseref), 1e-4)]
     if bwd:
         d_o = rnd(nb, nq, Cc, seed=28).to(BF)
@@ -211,7 +213,7 @@ def check_attention(nb, heads, nq, nk, bwd=True, use_acc=False, strided=False):
         dk = torch.empty(nb, nk, Cc, dtype=BF, device=DEV)
         dv = torch.empty(nb, nk, Cc, dtype=BF, device=DEV)
         acc = ws().dkv if use_acc else None
-        ops.attention_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, heads, dkv_acc=acc)
+        ops.attention_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, heads, dkv_acc=acc, causal=causal)
         out += [(lab + " dq", rel(dq, qr.grad), 1.2e-2), (lab + " dk", rel(dk, kr.grad), 1.2e-2),
                 (lab + " dv", rel(dv, vr.grad), 1.2e-2)]
         if use_acc:
@@ -390,6 +392,10 @@ def all_checks():
     for (nb, heads, n) in [(1, 5, 4096), (2, 10, 1024), (1, 20, 256), (1, 20, 64)]:
         L.append((check_attention, dict(nb=nb, heads=heads, nq=n, nk=77, use_acc=True)))
     L.append((check_attention, dict(nb=1, heads=2, nq=200, nk=77, use_acc=False)))
+    # causal mask (CLIP text encoder: 77 tokens; and multi-tile shapes crossing the diagonal)
+    L.append((check_attention, dict(nb=16, heads=16, nq=77, nk=77, strided=True, causal=True)))
+    L.append((check_attention, dict(nb=2, heads=2, nq=300, nk=300, causal=True)))
+    L.append((check_attention, dict(nb=1, heads=1, nq=128, nk=128, causal=True)))
     L.append((check_resample, dict(nb=1, H=16, W=16, Cc=128)))
     L.append((check_resample, dict(nb=2, H=12, W=16, Cc=64)))
     L.append((check_edge_convs, dict(nb=2, H=32, W=32, Cw=320)))

@@ -54,6 +54,7 @@ class AttnDesc(C.Structure):
         ("dk", C.c_void_p), ("lddk", C.c_int64), ("bsdk", C.c_int64),
         ("dv", C.c_void_p), ("lddv", C.c_int64), ("bsdv", C.c_int64),
         ("dkv_acc", C.c_void_p),
+        ("causal", C.c_int32),
     ]
 
 

@@ -34,6 +34,7 @@ struct BwdParams {
   double* dkv_acc;
   int qsplits, qtiles_per_split;
   int n_dkv, ktiles, qtiles;        // fused-grid decomposition
+  int causal;                       // key j visible to query i only if j <= i
 };
 
 __device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr) {
@@ -253,6 +254,12 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
             for (int c = 0; c < 8; ++c)
               if (g * 8 + c >= qvalid) { pe[c] = 0.f; de[c] = 0.f; }
           }
+          if (p.causal) {                              // queries before this key row do not see it
+            const int qfirst = k0 + r - (q0 + cbase + g * 8);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (c < qfirst) { pe[c] = 0.f; de[c] = 0.f; }
+          }
           store_row8(prow, hf * 4 + g, r, pe);
           store_row8(drow, hf * 4 + g, r, de);
         }
@@ -429,6 +436,12 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
             for (int c = 0; c < 8; ++c)
               if (g * 8 + c >= kvalid) de[c] = 0.f;
           }
+          if (p.causal) {                              // keys after this query row are masked
+            const int klast = row - (j * T + cbase + g * 8);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (c > klast) de[c] = 0.f;
+          }
           store_row8(drow, hf * 4 + g, r, de);
         }
         tc_fence_before();
@@ -579,6 +592,7 @@ extern "C" int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s) {
   p.dk = (bf16*)d->dk; p.lddk = d->lddk; p.bsdk = d->bsdk;
   p.dv = (bf16*)d->dv; p.lddv = d->lddv; p.bsdv = d->bsdv;
   p.dkv_acc = d->dkv_acc;
+  p.causal = d->causal;
   constexpr int SMEM = DKV_SMEM > DQ_SMEM ? DKV_SMEM : DQ_SMEM;
   static bool configured = false;
   if (!configured) {

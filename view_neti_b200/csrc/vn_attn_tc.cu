@@ -35,7 +35,7 @@ constexpr int SMEM_BYTES = TILE_BYTES /*Q*/ + KV_STAGES * 2 * TILE_BYTES /*K,V*/
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct FwdParams {
-  int nq, nk, heads;
+  int nq, nk, heads, causal;
   float scale;
   bf16* o; long long ldo, bso;
   float* lse;
@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
         tmem_ld32(tS, c0); tmem_ld32(tS + 32, c1);
         tmem_ld_wait();
       }
-      const int kvalid = p.nk - j * BKV - hf * 64;     // keys of this half-tile that exist (may be <= 0 on the last tile)
+      int kvalid = p.nk - j * BKV - hf * 64;           // keys of this half-tile that exist (may be <= 0 on the last tile)
+      if (p.causal) kvalid = min(kvalid, q0 + r + 1 - j * BKV - hf * 64);   // ... and that query row q0 + r may see
       if (kvalid < 64) {
 #pragma unroll
         for (int i = 0; i < 64; ++i)
@@ -302,7 +303,7 @@ extern "C" int vn_attention_fwd(const vn_attn_desc* d, vn_stream_t s) {
   if (make_qkv_map(&tk, d->k, width, d->nk, d->nb, d->ldk, d->bsk)) return -1;
   if (make_qkv_map(&tv, d->v, width, d->nk, d->nb, d->ldv, d->bsv)) return -1;
   FwdParams p{};
-  p.nq = d->nq; p.nk = d->nk; p.heads = d->heads; p.scale = d->scale;
+  p.nq = d->nq; p.nk = d->nk; p.heads = d->heads; p.scale = d->scale; p.causal = d->causal;
   p.o = (bf16*)d->o; p.ldo = d->ldo; p.bso = d->bso;
   p.lse = d->lse;
   static bool configured = false;

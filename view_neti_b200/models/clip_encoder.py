@@ -106,6 +106,10 @@ class ClipEncoderEngine:
             l.fc2_bias = f32(p + "mlp.fc2.bias")
             self.layers.append(l)
         self._plans: Dict[Tuple[int, int], "_ClipPlan"] = {}
+        # attention core: "tc" = the tcgen05 flash-attention kernels with their causal mask (one 128 x 128 tile per
+        # (sequence, head)); "seq" = the CUDA-core short-sequence kernels of csrc/vn_clip.cu (kept as cross-check)
+        import os
+        self.attn_impl = os.environ.get("VN_CLIP_ATTN", "tc")
 
     def plan(self, nseq: int, L: int, train: bool = True) -> "_ClipPlan":
         key = (nseq, L, train)
@@ -143,6 +147,7 @@ class _ClipPlan:
         self.qkv = per(lambda: z(nseq, L, 3 * C), nl)
         self.o = per(lambda: z(nseq, L, C), nl)
         self.lse = per(lambda: z(nseq, cfg.num_attention_heads, L, dt=F32), nl)
+        self.delta = z(nseq, cfg.num_attention_heads, L, dt=F32)        # scratch of the tcgen05 attention backward
         self.h1 = per(lambda: z(nseq, L, I), nl)
         # scratch shared by all layers
         self.n = z(nseq, L, C)
@@ -165,8 +170,12 @@ class _ClipPlan:
             x, xm, qkv = self.x[i], self.xm[i], self.qkv[i]
             ops.layernorm_fwd(x, l.ln1[0], l.ln1[1], cfg.layer_norm_eps, self.n, self.st1[i], rows)
             ops.gemm(self.n, l.qkv_f, qkv, bias=l.qkv_bias, ws=self.ws)
-            ops.seq_attention_fwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.o[i], self.lse[i], heads,
+            if eng.attn_impl == "tc":
+                ops.attention_fwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.o[i], self.lse[i], heads,
                                   scale=scale, causal=True)
+            else:
+                ops.seq_attention_fwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.o[i], self.lse[i], heads,
+                                      scale=scale, causal=True)
             ops.gemm(self.o[i], l.o_f, xm, bias=l.o_bias, R=x, ws=self.ws)
             ops.layernorm_fwd(xm, l.ln2[0], l.ln2[1], cfg.layer_norm_eps, self.n, self.st2[i], rows)
             ops.gemm(self.n, l.fc1_f, self.h1[i], bias=l.fc1_bias, ws=self.ws)
@@ -193,9 +202,14 @@ class _ClipPlan:
             ops.gemm(self.g, l.fc1_b, self.n, ws=self.ws)                    # d LN2-out
             ops.layernorm_bwd(self.xm[i], self.n, l.ln2[0], self.st2[i], dxm, rows, add=dy)
             ops.gemm(dxm, l.o_b, self.n, ws=self.ws)                         # d attention-out
-            ops.seq_attention_bwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.o[i], self.lse[i], self.n,
-                                  self.dq[..., :C], self.dq[..., C:2 * C], self.dq[..., 2 * C:], heads, scale=scale,
-                                  causal=True)
+            if eng.attn_impl == "tc":
+                ops.attention_bwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.o[i], self.lse[i], self.n,
+                                  self.delta, self.dq[..., :C], self.dq[..., C:2 * C], self.dq[..., 2 * C:], heads,
+                                  scale=scale, causal=True)
+            else:
+                ops.seq_attention_bwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.o[i], self.lse[i], self.n,
+                                      self.dq[..., :C], self.dq[..., C:2 * C], self.dq[..., 2 * C:], heads, scale=scale,
+                                      causal=True)
             ops.gemm(self.dq, l.qkv_b, self.n, ws=self.ws)                   # d LN1-out
             ops.layernorm_bwd(self.x[i], self.n, l.ln1[0], self.st1[i], dx, rows, add=dxm)
             dy, dx = dx, dy

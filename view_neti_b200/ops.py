@@ -212,13 +212,15 @@ def _attn_desc(q, k, v, o, lse, heads, scale) -> AttnDesc:
     return d
 
 
-def attention_fwd(q, k, v, o, lse, heads, scale=0.125):
+def attention_fwd(q, k, v, o, lse, heads, scale=0.125, causal=False):
     d = _attn_desc(q, k, v, o, lse, heads, scale)
+    d.causal = int(causal)
     check(_abi.load().vn_attention_fwd(C.byref(d), stream()), "attention_fwd")
 
 
-def attention_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, heads, scale=0.125, dkv_acc=None):
+def attention_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, heads, scale=0.125, dkv_acc=None, causal=False):
     d = _attn_desc(q, k, v, o, lse, heads, scale)
+    d.causal = int(causal)
     d.d_o, d.lddo, d.bsdo = ptr(d_o), d_o.stride(1), d_o.stride(0)
     d.delta = ptr(delta)
     if dq is not None:
