@@ -205,8 +205,10 @@ int vn_cfg_ddim_step(float* latents, const float* eps_uncond, const float* eps_c
  * Projections / LayerNorms use vn_gemm / vn_layernorm_*.
  *   vn_gelu_*            CLIPMLP activation (erf GELU): y = gelu(h);  dh = dy * gelu'(h).
  *   vn_seq_attention_*   CLIPAttention core for short sequences (nq == nk <= 128, head_dim 64), optional causal mask
- *                        (CLIPTextTransformer._build_causal_attention_mask); same descriptor as vn_attention_*; lse is
- *                        the natural-log sum-exp of the scaled logits; bwd needs q,k,v,o,lse,d_o and writes dq,dk,dv.
+ *                        (CLIPTextTransformer._build_causal_attention_mask) on CUDA cores; same descriptor as
+ *                        vn_attention_*; lse is the natural-log sum-exp of the scaled logits; bwd needs q,k,v,o,lse,d_o and
+ *                        writes dq,dk,dv.  The encoder uses vn_attention_* with desc.causal = 1 (tensor cores); these
+ *                        kernels are the independent cross-check of that path.
  * ------------------------------------------------------------------------------------------------ */
 int vn_gelu_fwd(const void* h, int64_t ldh, void* y, int64_t ldy, int rows, int F, vn_stream_t s);
 int vn_gelu_bwd(const void* h, int64_t ldh, const void* dy, int64_t lddy, void* dh, int64_t lddh, int rows, int F,

@@ -49,11 +49,17 @@ class NeTIConditioning(torch.nn.Module):
         self.mapper_view = mapper_view
 
     @staticmethod
-    def _positions(input_ids: torch.Tensor, placeholder: torch.Tensor) -> torch.Tensor:
+    def _as_list(ids):
+        """Placeholder ids as python ints with at most ONE device round trip (they usually arrive as host tensors / lists
+        from the data loader; per-element reads of a CUDA tensor would cost one synchronisation each)."""
+        if ids is None:
+            return None
+        return [int(v) for v in (ids.tolist() if torch.is_tensor(ids) else ids)]
+
+    @staticmethod
+    def _positions(input_ids: torch.Tensor, placeholder: torch.Tensor):
         locs = input_ids == placeholder.unsqueeze(1)
-        if not bool((locs.sum(1) == 1).all()):
-            raise VNError("every prompt must hold its placeholder token exactly once (net_clip_text_embedding.py:99,130)")
-        return locs.float().argmax(1)
+        return locs.float().argmax(1), (locs.sum(1) == 1).all()
 
     @staticmethod
     def _inject_bypass(state, rows, pos, bypass, unconstrained: bool, alpha: float):
@@ -83,23 +89,28 @@ class NeTIConditioning(torch.nn.Module):
         rows = torch.arange(N, device=dev)
         emb = self.token_embedding[input_ids].repeat(nl, 1, 1)                 # [N, L, C] (a fresh tensor: written below)
         obj = view = None
-        if len(self.mapper_object_lookup) > 0 and input_ids_placeholder_object is not None:
-            ph_o = torch.as_tensor(input_ids_placeholder_object, device=dev)
-            if not bool((ph_o == ph_o[0]).all()):
+        ok = []
+        ph_o = self._as_list(input_ids_placeholder_object)
+        ph_v = self._as_list(input_ids_placeholder_view)
+        if len(self.mapper_object_lookup) > 0 and ph_o is not None and ph_o[0] != -1:
+            if any(v != ph_o[0] for v in ph_o):
                 raise VNError("one object per batch (net_clip_text_embedding.py:67-68)")
-            mapper = self.mapper_object_lookup[str(int(ph_o[0]))]
+            mapper = self.mapper_object_lookup[str(ph_o[0])]
             out = mapper(timestep=t_rep, unet_layer=l_rep, input_ids_placeholder_view=None, truncation_idx=None)
-            pos_o = self._positions(input_ids, ph_o).repeat(nl)
+            pos_o, good = self._positions(input_ids, torch.tensor(ph_o, device=dev))
+            ok.append(good)
+            pos_o = pos_o.repeat(nl)
             emb[rows, pos_o] = out.word_embedding.to(emb.dtype)
             obj = (out, pos_o)
-        if self.mapper_view is not None and input_ids_placeholder_view is not None:
-            ph_v = torch.as_tensor(input_ids_placeholder_view, device=dev)
-            if not bool((ph_v == -1).all()):                                   # net_clip_text_embedding.py:105-106
-                out = self.mapper_view(timestep=t_rep, unet_layer=l_rep, input_ids_placeholder_view=ph_v.repeat(nl),
-                                       truncation_idx=None)
-                pos_v = self._positions(input_ids, ph_v).repeat(nl)
-                emb[rows, pos_v] = out.word_embedding.to(emb.dtype)
-                view = (out, pos_v)
+        if self.mapper_view is not None and ph_v is not None and not all(v == -1 for v in ph_v):   # net_clip_text_embedding.py:105-106
+            out = self.mapper_view(timestep=t_rep, unet_layer=l_rep, input_ids_placeholder_view=ph_v * nl, truncation_idx=None)
+            pos_v, good = self._positions(input_ids, torch.tensor(ph_v, device=dev))
+            ok.append(good)
+            pos_v = pos_v.repeat(nl)
+            emb[rows, pos_v] = out.word_embedding.to(emb.dtype)
+            view = (out, pos_v)
+        if ok and not bool(torch.stack(ok).all()):              # one synchronisation for both checks
+            raise VNError("every prompt must hold its placeholder token exactly once (net_clip_text_embedding.py:99,130)")
         x = emb + self.position_embedding[:L]
         last = self.encoder(inputs_embeds=x)[0]
         with_bypass = None
@@ -114,9 +125,12 @@ class NeTIConditioning(torch.nn.Module):
         if original_ti:
             return last_n[:B]                                                  # coach.py:307-309
         hs: Dict = {"this_idx": 0}
-        bypass_n = ln(with_bypass) if with_bypass is not None else None
+        # unbind, not 16 slices: its backward is ONE stack of the 16 context gradients instead of 16 zero-filled
+        # full-size tensors that autograd would have to add up
+        plain = last_n.view(nl, B, L, C).unbind(0)
+        bypass = ln(with_bypass).view(nl, B, L, C).unbind(0) if with_bypass is not None else None
         for i in range(nl):
-            hs[f"CONTEXT_TENSOR_{i}"] = last_n[i * B:(i + 1) * B]
-            if bypass_n is not None:
-                hs[f"CONTEXT_TENSOR_BYPASS_{i}"] = bypass_n[i * B:(i + 1) * B]
+            hs[f"CONTEXT_TENSOR_{i}"] = plain[i]
+            if bypass is not None:
+                hs[f"CONTEXT_TENSOR_BYPASS_{i}"] = bypass[i]
         return hs
