@@ -91,7 +91,10 @@ def _worker(rank, world, port, q):
     b.grad = torch.arange(5.0) * (rank + 1)          # c.grad stays None on every rank -> zeros
     red = FlatGradAllReducer([a, b, c])
     flat = red.allreduce_()
-    q.put((rank, a.grad.clone(), b.grad.clone(), c.grad.clone(), flat.numel()))
+    # construction-time broadcast (DDP semantics): ranks start from rank 0's values whatever their local init was
+    w = torch.nn.Parameter(torch.full((4,), float(10 + rank)))
+    FlatGradAllReducer([w]).broadcast_parameters_(0)
+    q.put((rank, a.grad.clone(), b.grad.clone(), c.grad.clone(), flat.numel(), w.detach().clone()))
     dist.destroy_process_group()
 
 
@@ -107,7 +110,8 @@ def test_flat_gradient_allreduce_gloo_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, a, b, c, n in res:
+    for rank, a, b, c, n, w in res:
+        assert torch.equal(w, torch.full((4,), 10.0))
         assert n == 12 + 5 + 2
         assert torch.allclose(a, torch.full((3, 4), 1.5))            # mean of 1 and 2
         assert torch.allclose(b, torch.arange(5.0) * 1.5)

@@ -38,6 +38,8 @@ class Coach:
                                        if params else None)
         self.lr_scheduler = lr_scheduler
         self.reducer = FlatGradAllReducer(params) if params else None
+        if self.reducer is not None:
+            self.reducer.broadcast_parameters_(0)       # what accelerate's DDP wrapper does at coach.py:97-99
         self.generator = generator
         self.global_step = 0
 

@@ -29,6 +29,18 @@ class FlatGradAllReducer:
     def world(self) -> int:
         return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
+    def broadcast_parameters_(self, src: int = 0) -> None:
+        """DDP's construction-time step: every rank starts from rank `src`'s parameter values (module init draws from the
+        process-local default generator, which torch seeds differently per process).  One broadcast of the flat buffer."""
+        if not self.params or self.world == 1:
+            return
+        with torch.no_grad():
+            for p, v in zip(self.params, self.views):
+                v.copy_(p)
+            dist.broadcast(self.flat, src=src)
+            for p, v in zip(self.params, self.views):
+                p.copy_(v)
+
     def allreduce_(self) -> Optional[torch.Tensor]:
         """In place: p.grad <- mean over ranks of p.grad (a missing grad counts as zero)."""
         if not self.params:

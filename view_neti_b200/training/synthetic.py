@@ -27,9 +27,11 @@ def build_conditioning(device="cuda", cfg: ClipEncoderConfig = SD21_TEXT, seed: 
     sig = PESigmas(sigma_t=0.03, sigma_l=2.0, sigma_theta=0.5, sigma_phi=0.5, sigma_r=0.5, sigma_dtu12=0.5)
     kw = dict(output_dim=C, arch_mlp_hidden_dims=64, arch_view_net=15, arch_view_disable_tl=False, use_nested_dropout=False,
               pe_sigmas=sig, output_bypass=True, bypass_unconstrained=True, output_bypass_alpha=0.2)
-    mo = NeTIMapper(embedding_type="object", norm_scale=torch.tensor(0.3714), placeholder_object_token="<statue>", **kw).to(device)
-    mv = NeTIMapper(embedding_type="view", norm_scale=torch.tensor(0.4102), placeholder_view_tokens=list(VIEW_TOKENS),
-                    placeholder_view_token_ids=list(VIEW_TOKEN_IDS), **kw).to(device)
+    with torch.random.fork_rng(devices=[]):          # nn.Linear init draws from the process-local default generator
+        torch.manual_seed(seed + 1)
+        mo = NeTIMapper(embedding_type="object", norm_scale=torch.tensor(0.3714), placeholder_object_token="<statue>", **kw).to(device)
+        mv = NeTIMapper(embedding_type="view", norm_scale=torch.tensor(0.4102), placeholder_view_tokens=list(VIEW_TOKENS),
+                        placeholder_view_token_ids=list(VIEW_TOKEN_IDS), **kw).to(device)
     return NeTIConditioning(tok, pos, (torch.ones(C), torch.zeros(C)), enc, {OBJECT_TOKEN_ID: mo}, mv)
 
 
