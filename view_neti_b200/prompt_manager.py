@@ -18,7 +18,7 @@ from .models.neti_conditioning import NeTIConditioning
 
 
 class PromptManager:
-    """ Class for computing all time and space embeddings for a given prompt. """
+    """Precomputes, for one prompt, the per-timestep / per-UNet-layer context dicts of a whole sampling schedule."""
 
     def __init__(self, tokenizer, text_encoder: NeTIConditioning, timesteps: Sequence[int] = constants.SD_INFERENCE_TIMESTEPS,
                  unet_layers: List[str] = constants.UNET_LAYERS, placeholder_view_token_ids: List[int] = None,
