@@ -55,19 +55,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// D[tmem] (+)= A[128 x 64 k, K-major] * B[N x 64 k, K-major]^T : 4 k-steps
-__device__ __forceinline__ void mma_kk(uint32_t tacc, uint32_t a, uint32_t b, uint32_t id) {
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    umma_bf16(tacc, umma_desc_k_sw128(a) + (uint64_t)(k * 2), umma_desc_k_sw128(b) + (uint64_t)(k * 2), id, k ? 1u : 0u);
-}
-// D[tmem] (+)= A[128 x 128 k: two K-major 64-wide blocks] * B[128 k x 64 n, MN-major tile used in place] : 8 k-steps
-__device__ __forceinline__ void mma_kmn(uint32_t tacc, uint32_t a, uint32_t b, uint32_t id, bool accumulate) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k)
-    umma_bf16(tacc, umma_desc_k_sw128(a + (k >> 2) * TILE_BYTES) + (uint64_t)((k & 3) * 2), desc_mn_sw128(b + k * 2048), id,
-              (accumulate || k) ? 1u : 0u);
-}
 // half-tile variants (64 of the 128 columns / k-rows), used to pipeline the tensor pipe against the compute warps:
 // D[128 x 64] = A[128 x 64 k] * B[rows h*64.. of a 128-row K-major tile]^T
 __device__ __forceinline__ void mma_kk_half(uint32_t tacc, uint32_t a, uint32_t b, int h, uint32_t id64) {
