@@ -166,3 +166,36 @@ def test_gemm_tuning_table_is_well_formed():
             assert split == 1 and bn in (128, 192, 256), (key, bn, code)
             if mode == 0:                      # (conv m-tiles depend on the spatial tiling; vn_gemm falls back if odd)
                 assert ((M + 127) // 128) % 2 == 0, key
+
+
+def test_prompt_manager_host_logic():
+    """PromptManager's host side (reference prompt_manager.py:52-71): tokenizer call convention and which placeholder
+    ids a prompt holds (-1 when none, exactly one of a kind otherwise); the embedding itself is CUDA-only."""
+    from types import SimpleNamespace
+    from view_neti_b200.prompt_manager import PromptManager
+
+    class Tok:
+        model_max_length = 77
+
+        def __call__(self, text, padding=None, max_length=None, return_tensors=None):
+            assert padding == "max_length" and max_length == 77 and return_tensors == "pt"
+            ids = torch.full((1, 77), 7)
+            ids[0, 2], ids[0, 5] = 49410, 49408
+            return SimpleNamespace(input_ids=ids)
+
+    cond = SimpleNamespace(n_layers=16)
+    pm = PromptManager(Tok(), cond, timesteps=[999, 500], placeholder_view_token_ids=[49409, 49410],
+                       placeholder_object_token_ids=[49408])
+    ids = pm._tokenize("<view_10_40_1p2>. a photo of a <statue>")
+    assert ids.shape == (1, 77)
+    assert pm._placeholder(ids, pm.placeholder_view_token_ids, "p").tolist() == [49410]
+    assert pm._placeholder(ids, pm.placeholder_object_token_ids, "p").tolist() == [49408]
+    assert pm._placeholder(ids, [55555], "p").tolist() == [-1] and pm._placeholder(ids, None, "p").tolist() == [-1]
+    two = ids.clone()
+    two[0, 9] = 49409
+    with pytest.raises(AssertionError):
+        pm._placeholder(two, pm.placeholder_view_token_ids, "p")
+    assert torch.equal(pm._tokenize(torch.arange(77)), torch.arange(77).view(1, 77))
+    from view_neti_b200 import constants
+    assert len(constants.SD_INFERENCE_TIMESTEPS) == 50 and constants.SD_INFERENCE_TIMESTEPS[:3] == [999, 979, 959]
+    assert constants.SD_INFERENCE_TIMESTEPS[24:27] == [519, 500, 480] and constants.SD_INFERENCE_TIMESTEPS[-1] == 20
