@@ -345,6 +345,10 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     const int pf_end = min(nkb, p.pf_dist);
     for (int i = 0; i < pf_end; ++i) tma_prefetch_l2_2d(&tmB, (kb_begin + i) * BK, n0);
   }
+  // coordinates of the CTA's first tile (a handful of integer divisions): computed here, where they overlap the
+  // predecessor kernel's tail, instead of at the head of every role's loop behind griddepcontrol.wait
+  const int tile_first = VN_TILE_OF(tile_begin);
+  const TileCoord c_first = tile_coord(p, tile_first, BN);
   pdl_wait();          // everything above overlapped the previous kernel; activations are touched only from here on
   if (threadIdx.x == 0) VN_STAMP(3);
   const bool tma_epi = !SPLIT && p.use_tma_epilogue;
@@ -360,8 +364,7 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
       int s = 0, t = 0;
       uint32_t ph = 1;                             // parity to wait for on empty_bar[s]
       for (int w = tile_begin; w < num_tiles; w += tile_step, ++t) {
-        const int tile = VN_TILE_OF(w);
-        const TileCoord c = tile_coord(p, tile, BN);
+        const TileCoord c = w == tile_begin ? c_first : tile_coord(p, VN_TILE_OF(w), BN);
         int kx = kb_begin * BK;                    // K coordinate (elements) of the next k-block
         int cb = 0, dx = 0, dy = 0;                // conv: 64-channel block and 3x3 tap of the next k-block
         if (p.mode == 1) {
@@ -423,8 +426,7 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
       uint32_t ph = 1;
       const uint32_t lead_full = CG == 2 ? mapa_shared(smem_u32(full_bar), 0) : 0;
       for (int w = tile_begin; w < num_tiles; w += tile_step) {
-        const int tile = VN_TILE_OF(w);
-        int n0 = (tile / p.m_tiles) * BN;
+        int n0 = w == tile_begin ? c_first.n0 : (VN_TILE_OF(w) / p.m_tiles) * BN;
         if (CG == 2) {
           // the pair's MMA takes B rows [0, n/2) from the leader and [n/2, n) from its peer (n = the tile's UMMA N)
           const int n_eff = (min(BN, p.N - n0) + 15) & ~15;
@@ -451,8 +453,7 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
       constexpr uint64_t kStageStep = (uint64_t)(STAGE_BYTES >> 4);      // descriptor start-address units of 16 B
       constexpr uint64_t kBOffset = (uint64_t)(A_BYTES >> 4);
       for (int w = tile_begin; w < num_tiles; w += tile_step, ++t) {
-        const int tile = VN_TILE_OF(w);
-        const int n0 = (tile / p.m_tiles) * BN;
+        const int n0 = w == tile_begin ? c_first.n0 : (VN_TILE_OF(w) / p.m_tiles) * BN;
         int n_eff = min(BN, p.N - n0);
         n_eff = (n_eff + 15) & ~15;               // UMMA N granularity; B rows beyond N are TMA zero-fill
         const uint32_t idesc = umma_idesc_bf16(BM * CG, n_eff);
@@ -497,8 +498,7 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     int t = 0;
     const uint32_t lead_tempty = CG == 2 ? mapa_shared(smem_u32(tempty_bar), 0) : 0;
     for (int w = tile_begin; w < num_tiles; w += tile_step, ++t) {
-      const int tile = VN_TILE_OF(w);
-      const TileCoord c = tile_coord(p, tile, BN);
+      const TileCoord c = w == tile_begin ? c_first : tile_coord(p, VN_TILE_OF(w), BN);
       const int as = t & 1;
       long long gm;
       int bidx;
@@ -636,8 +636,7 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     // pieces per instruction, measured 1.7x slower on B200); the finishing threads read it back with LDS.128,
     // conflict-free for the same reason.
     float* exch = reinterpret_cast<float*>(smem);
-    const int tile = tile_begin;
-    const TileCoord c = tile_coord(p, tile, BN);
+    const TileCoord c = c_first;
     if (warp >= 2 && warp < 6) {
       mbar_wait(&tfull_bar[0], 0);                // my accumulator is complete => my stages are no longer read
       tc_fence_after();
