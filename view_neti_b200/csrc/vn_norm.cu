@@ -730,11 +730,29 @@ __global__ void __launch_bounds__(256) ln_kernel(const bf16* __restrict__ x, lon
                                                  long long ldadd, bf16* __restrict__ y, long long ldy, int rows,
                                                  int C) {
   pdl_trigger();
-  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
   const int vecs = C >> 3;
+  // the affine parameters are frozen: fetched ahead of the grid dependency, so their latency overlaps the predecessor
+  float gm[NV][8], bt[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + i * 32;
+    if (v < vecs) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+      gm[i][0] = g0.x; gm[i][1] = g0.y; gm[i][2] = g0.z; gm[i][3] = g0.w;
+      gm[i][4] = g1.x; gm[i][5] = g1.y; gm[i][6] = g1.z; gm[i][7] = g1.w;
+      if (MODE == 0) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+        bt[i][0] = b0.x; bt[i][1] = b0.y; bt[i][2] = b0.z; bt[i][3] = b0.w;
+        bt[i][4] = b1.x; bt[i][5] = b1.y; bt[i][6] = b1.z; bt[i][7] = b1.w;
+      }
+    }
+  }
+  pdl_wait();
+  if (row >= rows) return;
   const bf16* xr = x + (long long)row * ldx;
   float xf[NV][8];
   uint4 raw[NV], draw[NV], araw[NV];
@@ -775,15 +793,9 @@ __global__ void __launch_bounds__(256) ln_kernel(const bf16* __restrict__ x, lon
     for (int i = 0; i < NV; ++i) {
       const int v = lane + i * 32;
       if (v < vecs) {
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (xf[i][j] - mean) * rstd * g[j] + bb[j];
+        for (int j = 0; j < 8; ++j) o[j] = (xf[i][j] - mean) * rstd * gm[i][j] + bt[i][j];
         *reinterpret_cast<uint4*>(yr + v * 8) = pack8(o);
       }
     }
@@ -795,14 +807,11 @@ __global__ void __launch_bounds__(256) ln_kernel(const bf16* __restrict__ x, lon
     for (int i = 0; i < NV; ++i) {
       const int v = lane + i * 32;
       if (v < vecs) {
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
         float df[8];
         unpack8(draw[i], df);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          dh[i][j] = df[j] * g[j];
+          dh[i][j] = df[j] * gm[i][j];
           xf[i][j] = (xf[i][j] - mean) * rstd;
           c1 += dh[i][j];
           c2 = fmaf(dh[i][j], xf[i][j], c2);
