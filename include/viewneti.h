@@ -51,6 +51,8 @@ void        vn_set_pdl(int enabled);
  *         k = tap*C + c; M = nb*H*W.                 replaces cuDNN Conv2d in diffusers ResnetBlock2D /
  *         Upsample2D; with flipped+transposed weights it is the conv dgrad.
  * B is always [N,K] bf16 K-major (ldb).  D is bf16 (or fp32 when out_fp32) with row stride ldd.
+ * B is treated as FROZEN WEIGHTS: its first tiles are fetched ahead of the programmatic dependency on the preceding
+ * kernel of the stream, so B must not be the output of a preceding vn_* launch (A, R and D may be).
  * Constraints: K % 64 == 0 (mode 1: C % 64 == 0), N % 8 == 0, lda/ldb/ldd/ldr % 8 == 0, 16-byte aligned bases.
  * Split-K: `workspace` must hold >= vn_gemm_workspace_bytes() bytes, be all-zero before the first call
  * and is left all-zero by every call (self-cleaning), so one buffer serves a whole stream.

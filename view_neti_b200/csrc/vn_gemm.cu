@@ -339,11 +339,24 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
   // cp.async.bulk.prefetch.tensor (no shared memory, no barrier); the first ones even before griddepcontrol.wait,
   // because nothing on the device ever writes the frozen weights.
   constexpr int kBWarp = SPLIT ? 6 : 2 + 4 * kEpiHalves;
-  if (kProducers == 2 && MC == 1 && p.pf_dist > 0 && warp == kBWarp && lane == 0 && tile_begin < num_tiles) {
+  // The B producer also puts the weight tiles of the first STAGES k-blocks in flight BEFORE the grid dependency is
+  // resolved (all stages are free at start; the A producer arms the barriers with expect_tx afterwards - a complete_tx
+  // that lands first only drives the transaction count negative until then, the phase cannot complete without the
+  // pending arrival).  Costs the A producer nothing: it is a different thread.
+  int b_pre = 0;
+  if (kProducers == 2 && MC == 1 && warp == kBWarp && lane == 0 && tile_begin < num_tiles) {
     int n0 = (VN_TILE_OF(tile_begin) / p.m_tiles) * BN;
     if (CG == 2) n0 += (int)crank * (((min(BN, p.N - n0) + 15) & ~15) >> 1);
-    const int pf_end = min(nkb, p.pf_dist);
-    for (int i = 0; i < pf_end; ++i) tma_prefetch_l2_2d(&tmB, (kb_begin + i) * BK, n0);
+    b_pre = min(nkb, STAGES);
+    const uint32_t lead_full0 = CG == 2 ? mapa_shared(smem_u32(full_bar), 0) : 0;
+    for (int i = 0; i < b_pre; ++i) {
+      if (CG == 2) tma_load_2d_cg2(smem + i * STAGE_BYTES + A_BYTES, &tmB, lead_full0 + (uint32_t)(i * 8), (kb_begin + i) * BK, n0);
+      else tma_load_2d(smem + i * STAGE_BYTES + A_BYTES, &tmB, &full_bar[i], (kb_begin + i) * BK, n0);
+    }
+    if (p.pf_dist > 0) {
+      const int pf_end = min(nkb, p.pf_dist);
+      for (int i = b_pre; i < pf_end; ++i) tma_prefetch_l2_2d(&tmB, (kb_begin + i) * BK, n0);
+    }
   }
   // coordinates of the CTA's first tile (a handful of integer divisions): computed here, where they overlap the
   // predecessor kernel's tail, instead of at the head of every role's loop behind griddepcontrol.wait
@@ -435,9 +448,11 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
         int kx = kb_begin * BK;
         for (int i = 0; i < nkb; ++i) {
           if (p.pf_dist > 0 && i + p.pf_dist < nkb) tma_prefetch_l2_2d(&tmB, kx + p.pf_dist * BK, n0);
-          mbar_wait(&empty_bar[s], ph);
-          if (CG == 2) tma_load_2d_cg2(smem + s * STAGE_BYTES + A_BYTES, &tmB, lead_full + (uint32_t)(s * 8), kx, n0);
-          else tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &tmB, &full_bar[s], kx, n0);
+          if (w != tile_begin || i >= b_pre) {             // (the first b_pre tiles of the first tile are already in flight)
+            mbar_wait(&empty_bar[s], ph);
+            if (CG == 2) tma_load_2d_cg2(smem + s * STAGE_BYTES + A_BYTES, &tmB, lead_full + (uint32_t)(s * 8), kx, n0);
+            else tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &tmB, &full_bar[s], kx, n0);
+          }
           kx += BK;
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
