@@ -199,3 +199,46 @@ def test_prompt_manager_host_logic():
     from view_neti_b200 import constants
     assert len(constants.SD_INFERENCE_TIMESTEPS) == 50 and constants.SD_INFERENCE_TIMESTEPS[:3] == [999, 979, 959]
     assert constants.SD_INFERENCE_TIMESTEPS[24:27] == [519, 500, 480] and constants.SD_INFERENCE_TIMESTEPS[-1] == 20
+
+
+def test_checkpoint_handler_reads_reference_format_and_round_trips(tmp_path):
+    """tests/golden/mapper_ckpt_{object,view}.pt are in the layout the reference writes, built from the reference's own
+    NeTIMapper / RunConfig objects (tests/golden/make_golden_checkpoint.py) - they pickle reference classes.  They must
+    load here WITHOUT the reference on sys.path, give back the exact weights, and survive a save / load round trip."""
+    import sys
+    from view_neti_b200.checkpoint_handler import CheckpointHandler
+    assert not any(p.rstrip("/").endswith("reference") for p in sys.path)
+    gdir = os.path.join(ROOT, "tests", "golden")
+    raw = torch.load(os.path.join(gdir, "mapper_ckpt_object.pt"), map_location="cpu", weights_only=False,
+                     pickle_module=__import__("view_neti_b200.checkpoint_handler", fromlist=["_PickleModule"])._PickleModule)
+    cfg, objs = CheckpointHandler.load_mapper(os.path.join(gdir, "mapper_ckpt_object.pt"), "object",
+                                              placeholder_object_tokens=["<statue>", "<teapot>"],
+                                              placeholder_object_token_ids=[49408, 49409])
+    assert cfg["model"]["arch_view_net"] == 15 and sorted(objs) == [49408, 49409]
+    for tid, m in objs.items():
+        ref_sd = raw["mappers"][tid]["state_dict"]
+        assert m.placeholder_object_token == raw["mappers"][tid]["placeholder_object_token"]
+        for k, v in m.state_dict().items():
+            assert torch.equal(v, ref_sd[k]), k
+        assert torch.equal(m.encoder_w, ref_sd["encoder.w"]) and abs(float(m.norm_scale) - 0.3714) < 1e-6
+        assert m.bypass_unconstrained and m.output_bypass and sum(p.numel() for p in m.parameters()) == 64 * 64 * 2 + 64 * 4 + 64 * 2 + 256 * 64 + 256
+    toks, ids = ["<view_0_10_1p2>", "<view_10_40_1p2>", "<view_20_70_1p2>"], [49410, 49411, 49412]
+    cfg, mv = CheckpointHandler.load_mapper(os.path.join(gdir, "mapper_ckpt_view.pt"), "view", placeholder_view_tokens=toks,
+                                            placeholder_view_token_ids=ids)
+    assert mv.deg_freedom == "theta-phi" and mv.embedding_type == "view"
+    # round trip through our writer (file names as the reference derives them, checkpoint_handler.py:73-76,93-96)
+    h = CheckpointHandler(cfg=cfg, placeholder_view_tokens=toks, placeholder_view_token_ids=ids,
+                          placeholder_object_tokens=["<statue>", "<teapot>"], placeholder_object_token_ids=[49408, 49409],
+                          save_root=tmp_path)
+    h.save_mapper(objs, mv, "mapper-steps-250.pt")
+    assert sorted(os.listdir(tmp_path)) == ["mapper-steps-250_object.pt", "mapper-steps-250_view.pt"]
+    _, objs2 = CheckpointHandler.load_mapper(tmp_path / "mapper-steps-250_object.pt", "object",
+                                             placeholder_object_tokens=["<statue>", "<teapot>"], placeholder_object_token_ids=[49408, 49409])
+    _, mv2 = CheckpointHandler.load_mapper(tmp_path / "mapper-steps-250_view.pt", "view", placeholder_view_tokens=toks,
+                                           placeholder_view_token_ids=ids)
+    for a, b in ((objs[49408], objs2[49408]), (objs[49409], objs2[49409]), (mv, mv2)):
+        assert all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), b.state_dict().values()))
+    emb = torch.randn(49420, 16)
+    h.save_learned_embeds(emb, "learned_embeds-steps-250.bin")
+    tokens, rows = CheckpointHandler.load_learned_embeds(tmp_path / "learned_embeds-steps-250.bin")
+    assert tokens == toks + ["<statue>", "<teapot>"] and torch.equal(rows, emb[ids + [49408, 49409]])
