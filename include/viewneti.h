@@ -170,6 +170,9 @@ int vn_upsample2x_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, int nb, 
 int vn_upsample2x_bwd(const void* dy, int64_t lddy, void* dx, int64_t lddx, int nb, int H, int W, int C, vn_stream_t s);
 /* diffusers Downsample2D (Conv 3x3 stride 2 pad 1) = im2col + vn_gemm.  col [nb*Ho*Wo, 9*C], k = tap*C + c */
 int vn_im2col_s2(const void* x, int64_t ldx, void* col, int nb, int H, int W, int C, vn_stream_t s);
+/* the VAE encoder's Downsample2D(padding=0): F.pad(x, (0,1,0,1)) + Conv 3x3 stride 2 pad 0 (replaces diffusers
+ * AutoencoderKL.encode called at reference training/coach.py:167).  Ho = (H-2)/2 + 1; same col layout */
+int vn_im2col_s2_pad0(const void* x, int64_t ldx, void* col, int nb, int H, int W, int C, vn_stream_t s);
 /* dgrad: dx[nb,H,W,C] = col2im(dcol) (+ add) */
 int vn_col2im_s2(const void* dcol, const void* add, int64_t ldadd, void* dx, int64_t lddx,
                  int nb, int H, int W, int C, vn_stream_t s);
@@ -215,6 +218,10 @@ int vn_cfg_ddim_step(float* latents, const float* eps_uncond, const float* eps_c
 int vn_gelu_fwd(const void* h, int64_t ldh, void* y, int64_t ldy, int rows, int F, vn_stream_t s);
 int vn_gelu_bwd(const void* h, int64_t ldh, const void* dy, int64_t lddy, void* dh, int64_t lddh, int rows, int F,
                 vn_stream_t s);
+/* VAE mid-block attention (one head over all channels, reference training/coach.py:167 / sd_pipeline_call.py:115 ->
+ * diffusers AttentionBlock): P[r,:] = softmax(scale * S[r,:]), S fp32 [rows, cols] (vn_gemm with out_fp32), P bf16.
+ * cols % 4 == 0, cols <= 8192, scale > 0 */
+int vn_softmax_rows(const float* S, int64_t lds, void* P, int64_t ldp, int rows, int cols, float scale, vn_stream_t s);
 int vn_seq_attention_fwd(const struct vn_attn_desc* d, int causal, vn_stream_t s);
 int vn_seq_attention_bwd(const struct vn_attn_desc* d, int causal, vn_stream_t s);
 

@@ -1,0 +1,105 @@
+"""CPU checks of the VAE: the oracle's structural pins, and the host logic of models/vae.py run
+through a torch emulation of the kernels it launches (tests/ops_emulation.py) against the oracle."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import vae as ovae
+from tests import ops_emulation as emu
+from view_neti_b200.models import vae as vmod
+from view_neti_b200.models.vae import SD21_VAE, TINY_VAE, init_state_dict, num_params, param_table
+
+
+def rel(a, b):
+    return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-20))
+
+
+def test_vae_param_table_matches_sd21_checkpoint_layout():
+    # stabilityai/stable-diffusion-2-1 vae: 83 653 863 parameters (public model card / any loader's count)
+    assert num_params(SD21_VAE) == 83_653_863
+    names = [n for n, _, _ in param_table(SD21_VAE)]
+    assert len(names) == len(set(names)) == 248
+    for k in ("encoder.down_blocks.1.resnets.0.conv_shortcut.weight", "encoder.down_blocks.2.downsamplers.0.conv.bias",
+              "encoder.mid_block.attentions.0.proj_attn.weight", "decoder.up_blocks.2.resnets.0.conv_shortcut.bias",
+              "decoder.up_blocks.0.upsamplers.0.conv.weight", "decoder.mid_block.attentions.0.group_norm.weight",
+              "quant_conv.weight", "post_quant_conv.bias"):
+        assert k in names, k
+    assert "encoder.down_blocks.3.downsamplers.0.conv.weight" not in names
+    assert "decoder.up_blocks.3.upsamplers.0.conv.weight" not in names
+    shapes = {n: s for n, s, _ in param_table(SD21_VAE)}
+    assert shapes["decoder.up_blocks.2.resnets.0.conv1.weight"] == (256, 512, 3, 3)
+    assert shapes["decoder.up_blocks.3.resnets.0.conv1.weight"] == (128, 256, 3, 3)
+    assert shapes["encoder.conv_out.weight"] == (8, 512, 3, 3)
+
+
+def test_vae_oracle_pieces_against_independent_formulas():
+    cfg = TINY_VAE
+    sd = {k: v.double() for k, v in init_state_dict(cfg, 3).items()}
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 128, 8, 8, generator=g, dtype=torch.float64)
+    # attention: explicit per-pixel loops over the definition
+    p = "encoder.mid_block.attentions.0"
+    got = ovae.attention(sd, p, x, 32, 1e-6)
+    t = F.group_norm(x, 32, sd[p + ".group_norm.weight"], sd[p + ".group_norm.bias"], 1e-6).flatten(2)[0].t()
+    q = t @ sd[p + ".query.weight"].t() + sd[p + ".query.bias"]
+    k = t @ sd[p + ".key.weight"].t() + sd[p + ".key.bias"]
+    v = t @ sd[p + ".value.weight"].t() + sd[p + ".value.bias"]
+    want = torch.empty(64, 128, dtype=torch.float64)
+    for i in range(64):
+        w = torch.exp((q[i] * k).sum(-1) / math.sqrt(128))
+        want[i] = (w[:, None] * v).sum(0) / w.sum()
+    want = want @ sd[p + ".proj_attn.weight"].t() + sd[p + ".proj_attn.bias"]
+    assert rel(got, x + want.t().reshape(1, 128, 8, 8)) < 1e-12
+    # encoder downsample: output (y, x) reads input rows 2y..2y+2, zero beyond the far edge only
+    h = torch.randn(1, 64, 6, 6, generator=g, dtype=torch.float64)
+    wgt, b = sd["encoder.down_blocks.0.downsamplers.0.conv.weight"], sd["encoder.down_blocks.0.downsamplers.0.conv.bias"]
+    got = F.conv2d(F.pad(h, (0, 1, 0, 1)), wgt, b, stride=2)
+    assert got.shape == (1, 64, 3, 3)
+    hp = torch.zeros(1, 64, 7, 7, dtype=torch.float64)
+    hp[..., :6, :6] = h
+    for (yy, xx) in [(0, 0), (2, 2), (1, 2)]:
+        want = (wgt * hp[0, :, 2 * yy:2 * yy + 3, 2 * xx:2 * xx + 3]).sum(dim=(1, 2, 3)) + b
+        assert rel(got[0, :, yy, xx], want) < 1e-12
+    # shapes and the sampling formula of coach.py:165-169
+    img = torch.randn(2, 3, 64, 64, generator=g, dtype=torch.float64)
+    mean, logvar = ovae.encode_moments(sd, cfg, img)
+    assert mean.shape == logvar.shape == (2, 4, 8, 8) and float(logvar.max()) <= 20 and float(logvar.min()) >= -30
+    noise = torch.randn(2, 4, 8, 8, generator=g, dtype=torch.float64)
+    lat = ovae.encode_latents(sd, cfg, img, noise)
+    assert rel(lat, (mean + (logvar / 2).exp() * noise) * 0.18215) < 1e-14
+    out = ovae.decode_latents(sd, cfg, lat)
+    assert out.shape == (2, 64, 64, 3) and float(out.min()) >= 0 and float(out.max()) <= 1
+
+
+@pytest.mark.parametrize("nb,size", [(1, 64), (2, 64)])
+def test_vae_host_logic_through_emulated_kernels(monkeypatch, nb, size):
+    cfg = TINY_VAE
+    sd = init_state_dict(cfg, 0)
+    monkeypatch.setattr(vmod, "ops", emu)
+    monkeypatch.setattr(vmod, "_require_cuda", lambda dev: None)
+    emu.reset()
+    vae = vmod.AutoencoderKL(sd, cfg, device="cpu")
+    g = torch.Generator().manual_seed(1)
+    img = torch.rand(nb, 3, size, size, generator=g) * 2 - 1
+    mean_o, logvar_o = ovae.encode_moments(sd, cfg, img)
+    for _ in range(2):                                   # second call: scratch reuse, statistics slots re-zeroed
+        dist = vae.encode(img).latent_dist
+        assert rel(dist.mean, mean_o) < 2e-2 and rel(dist.logvar, logvar_o) < 2e-2, (rel(dist.mean, mean_o),
+                                                                                      rel(dist.logvar, logvar_o))
+    assert dist.sample(torch.Generator().manual_seed(0)).shape == (nb, 4, size // 8, size // 8)
+    z = torch.randn(nb, 4, size // 8, size // 8, generator=g)
+    dec_o = ovae.decode(sd, cfg, z)
+    for _ in range(2):
+        dec = vae.decode(z).sample
+        assert dec.shape == (nb, 3, size, size) and rel(dec, dec_o) < 2e-2, rel(dec, dec_o)
+    got = vmod.decode_latents(vae, z * cfg.scaling_factor)
+    want = ovae.decode_latents(sd, cfg, z * cfg.scaling_factor).numpy()
+    assert got.shape == want.shape == (nb, size, size, 3) and abs(got - want).max() < 3e-2
+
+
+def test_vae_engine_refuses_cpu():
+    from view_neti_b200._abi import VNError
+    with pytest.raises(VNError):
+        vmod.VAEEngine(init_state_dict(TINY_VAE, 0), TINY_VAE, device="cpu")

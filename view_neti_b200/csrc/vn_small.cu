@@ -76,12 +76,13 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const bf16* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
-// stride-2 3x3 pad-1 convolution support (diffusers Downsample2D): explicit im2col and its adjoint.
-// col row = output pixel, k = tap*C + c.  Ho = (H-1)/2 + 1.
+// stride-2 3x3 convolution support (diffusers Downsample2D): explicit im2col and its adjoint.
+// col row = output pixel, k = tap*C + c.  `pad` zero rows/columns in front: 1 = the UNet's symmetric pad-1 form
+// (Ho = (H-1)/2 + 1); 0 = the VAE encoder's F.pad(x, (0,1,0,1)) + pad-0 conv (Ho = (H-2)/2 + 1).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) im2col_s2_kernel(const bf16* __restrict__ x, long long ldx,
                                                         bf16* __restrict__ col, int nb, int H, int W, int Ho, int Wo,
-                                                        int C) {
+                                                        int C, int pad) {
   pdl_trigger();
   pdl_wait();
   const int vecs = C >> 3;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const bf16* __restrict__
     const int wo = (int)(p % Wo); p /= Wo;
     const int ho = (int)(p % Ho);
     const int b = (int)(p / Ho);
-    const int h = 2 * ho + tap / 3 - 1, w = 2 * wo + tap % 3 - 1;
+    const int h = 2 * ho + tap / 3 - pad, w = 2 * wo + tap % 3 - pad;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (h >= 0 && h < H && w >= 0 && w < W) v = *reinterpret_cast<const uint4*>(x + (((long long)b * H + h) * W + w) * ldx + c);
     const long long row = ((long long)b * Ho + ho) * Wo + wo;
@@ -387,7 +388,17 @@ extern "C" int vn_im2col_s2(const void* x, int64_t ldx, void* col, int nb, int H
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long long total = (long long)nb * Ho * Wo * 9 * (C / 8);
   VN_LAUNCH(im2col_s2_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)s, (const bf16*)x, ldx, (bf16*)col, nb, H, W, Ho, Wo,
-                                                                       C);
+                                                                       C, 1);
+  return 0;
+}
+
+extern "C" int vn_im2col_s2_pad0(const void* x, int64_t ldx, void* col, int nb, int H, int W, int C, vn_stream_t s) {
+  VN_CHECK(C % 8 == 0 && ldx % 8 == 0, "im2col_s2_pad0: C and stride must be multiples of 8");
+  VN_CHECK(H >= 2 && W >= 2, "im2col_s2_pad0: image smaller than 2x2");
+  const int Ho = (H - 2) / 2 + 1, Wo = (W - 2) / 2 + 1;
+  const long long total = (long long)nb * Ho * Wo * 9 * (C / 8);
+  VN_LAUNCH(im2col_s2_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)s, (const bf16*)x, ldx, (bf16*)col, nb, H, W, Ho, Wo,
+                                                                       C, 0);
   return 0;
 }
 

@@ -6,6 +6,8 @@ computes: each function is exactly one library call (there is no CPU / eager fal
 """
 from __future__ import annotations
 
+import contextlib
+
 import ctypes as C
 from typing import Optional
 
@@ -72,8 +74,17 @@ class Workspace:
 
 
 def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, bias=None, rowbias=None, rows_per_batch: int = 0,
-         R=None, ws: Optional[Workspace] = None, force_bn: int = 0, force_split: int = 0) -> torch.Tensor:
-    """D[M,N] = A[M,K] @ B[N,K]^T (+bias[N]) (+rowbias[row // rows_per_batch, N]) (+R[M,N])."""
+         R=None, ws: Optional[Workspace] = None, force_bn: int = 0, force_split: int = 0,
+         b_dynamic: bool = False) -> torch.Tensor:
+    """D[M,N] = A[M,K] @ B[N,K]^T (+bias[N]) (+rowbias[row // rows_per_batch, N]) (+R[M,N]).
+
+    b_dynamic: B was written by an earlier launch on this stream (not a frozen weight).  The kernel requests its first
+    B tiles before it waits for its predecessor (include/viewneti.h, vn_gemm), so such a product is launched without
+    programmatic dependent launch."""
+    if b_dynamic and _PDL:
+        with pdl_off():
+            return gemm(A, B, D, bias=bias, rowbias=rowbias, rows_per_batch=rows_per_batch, R=R, ws=ws,
+                        force_bn=force_bn, force_split=force_split)
     lib = _abi.load()
     M, K = A.shape[-2] * (A.numel() // (A.shape[-1] * A.shape[-2])), A.shape[-1]
     N = B.shape[0]
@@ -272,6 +283,20 @@ def im2col_s2(x, col):
     check(_abi.load().vn_im2col_s2(ptr(x), _pix_ld(x), ptr(col), nb, H, W, Cc, stream()), "im2col_s2")
 
 
+def im2col_s2_pad0(x, col):
+    """VAE-encoder downsample: zero pad (0,1,0,1), 3x3 taps at stride 2.  col [nb*(H//2)*(W//2), 9*C]."""
+    nb, H, W, Cc = x.shape
+    check(_abi.load().vn_im2col_s2_pad0(ptr(x), _pix_ld(x), ptr(col), nb, H, W, Cc, stream()), "im2col_s2_pad0")
+
+
+def softmax_rows(S, P, scale):
+    """P = softmax(scale * S) over the last axis; S fp32 [rows, cols], P bf16 [rows, cols]."""
+    rows, cols = S.shape
+    assert S.dtype == torch.float32 and P.dtype == torch.bfloat16 and P.shape == S.shape
+    check(_abi.load().vn_softmax_rows(ptr(S), S.stride(0), ptr(P), P.stride(0), rows, cols, float(scale), stream()),
+          "softmax_rows")
+
+
 def col2im_s2(dcol, dx, add=None):
     nb, H, W, Cc = dx.shape
     check(_abi.load().vn_col2im_s2(ptr(dcol), ptr(add), _pix_ld(add) if add is not None else 0, ptr(dx), _pix_ld(dx),
@@ -358,6 +383,22 @@ def launch_count_reset() -> None:
     _abi.load().vn_launch_count_reset()
 
 
+_PDL = True
+
+
 def set_pdl(enabled: bool) -> None:
-    """Programmatic dependent launch on/off (off only to time kernels in isolation)."""
+    """Programmatic dependent launch on/off (off to time kernels in isolation, or around a launch whose early reads
+    depend on its predecessor: gemm(b_dynamic=True))."""
+    global _PDL
+    _PDL = bool(enabled)
     _abi.load().vn_set_pdl(1 if enabled else 0)
+
+
+@contextlib.contextmanager
+def pdl_off():
+    prev = _PDL
+    set_pdl(False)
+    try:
+        yield
+    finally:
+        set_pdl(prev)

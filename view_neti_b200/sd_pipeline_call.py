@@ -6,10 +6,9 @@
 B200-native shape of the same loop: the unconditional and the conditional pass run as ONE batched UNet forward
 (batch 2n, the negative embedding bound to every layer of the first half, the per-timestep NeTI dict to the second
 half) replayed from a CUDA graph, followed by ONE fused kernel for the guidance combine + eta-0 DDIM update
-(vn_cfg_ddim_step).  Everything stays on the device; `callback` is honoured.  Text encoding of the negative prompt
-and VAE decoding are outside this path: the negative embedding comes from `pipeline.text_encoder`
-when the pipeline has one, else from `pipeline.negative_prompt_embeds`; `output_type="latent"` returns latents and
-other output types need `pipeline.decode_latents`.
+(vn_cfg_ddim_step).  Everything stays on the device; `callback` is honoured.  The negative embedding comes from `pipeline.text_encoder`
+when the pipeline has one, else from `pipeline.negative_prompt_embeds`; `output_type="latent"` returns latents, other
+output types go through `pipeline.decode_latents` (:115 - models/vae.py when the pipeline holds our AutoencoderKL).
 """
 from __future__ import annotations
 
@@ -44,6 +43,20 @@ class ViewNeTIPipeline:
             latents = torch.randn(shape, generator=generator, device=generator.device if generator is not None else "cpu",
                                   dtype=torch.float32).to(device)
         return latents.to(device=device, dtype=torch.float32) * self.scheduler.init_noise_sigma
+
+    def decode_latents(self, latents):
+        """diffusers StableDiffusionPipeline.decode_latents (reference sd_pipeline_call.py:115): numpy NHWC in [0, 1]."""
+        if self.vae is None:
+            raise VNError("decode_latents: the pipeline has no vae (use output_type='latent')")
+        from .models.vae import decode_latents
+        return decode_latents(self.vae, latents)
+
+    @staticmethod
+    def numpy_to_pil(images):
+        from PIL import Image
+        if images.ndim == 3:
+            images = images[None, ...]
+        return [Image.fromarray((im * 255).round().astype("uint8")) for im in images]
 
 
 def get_neg_prompt_input_ids(pipeline, negative_prompt: Optional[Union[str, List[str]]] = None):

@@ -1,6 +1,7 @@
 """Coach — the reference's training driver (reference training/coach.py:36-834) reduced to the part that IS the hot
 path, with the same step semantics and method names:
 
+    coach.py:165-169  latents = vae.encode(pixel_values).latent_dist.sample().detach() * scaling_factor   [models/vae.py]
     coach.py:172-183  noise, timesteps ~ U[0, T), noisy_latents = scheduler.add_noise(latents, noise, timesteps)
     coach.py:186-194  _hs = self.get_text_conditioning(...)            -> context dict (XTI protocol)
     coach.py:197-198  model_pred = self.unet(noisy_latents, timesteps, _hs).sample      [CUDA library]
@@ -28,9 +29,11 @@ from .dist import FlatGradAllReducer
 class Coach:
 
     def __init__(self, cfg, unet, conditioning: Callable[..., Dict], noise_scheduler: Optional[DDPMScheduler] = None,
-                 optimizer: Optional[torch.optim.Optimizer] = None, lr_scheduler=None, generator: Optional[torch.Generator] = None):
+                 optimizer: Optional[torch.optim.Optimizer] = None, lr_scheduler=None, generator: Optional[torch.Generator] = None,
+                 vae=None):
         self.cfg = cfg
         self.unet = unet
+        self.vae = vae
         self.conditioning = conditioning
         self.noise_scheduler = noise_scheduler or DDPMScheduler()
         params = list(conditioning.parameters()) if isinstance(conditioning, torch.nn.Module) else []
@@ -50,8 +53,19 @@ class Coach:
                                  input_ids_placeholder_object=input_ids_placeholder_object,
                                  input_ids_placeholder_view=input_ids_placeholder_view, device=device, original_ti=original_ti)
 
-    def train_step(self, latents: torch.Tensor, batch: Optional[Dict] = None) -> torch.Tensor:
+    def encode_images(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        """coach.py:165-169: images in [-1, 1] -> scaled latents, frozen VAE, no autograd history."""
+        if self.vae is None:
+            raise ValueError("Coach: batch carries pixel_values but no vae was given")
+        dist = self.vae.encode(pixel_values).latent_dist
+        return dist.sample(self.generator).detach() * self.vae.config.scaling_factor
+
+    def train_step(self, latents: Optional[torch.Tensor] = None, batch: Optional[Dict] = None) -> torch.Tensor:
+        """One optimisation step.  `latents` given: the step starts at coach.py:172 (pre-encoded data); otherwise
+        `batch["pixel_values"]` goes through the VAE first, as the reference does every step."""
         batch = batch or {}
+        if latents is None:
+            latents = self.encode_images(batch["pixel_values"])
         dev = latents.device
         noise = torch.randn(latents.shape, generator=self.generator, device=dev, dtype=latents.dtype)
         bsz = latents.shape[0]
@@ -80,11 +94,12 @@ class Coach:
         self.global_step += 1
         return loss.detach()
 
-    def train(self, latent_batches: Iterable[torch.Tensor], max_train_steps: Optional[int] = None):
+    def train(self, latent_batches: Iterable, max_train_steps: Optional[int] = None):
+        """Batches are latent tensors, or dicts as the reference's dataloader yields (`pixel_values`, `input_ids`, ...)."""
         max_steps = max_train_steps or getattr(getattr(self.cfg, "optim", SimpleNamespace()), "max_train_steps", None)
         losses = []
-        for latents in latent_batches:
-            losses.append(self.train_step(latents))
+        for b in latent_batches:
+            losses.append(self.train_step(batch=b) if isinstance(b, dict) else self.train_step(b))
             if max_steps is not None and self.global_step >= max_steps:
                 break
         return losses
