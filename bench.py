@@ -338,6 +338,22 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                          "what": "Coach.train_step: NeTI mappers + batched 16-layer CLIP-H conditioning (23-layer encoder on "
                                  "[16,77,1024]) + UNet fwd/bwd + mapper gradients + AdamW; synthetic prompt, seeded weights",
                          "trainable_params": sum(p.numel() for p in cond.parameters()), "loss": float(fl_loss)}
+            # the same step started from the image, as reference coach.py:165-169 does every step: VAE encode first
+            from view_neti_b200.models.vae import SD21_VAE, AutoencoderKL, init_state_dict as vae_init
+            coach.vae = AutoencoderKL(vae_init(SD21_VAE, 0), SD21_VAE, dev)
+            pb = dict(prompt)
+            pb["pixel_values"] = torch.rand(1, 3, 8 * L, 8 * L, device=dev) * 2 - 1
+            for _ in range(3):
+                coach.train_step(batch=pb)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(kf):
+                coach.train_step(batch=pb)
+            e1.record()
+            torch.cuda.synchronize()
+            px_ms = e0.elapsed_time(e1) / kf
+            full_step["from_pixel_values"] = {"value": 1e3 / px_ms, "unit": "images/s", "ms_per_step": px_ms,
+                                              "what": "the same step with vae.encode(pixel_values [1,3,%d,%d]) in front" % (8 * L, 8 * L)}
             del coach, cond
         except Exception as e:          # the headline metric above must survive a failure of the widened path
             full_step = {"error": f"{type(e).__name__}: {e}"[:300]}

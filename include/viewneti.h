@@ -176,6 +176,10 @@ int vn_im2col_s2_pad0(const void* x, int64_t ldx, void* col, int nb, int H, int 
 /* dgrad: dx[nb,H,W,C] = col2im(dcol) (+ add) */
 int vn_col2im_s2(const void* dcol, const void* add, int64_t ldadd, void* dx, int64_t lddx,
                  int nb, int H, int W, int C, vn_stream_t s);
+/* few-channel 3x3 / stride 1 / pad 1 conv as a GEMM (the VAE's conv_in layers, reference training/coach.py:167 and
+ * sd_pipeline_call.py:115 -> diffusers Encoder / Decoder.conv_in): x NCHW fp32 [nb,Ct,H,W] -> col bf16 [nb*H*W, ldc],
+ * k = tap*Ct + ct, zero for 9*Ct <= k < ldc; ldc % 64 == 0 */
+int vn_im2col_thin(const float* x, void* col, int64_t ldc, int nb, int Ct, int H, int W, vn_stream_t s);
 /* conv_in: NCHW fp32 latents [nb,Cin,H,W] -> NHWC bf16 [nb,H,W,Cout]; w fp32 [Cout,Cin,3,3] */
 int vn_conv_in_fwd(const float* x, const float* w, const float* bias, void* y, int64_t ldy,
                    int nb, int Cin, int H, int W, int Cout, vn_stream_t s);

@@ -23,6 +23,11 @@ coach = Coach(cfg=None, unet=unet, conditioning=cond, optimizer=torch.optim.Adam
               generator=torch.Generator(device=dev).manual_seed(1))
 batch = synthetic_prompt(1, dev)
 latents = torch.randn(1, 4, 64, 64, generator=g).to(dev)
+if os.environ.get("VAE"):       # start from the image: vae.encode(pixel_values) every step (reference coach.py:165-169)
+    from view_neti_b200.models.vae import SD21_VAE, AutoencoderKL, init_state_dict as vae_init
+    coach.vae = AutoencoderKL(vae_init(SD21_VAE, 0), SD21_VAE, dev)
+    batch["pixel_values"] = torch.rand(1, 3, 512, 512, generator=g).to(dev) * 2 - 1
+    latents = None
 losses = []
 for _ in range(4):
     losses.append(float(coach.train_step(latents, batch)))

@@ -61,8 +61,10 @@ def timed(fn, iters=10, warm=3):
 def main():
     cfg = SD21_VAE
     vae = AutoencoderKL(init_state_dict(cfg, 0), cfg, "cuda")
-    out = {"weights_MB": round(vae.engine.weight_bytes() / 2 ** 20, 1)}
-    for (nb, H, W) in [(1, 512, 512), (1, 512, 384), (2, 512, 512)]:
+    out = {"weights_MB": round(vae.engine.weight_bytes() / 2 ** 20, 1), "gn_fused_elems": vae.engine.FUSED_GN_ELEMS,
+           "thin_on_gemm": vae.engine.THIN_ON_GEMM}
+    shapes = [(1, 512, 512)] if os.environ.get("VAE_BENCH_QUICK") else [(1, 512, 512), (1, 512, 384), (2, 512, 512)]
+    for (nb, H, W) in shapes:
         img = torch.rand(nb, 3, H, W, device="cuda") * 2 - 1
         z = torch.randn(nb, 4, H // 8, W // 8, device="cuda")
         fe, fd = flops(cfg, H, W)
@@ -81,7 +83,7 @@ def main():
             "decode_launches": ld, "scratch_MB": round(vae.engine.scratch_bytes() / 2 ** 20, 1)}
     print(json.dumps(out))
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/vae_bench.json", "w") as f:
+    with open(os.environ.get("VAE_BENCH_OUT", "gpurun_out/vae_bench.json"), "w") as f:
         json.dump(out, f, indent=1)
 
 

@@ -100,6 +100,16 @@ def im2col_s2_pad0(x, col):
     _mark(col)
 
 
+def im2col_thin(x, col):
+    nb, Ct, H, W = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and col.dtype == BF
+    assert col.shape[0] == nb * H * W and col.shape[1] % 64 == 0 and col.shape[1] >= 9 * Ct
+    u = F.unfold(x, 3, padding=1).view(nb, Ct, 9, H * W).permute(0, 3, 2, 1).reshape(nb * H * W, 9 * Ct)
+    col.zero_()
+    col[:, : 9 * Ct] = u
+    _mark(col)
+
+
 def softmax_rows(S, P, scale):
     assert S.dtype == torch.float32 and P.dtype == BF and S.shape == P.shape and S.shape[1] % 4 == 0
     P.copy_(torch.softmax(S * scale, dim=-1))

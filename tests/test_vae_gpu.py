@@ -55,6 +55,33 @@ def test_im2col_s2_pad0_bit_exact(nb, H, W, C):
     assert torch.equal(col.float(), u)
 
 
+@pytest.mark.parametrize("nb,Ct,H,W", [(1, 3, 16, 16), (2, 4, 8, 24), (1, 3, 512, 512), (3, 7, 5, 9)])
+def test_im2col_thin_bit_exact(nb, Ct, H, W):
+    from view_neti_b200 import ops
+    x = torch.randn(nb, Ct, H, W, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    col = torch.full((nb * H * W, 64), 3.0, dtype=torch.bfloat16, device="cuda")
+    ops.im2col_thin(x, col)
+    u = F.unfold(x, 3, padding=1).view(nb, Ct, 9, H * W).permute(0, 3, 2, 1).reshape(nb * H * W, 9 * Ct)
+    assert torch.equal(col[:, : 9 * Ct], u.to(torch.bfloat16)) and float(col[:, 9 * Ct:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("nb,H,W,C,Ct", [(1, 64, 64, 512, 8), (1, 128, 128, 128, 3), (2, 24, 40, 64, 3)])
+def test_conv_to_few_channels_on_the_gemm(nb, H, W, C, Ct):
+    """conv_out of the VAE as the implicit 3x3 GEMM with N padded to 8 and an fp32 destination."""
+    from view_neti_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(nb, H, W, C, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(Ct, C, 3, 3, device="cuda", generator=g) / math.sqrt(9 * C)).to(torch.bfloat16)
+    b = torch.randn(8, device="cuda", generator=g)
+    wk = torch.zeros(8, 9 * C, dtype=torch.bfloat16, device="cuda")
+    wk[:Ct] = w.permute(0, 2, 3, 1).reshape(Ct, -1)
+    d = torch.full((nb, H, W, 8), 9.0, device="cuda")
+    ops.conv3x3(x, wk, d, bias=b, ws=ops.Workspace(8192, 8192, "cuda"), force_bn=64, force_split=1)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b[:Ct], padding=1).permute(0, 2, 3, 1)
+    assert rel(d[..., :Ct], ref) < 1e-5
+    assert rel(d[..., Ct:], b[Ct:].expand(nb, H, W, 8 - Ct)) < 1e-6 if Ct < 8 else True
+
+
 def test_gemm_with_computed_strided_operands():
     """The attention products of the VAE: A and B are column slices of one [hw, 2C] buffer written by the launch
     before, fp32 output; V^T straight out of a GEMM with the weight as the A operand."""

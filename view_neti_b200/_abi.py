@@ -94,6 +94,7 @@ SIGNATURES = {
     "vn_upsample2x_bwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _I, _I, _P]),
     "vn_im2col_s2": (C.c_int, [_P, _L, _P, _I, _I, _I, _I, _P]),
     "vn_im2col_s2_pad0": (C.c_int, [_P, _L, _P, _I, _I, _I, _I, _P]),
+    "vn_im2col_thin": (C.c_int, [_P, _P, _L, _I, _I, _I, _I, _P]),
     "vn_softmax_rows": (C.c_int, [_P, _L, _P, _L, _I, _I, _F, _P]),
     "vn_col2im_s2": (C.c_int, [_P, _P, _L, _P, _L, _I, _I, _I, _I, _P]),
     "vn_conv_in_fwd": (C.c_int, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),

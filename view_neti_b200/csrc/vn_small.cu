@@ -245,6 +245,38 @@ __global__ void __launch_bounds__(256) conv_wide_to_thin_kernel(const bf16* __re
   }
 }
 
+// im2col of a FEW-channel NCHW fp32 image for a 3x3 / stride 1 / pad 1 convolution on vn_gemm: col [nb*H*W, ldc] bf16,
+// k = tap*Ct + ct for k < 9*Ct, zero up to ldc (a multiple of 64: one or two k-blocks).  The VAE's conv_in layers
+// (3 -> 128 at the image resolution, 4 -> 512 at the latent resolution) become memory-bound GEMMs this way.
+__global__ void __launch_bounds__(256) im2col_thin_kernel(const float* __restrict__ x, bf16* __restrict__ col,
+                                                          long long ldc, int nb, int Ct, int H, int W) {
+  pdl_trigger();
+  pdl_wait();
+  const int vecs = (int)(ldc >> 3);
+  const int kmax = 9 * Ct;
+  const long long total = (long long)nb * H * W * vecs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vecs);
+    long long pix = i / vecs;
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = v * 8 + j;
+      a[j] = 0.f;
+      if (k < kmax) {
+        const int tap = k / Ct, ct = k - tap * Ct;
+        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) a[j] = __ldg(x + (((long long)b * Ct + ct) * H + hh) * W + ww);
+      }
+    }
+    *reinterpret_cast<uint4*>(col + pix * ldc + v * 8) = pack8(a);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // time embedding pieces
 // ---------------------------------------------------------------------------------------------
@@ -409,6 +441,14 @@ extern "C" int vn_col2im_s2(const void* dcol, const void* add, int64_t ldadd, vo
   const long long total = (long long)nb * H * W * (C / 8);
   VN_LAUNCH(col2im_s2_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)s, (const bf16*)dcol, (const bf16*)add, ldadd,
                                                                        (bf16*)dx, lddx, nb, H, W, Ho, Wo, C);
+  return 0;
+}
+
+extern "C" int vn_im2col_thin(const float* x, void* col, int64_t ldc, int nb, int Ct, int H, int W, vn_stream_t s) {
+  VN_CHECK(Ct >= 1 && ldc % 64 == 0 && ldc >= 9 * Ct, "im2col_thin: need ldc %% 64 == 0 and ldc >= 9*Ct (Ct=%d ldc=%lld)", Ct,
+           (long long)ldc);
+  const long long total = (long long)nb * H * W * (ldc / 8);
+  VN_LAUNCH(im2col_thin_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)s, x, (bf16*)col, (long long)ldc, nb, Ct, H, W);
   return 0;
 }
 

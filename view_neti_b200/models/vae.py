@@ -19,6 +19,7 @@ head_dim-64 attention kernels; it is three GEMMs around a row softmax (vn_softma
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from types import SimpleNamespace
 from typing import Dict, List, Optional, Tuple
@@ -140,8 +141,14 @@ class VAEEngine:
     """Weights in kernel layout + launch sequences.  Activations are [nb, H*W, C] bf16; scratch buffers are keyed by
     role and shape and reused along the chain (forward only, one stream, stream order keeps reuse safe)."""
 
-    # GroupNorm inputs up to this many elements take the one-launch register-resident form
-    FUSED_GN_ELEMS = 4 * 1024 * 1024
+    # GroupNorm inputs up to this many elements take the one-launch form; above it the two-kernel form.  Measured on
+    # B200 at 512 x 512: the one-launch form wins at every size of this network, even where a CTA's slab no longer
+    # fits in registers and is re-read from L2 (encode 2.01 -> 1.91 ms, decode 3.52 -> 3.32 ms), so the default is "always"
+    FUSED_GN_ELEMS = int(os.environ.get("VN_VAE_GN_FUSED_ELEMS", 1 << 40))
+    # the four few-channel edge convolutions (3 -> C, C -> 8, 4 -> C, C -> 3) on vn_gemm: conv_in as im2col_thin + GEMM
+    # with K padded to 64, conv_out as the implicit 3x3 GEMM with N padded to 8.  False: the CUDA-core thin-conv
+    # kernels of the UNet (fp32 weights; 683 us for the decoder's 128 -> 3 at 512 x 512 against ~50 us on tensor cores)
+    THIN_ON_GEMM = os.environ.get("VN_VAE_THIN_GEMM", "1") != "0"
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: VAEConfig = SD21_VAE, device="cuda"):
         self.cfg = cfg
@@ -204,6 +211,22 @@ class VAEEngine:
         self.dec_in = (f32("decoder.conv_in.weight"), f32("decoder.conv_in.bias"))
         self.dec_norm = (f32("decoder.conv_norm_out.weight"), f32("decoder.conv_norm_out.bias"))
         self.dec_out = (f32("decoder.conv_out.weight"), f32("decoder.conv_out.bias"))
+        # GEMM forms of the edge convolutions
+        def thin_in(w, b):          # [Cout, Ct, 3, 3] -> [Cout, Kpad], k = tap*Ct + ct (vn_im2col_thin)
+            k = 9 * w.shape[1]
+            wk = torch.zeros(w.shape[0], (k + 63) // 64 * 64, dtype=BF, device=dev)
+            wk[:, :k] = w.permute(0, 2, 3, 1).reshape(w.shape[0], k).to(BF)
+            return wk, b
+
+        def thin_out(w, b):         # [Ct, C, 3, 3] -> [8, 9*C] (rows >= Ct zero), k = tap*C + c (implicit 3x3 GEMM)
+            wk = torch.zeros(8, 9 * w.shape[1], dtype=BF, device=dev)
+            wk[: w.shape[0]] = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(BF)
+            bk = torch.zeros(8, dtype=F32, device=dev)
+            bk[: w.shape[0]] = b
+            return wk, bk
+
+        self.enc_in_g, self.dec_in_g = thin_in(*self.enc_in), thin_in(*self.dec_in)
+        self.enc_out_g, self.dec_out_g = thin_out(*self.enc_out), thin_out(*self.dec_out)
 
     def weight_bytes(self) -> int:
         seen, n = set(), 0
@@ -241,6 +264,27 @@ class VAEEngine:
         fused = nb * hw * C <= self.FUSED_GN_ELEMS
         ops.groupnorm_fwd(x, gb[0], gb[1], self.cfg.norm_eps, silu, y, nb, hw, self.cfg.norm_num_groups,
                           self._stats[i, :nb], self._parts[i] if fused else None)
+        return y
+
+    def _conv_in(self, x_in: torch.Tensor, w32, wg, out: torch.Tensor, H: int, W: int) -> None:
+        """x_in NCHW fp32 [nb,Ct,H,W] -> out [nb, H*W, C] bf16."""
+        nb, C = out.shape[0], out.shape[-1]
+        if self.THIN_ON_GEMM:
+            col = self._buf("thin.col", (nb * H * W, wg[0].shape[1]))
+            ops.im2col_thin(x_in, col)
+            ops.gemm(col, wg[0], out.view(nb * H * W, C), bias=wg[1], ws=self.ws)
+        else:
+            ops.conv_in_fwd(x_in, w32[0], w32[1], out.view(nb, H, W, C))
+
+    def _conv_out(self, a: torch.Tensor, w32, wg, H: int, W: int) -> torch.Tensor:
+        """a [nb, H*W, C] bf16 -> fresh NCHW fp32 [nb, Ct, H, W]."""
+        nb, C, Ct = a.shape[0], a.shape[-1], w32[0].shape[0]
+        if self.THIN_ON_GEMM:
+            d = self._buf("thin.out", (nb, H, W, 8), F32)
+            ops.conv3x3(a.view(nb, H, W, C), wg[0], d, bias=wg[1], ws=self.ws, force_bn=64, force_split=1)
+            return d[..., :Ct].permute(0, 3, 1, 2).contiguous()
+        y = torch.empty(nb, Ct, H, W, dtype=F32, device=self.dev)
+        ops.conv_out_fwd(a.view(nb, H, W, C), w32[0], w32[1], y)
         return y
 
     def _resnet(self, name: str, x: torch.Tensor, H: int, W: int, out_role: str) -> torch.Tensor:
@@ -304,7 +348,7 @@ class VAEEngine:
         self._begin(nb)
         ch = cfg.block_out_channels
         x = self._buf("x0", (nb, H * W, ch[0]))
-        ops.conv_in_fwd(x_in, self.enc_in[0], self.enc_in[1], x.view(nb, H, W, ch[0]))
+        self._conv_in(x_in, self.enc_in, self.enc_in_g, x, H, W)
         flip = 1
         for i in range(len(ch)):
             for j in range(cfg.layers_per_block):
@@ -321,8 +365,7 @@ class VAEEngine:
                 H, W = Ho, Wo
         x = self._mid("encoder.mid_block", x, H, W)
         a = self._gn(x, self.enc_norm, True)
-        m = torch.empty(nb, 2 * cfg.latent_channels, H, W, dtype=F32, device=self.dev)
-        ops.conv_out_fwd(a.view(nb, H, W, ch[-1]), self.enc_out[0], self.enc_out[1], m)
+        m = self._conv_out(a, self.enc_out, self.enc_out_g, H, W)
         mean, logvar = m.chunk(2, dim=1)
         return mean, logvar.clamp(-30.0, 20.0)
 
@@ -340,7 +383,7 @@ class VAEEngine:
         ch = cfg.block_out_channels
         rev = tuple(reversed(ch))
         x = self._buf("x0", (nb, H * W, rev[0]))
-        ops.conv_in_fwd(z, self.dec_in[0], self.dec_in[1], x.view(nb, H, W, rev[0]))
+        self._conv_in(z, self.dec_in, self.dec_in_g, x, H, W)
         x = self._mid("decoder.mid_block", x, H, W)
         flip = 0
         for i, cout in enumerate(rev):
@@ -356,9 +399,7 @@ class VAEEngine:
                 flip ^= 1
                 ops.conv3x3(up.view(nb, H, W, cout), wf, x.view(nb, H, W, cout), bias=bias, ws=self.ws)
         a = self._gn(x, self.dec_norm, True)
-        img = torch.empty(nb, cfg.out_channels, H, W, dtype=F32, device=self.dev)
-        ops.conv_out_fwd(a.view(nb, H, W, ch[0]), self.dec_out[0], self.dec_out[1], img)
-        return img
+        return self._conv_out(a, self.dec_out, self.dec_out_g, H, W)
 
     def scratch_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self._bufs.values())

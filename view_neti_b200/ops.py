@@ -289,6 +289,13 @@ def im2col_s2_pad0(x, col):
     check(_abi.load().vn_im2col_s2_pad0(ptr(x), _pix_ld(x), ptr(col), nb, H, W, Cc, stream()), "im2col_s2_pad0")
 
 
+def im2col_thin(x, col):
+    """x NCHW fp32 [nb,Ct,H,W] -> col bf16 [nb*H*W, Kpad] (k = tap*Ct + ct, zero-padded to Kpad % 64 == 0)."""
+    nb, Ct, H, W = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and col.dtype == BF16 and col.shape[0] == nb * H * W
+    check(_abi.load().vn_im2col_thin(ptr(x), ptr(col), col.stride(0), nb, Ct, H, W, stream()), "im2col_thin")
+
+
 def softmax_rows(S, P, scale):
     """P = softmax(scale * S) over the last axis; S fp32 [rows, cols], P bf16 [rows, cols]."""
     rows, cols = S.shape
