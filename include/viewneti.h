@@ -208,6 +208,12 @@ int vn_mse_loss(const float* pred, const float* target, int64_t n, float loss_sc
  * latents fp32 [n] updated in place.  acp_t / acp_prev = alphas_cumprod at t / t_prev; vpred: 0 eps, 1 v. */
 int vn_cfg_ddim_step(float* latents, const float* eps_uncond, const float* eps_cond, int64_t n,
                      float guidance, float acp_t, float acp_prev, int vpred, vn_stream_t s);
+/* the same fused step for DPM-Solver++(2M), the scheduler the reference's inference scripts install (reference
+ * training/validate.py:568, training/inference_dtu.py:304): m = u + g (c - u); x0 = p x + q m;
+ * latents = A x + B0 x0 + B1 x0_prev;  x0_prev = x0.  (p, q, A, B0, B1) per step from the host scheduler; B1 = 0 on
+ * first-order steps, when x0_prev is not read */
+int vn_cfg_dpmpp_step(float* latents, const float* eps_uncond, const float* eps_cond, float* x0_prev, int64_t n,
+                      float guidance, float p, float q, float A, float B0, float B1, vn_stream_t s);
 /* ------------------------------------------------------------------------------------------------
  * CLIP text transformer pieces (the batched conditioning path: reference
  * models/neti_clip_text_encoder.py:57-225 runs transformers' CLIPEncoder once per UNet layer; here the 16 passes are one batch).

@@ -80,6 +80,66 @@ def test_schedulers_match_oracle():
     assert np.allclose(d.get_velocity(x, e, t).numpy(), O.get_velocity(x.double().numpy(), e.double().numpy(), t.numpy()), atol=1e-5)
 
 
+def test_dpm_solver_pp_scheduler():
+    """DPM-Solver++(2M) (reference training/validate.py:568, inference_dtu.py:304).  Diffusers is absent, so the oracle
+    is pinned by identities of the published algorithm, then the host scheduler (and the five scalars the fused
+    kernel receives) is held to the oracle."""
+    import numpy as np
+    from oracle import schedulers as O
+    from view_neti_b200.schedulers import DDIMScheduler, DPMSolverMultistepScheduler
+    assert O.dpmpp_timesteps(50).tolist()[:3] == [999, 979, 959] and O.dpmpp_timesteps(50)[-1] == 20
+    assert O.dpmpp_timesteps(30)[-1] == 33 and len(O.dpmpp_timesteps(30)) == 30
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 4, 8, 8, generator=g).double().numpy()
+    outs = [torch.randn(1, 4, 8, 8, generator=g).double().numpy() for _ in range(50)]
+    acp = O.alphas_cumprod()
+    for pt in ("epsilon", "v_prediction"):
+        # identity 1: a single first-order DPM-Solver++ step is the DDIM step between the same two timesteps
+        ts = O.dpmpp_timesteps(10)
+        one = O.dpmpp_2m_sample(lambda x_, t, i: outs[i], x, 1, pt)            # one step: t = 999 -> 0
+        a_t, a_p = acp[999], acp[0]
+        if pt == "epsilon":
+            x0, eps = (x - np.sqrt(1 - a_t) * outs[0]) / np.sqrt(a_t), outs[0]
+        else:
+            x0, eps = np.sqrt(a_t) * x - np.sqrt(1 - a_t) * outs[0], np.sqrt(a_t) * outs[0] + np.sqrt(1 - a_t) * x
+        assert np.allclose(one, np.sqrt(a_p) * x0 + np.sqrt(1 - a_p) * eps, rtol=1e-10, atol=1e-12)
+        # identity 2: with a constant DATA prediction the second-order correction vanishes and every step moves the
+        # sample along the straight DDIM line towards that x0: x_t = alpha_t x0 + sigma_t/sigma_s (x_s - alpha_s x0)
+        target = outs[7]
+
+        def model_const_x0(x_, t, i, pt=pt):
+            a, s = np.sqrt(acp[t]), np.sqrt(1 - acp[t])
+            return (x_ - a * target) / s if pt == "epsilon" else (a * x_ - target) / s
+
+        got = O.dpmpp_2m_sample(model_const_x0, x, 20, pt)
+        a0, s0 = np.sqrt(acp[999]), np.sqrt(1 - acp[999])
+        af, sf = np.sqrt(acp[0]), np.sqrt(1 - acp[0])
+        assert np.allclose(got, af * target + sf / s0 * (x - a0 * target), rtol=1e-9, atol=1e-10)
+        # the host scheduler and its kernel coefficients against the oracle loop, orders 2M with and without the
+        # first-order final step (N < 15)
+        for steps in (50, 30, 12, 2):
+            sch = DPMSolverMultistepScheduler.from_config(DDIMScheduler(pt).config)
+            assert sch.config.prediction_type == pt and sch.config.solver_order == 2
+            sch.set_timesteps(steps)
+            assert sch.timesteps.tolist() == O.dpmpp_timesteps(steps).tolist()
+            xs = torch.from_numpy(x)
+            xk, x0p = x.copy(), np.zeros_like(x)
+            for i, t in enumerate(sch.timesteps):
+                xs = sch.step(torch.from_numpy(outs[i]), t, xs).prev_sample
+                p_, q_, A, B0, B1 = sch.kernel_coefficients(i)
+                x0k = p_ * xk + q_ * outs[i]
+                xk, x0p = A * xk + B0 * x0k + B1 * x0p, x0k
+                if i == 0 or (i == steps - 1 and steps < 15):
+                    assert B1 == 0.0
+            ref = O.dpmpp_2m_sample(lambda x_, t, i: outs[i], x, steps, pt)
+            # the host table of alphas_cumprod is float32 (as diffusers builds it), the oracle's float64
+            assert np.allclose(xs.numpy(), ref, rtol=2e-5, atol=2e-5) and np.allclose(xk, xs.numpy(), rtol=1e-12, atol=1e-12)
+    sch = DPMSolverMultistepScheduler()
+    sch.set_timesteps(5)
+    with pytest.raises(ValueError):
+        sch.step(torch.zeros(1), 5, torch.zeros(1))
+
+
 def _worker(rank, world, port, q):
     import torch.distributed as dist
     from view_neti_b200.training.dist import FlatGradAllReducer

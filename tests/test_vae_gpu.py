@@ -3,7 +3,9 @@ fp32 CPU oracle (oracle/vae.py), through the drop-in AutoencoderKL surface and t
 
 Tolerance: activations are stored in bf16 between kernels (fp32 accumulation inside), which puts ~1.1e-2 relative L2 on
 the outputs (measured with the CPU emulation of the same launch sequence, tests/test_vae_cpu.py); the bar is 2.5e-2.
-The two data-movement kernels (im2col, softmax rounding aside) are checked bit-exactly / to bf16 rounding."""
+The two data-movement kernels (im2col, softmax rounding aside) are checked bit-exactly / to bf16 rounding.
+Also here: the rest of the image-side tail of inference - the denoise loop under DPM-Solver++(2M), the scheduler the
+reference's inference scripts install, and the pipeline's decode to numpy / PIL."""
 import math
 
 import pytest
@@ -242,3 +244,48 @@ def test_sd_pipeline_call_decodes_through_the_vae():
     from view_neti_b200._abi import VNError
     with pytest.raises(VNError):
         sd_pipeline_call(bare, embeds, output_type="np", **kw)
+
+
+@pytest.mark.parametrize("steps,pt", [(6, "v_prediction"), (16, "epsilon")])
+def test_sd_pipeline_call_with_dpm_solver_matches_oracle_loop(steps, pt):
+    """sd_pipeline_call.py:71-101 under the scheduler the reference's inference scripts install (validate.py:568,
+    inference_dtu.py:304): batched CFG + fused DPM-Solver++(2M) step against the oracle's two-pass loop; 6 steps end with
+    the first-order final step (N < 15), 16 steps do not."""
+    from oracle import schedulers as O
+    from oracle.unet_sd21 import UNetOracle
+    from view_neti_b200.schedulers import DDIMScheduler, DPMSolverMultistepScheduler
+    from view_neti_b200.sd21 import TINY, init_state_dict
+    from view_neti_b200.sd_pipeline_call import ViewNeTIPipeline, sd_pipeline_call
+    from view_neti_b200.unet import UNet2DConditionModel
+    gs = 5.0
+    g = torch.Generator().manual_seed(21)
+    x0 = torch.randn(1, 4, 16, 16, generator=g)
+    neg = torch.randn(1, 77, TINY.cross_attention_dim, generator=g)
+    embeds = []
+    for _ in range(steps):
+        d = {"this_idx": 0}
+        for i in range(16):
+            d[f"CONTEXT_TENSOR_{i}"] = torch.randn(1, 77, TINY.cross_attention_dim, generator=g)
+            d[f"CONTEXT_TENSOR_BYPASS_{i}"] = torch.randn(1, 77, TINY.cross_attention_dim, generator=g)
+        embeds.append(d)
+    sd = init_state_dict(TINY, 0)
+    oracle = UNetOracle(TINY)
+    oracle.load_state_dict(sd)
+
+    def model(x, t, i):
+        xt = torch.from_numpy(x).float()
+        with torch.no_grad():
+            u = oracle(xt, t, neg).sample
+            c = oracle(xt, t, dict(embeds[i])).sample
+        return (u + gs * (c - u)).double().numpy()
+
+    want = O.dpmpp_2m_sample(model, x0.double().numpy(), steps, pt)
+    unet = UNet2DConditionModel(sd, TINY, "cuda")
+    pipe = ViewNeTIPipeline(unet, DPMSolverMultistepScheduler.from_config(DDIMScheduler(pt).config),
+                            negative_prompt_embeds=neg.cuda())
+    cuda_embeds = [{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in d.items()} for d in embeds]
+    seen = []
+    out = sd_pipeline_call(pipe, cuda_embeds, height=128, width=128, num_inference_steps=steps, guidance_scale=gs,
+                           latents=x0.cuda(), output_type="latent", callback=lambda i, t, l: seen.append(t))
+    assert seen == O.dpmpp_timesteps(steps).tolist()
+    assert rel(out.images, torch.from_numpy(want)) < 5e-2          # CFG amplifies the bf16 error of the UNet output

@@ -106,6 +106,7 @@ SIGNATURES = {
     "vn_cast_bf16_f32": (C.c_int, [_P, _P, _L, _P]),
     "vn_copy2d": (C.c_int, [_P, _L, _P, _L, _P, _L, _L, _I, _P]),
     "vn_mse_loss": (C.c_int, [_P, _P, _L, _F, _P, _P, _P]),
+    "vn_cfg_dpmpp_step": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P]),
     "vn_cfg_ddim_step": (C.c_int, [_P, _P, _P, _L, _F, _F, _F, _I, _P]),
     "vn_memset_zero": (C.c_int, [_P, _Z, _P]),
     "vn_memset": (C.c_int, [_P, _I, _Z, _P]),

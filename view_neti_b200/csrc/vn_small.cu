@@ -388,6 +388,27 @@ __global__ void __launch_bounds__(256) cfg_ddim_kernel(float* __restrict__ laten
   }
 }
 
+// sd_pipeline_call.py:98 + :101 with the DPM-Solver++(2M) scheduler the reference's inference scripts install: every
+// update is linear - x0 = p x + q m (m = guided model output), x_prev = A x + B0 x0 + B1 x0_prev - so one kernel does
+// guidance, conversion and update and keeps x0 for the next step.  Coefficients come from the host scheduler.
+__global__ void __launch_bounds__(256) cfg_dpmpp_kernel(float* __restrict__ latents, const float* __restrict__ eu,
+                                                        const float* __restrict__ ec, float* __restrict__ x0_prev,
+                                                        long long n, float guidance, float p, float q, float A,
+                                                        float B0, float B1) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float u = eu[i];
+    const float m = u + guidance * (ec[i] - u);
+    const float x = latents[i];
+    const float x0 = p * x + q * m;
+    float o = A * x + B0 * x0;
+    if (B1 != 0.f) o += B1 * x0_prev[i];          // first step: the slot holds nothing yet
+    latents[i] = o;
+    x0_prev[i] = x0;
+  }
+}
+
 template <typename K>
 int thin_smem_config(K kernel, size_t smem) {
   VN_CHECK(smem <= 200 * 1024, "edge conv: weights (%zu B) do not fit in shared memory", smem);
@@ -513,6 +534,15 @@ extern "C" int vn_mse_loss(const float* pred, const float* target, int64_t n, fl
                            float* dpred, vn_stream_t s) {
   VN_CHECK(n > 0, "mse: empty input");
   VN_LAUNCH(mse_kernel, 1, 1024, 0, (cudaStream_t)s, pred, target, n, loss_scale, loss, dpred);
+  return 0;
+}
+
+extern "C" int vn_cfg_dpmpp_step(float* latents, const float* eps_uncond, const float* eps_cond, float* x0_prev,
+                                 int64_t n, float guidance, float p, float q, float A, float B0, float B1,
+                                 vn_stream_t s) {
+  VN_CHECK(n > 0 && latents && eps_uncond && eps_cond && x0_prev, "cfg_dpmpp_step: bad arguments");
+  VN_LAUNCH(cfg_dpmpp_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)s, latents, eps_uncond, eps_cond, x0_prev, n, guidance,
+                                                                   p, q, A, B0, B1);
   return 0;
 }
 

@@ -356,6 +356,13 @@ def mse_loss(pred, target, loss, dpred=None, loss_scale=1.0):
           "mse")
 
 
+def cfg_dpmpp_step(latents, eps_u, eps_c, x0_prev, guidance, p, q, A, B0, B1):
+    """CFG combine + DPM-Solver++(2M) update in place; x0_prev carries the data prediction to the next step."""
+    assert latents.dtype == torch.float32 and x0_prev.dtype == torch.float32 and x0_prev.numel() == latents.numel()
+    check(_abi.load().vn_cfg_dpmpp_step(ptr(latents), ptr(eps_u), ptr(eps_c), ptr(x0_prev), latents.numel(), guidance,
+                                        p, q, A, B0, B1, stream()), "cfg_dpmpp_step")
+
+
 def cfg_ddim_step(latents, eps_u, eps_c, guidance, acp_t, acp_prev, vpred):
     check(_abi.load().vn_cfg_ddim_step(ptr(latents), ptr(eps_u), ptr(eps_c), latents.numel(), guidance, acp_t, acp_prev,
                                        int(vpred), stream()), "cfg_ddim")

@@ -5,8 +5,9 @@
 
 B200-native shape of the same loop: the unconditional and the conditional pass run as ONE batched UNet forward
 (batch 2n, the negative embedding bound to every layer of the first half, the per-timestep NeTI dict to the second
-half) replayed from a CUDA graph, followed by ONE fused kernel for the guidance combine + eta-0 DDIM update
-(vn_cfg_ddim_step).  Everything stays on the device; `callback` is honoured.  The negative embedding comes from `pipeline.text_encoder`
+half) replayed from a CUDA graph, followed by ONE fused kernel for the guidance combine + sampler update: DPM-Solver++(2M),
+which the reference's inference scripts install on the pipeline (validate.py:568, inference_dtu.py:304; vn_cfg_dpmpp_step),
+or eta-0 DDIM (vn_cfg_ddim_step).  Everything stays on the device; `callback` is honoured.  The negative embedding comes from `pipeline.text_encoder`
 when the pipeline has one, else from `pipeline.negative_prompt_embeds`; `output_type="latent"` returns latents, other
 output types go through `pipeline.decode_latents` (:115 - models/vae.py when the pipeline holds our AutoencoderKL).
 """
@@ -19,7 +20,7 @@ import torch
 
 from . import ops
 from ._abi import VNError
-from .schedulers import DDIMScheduler
+from .schedulers import DDIMScheduler, DPMSolverMultistepScheduler
 
 
 class StableDiffusionPipelineOutput(SimpleNamespace):
@@ -100,8 +101,10 @@ def sd_pipeline_call(pipeline, prompt_embeds, height: Optional[int] = None, widt
     if guidance_scale <= 1.0:
         raise VNError("guidance_scale <= 1 leaves noise_pred undefined in the reference loop (sd_pipeline_call.py:97-101)")
     sched = pipeline.scheduler
-    if not isinstance(sched, DDIMScheduler) or eta != 0.0:
-        raise VNError("the fused denoise loop implements the eta = 0 DDIM update; pass a view_neti_b200 DDIMScheduler")
+    dpm = isinstance(sched, DPMSolverMultistepScheduler)
+    if not (dpm or isinstance(sched, DDIMScheduler)) or (eta != 0.0 and not dpm):      # diffusers' DPM-Solver ignores eta
+        raise VNError("the fused denoise loop implements DPM-Solver++(2M) and the eta = 0 DDIM update; pass a "
+                      "view_neti_b200 DPMSolverMultistepScheduler or DDIMScheduler")
     sched.set_timesteps(num_inference_steps, device="cpu")
     timesteps = [int(t) for t in sched.timesteps]
     if isinstance(prompt_embeds, list) and len(prompt_embeds) < len(timesteps):
@@ -113,6 +116,7 @@ def sd_pipeline_call(pipeline, prompt_embeds, height: Optional[int] = None, widt
     nk, nv = _layer_contexts(unet, negative_prompt_embeds, n)
     vpred = 0 if sched.config.prediction_type == "epsilon" else 1
     tbuf = torch.empty(2 * n, dtype=torch.int64, device=device)
+    x0_prev = torch.zeros_like(latents) if dpm else None          # DPM-Solver++ carries one data prediction
     for i, t in enumerate(timesteps):
         embed = prompt_embeds[i] if isinstance(prompt_embeds, list) else prompt_embeds
         ck, cv = _layer_contexts(unet, embed, n)
@@ -124,8 +128,11 @@ def sd_pipeline_call(pipeline, prompt_embeds, height: Optional[int] = None, widt
         plan.timesteps.copy_(tbuf.fill_(t))
         plan.run_forward()
         unet._generation += 1
-        a_t, a_prev = sched.coefficients(t)
-        ops.cfg_ddim_step(latents, plan.eps[:n], plan.eps[n:], guidance_scale, a_t, a_prev, vpred)
+        if dpm:
+            ops.cfg_dpmpp_step(latents, plan.eps[:n], plan.eps[n:], x0_prev, guidance_scale, *sched.kernel_coefficients(i))
+        else:
+            a_t, a_prev = sched.coefficients(t)
+            ops.cfg_ddim_step(latents, plan.eps[:n], plan.eps[n:], guidance_scale, a_t, a_prev, vpred)
         if callback is not None and i % callback_steps == 0:
             callback(i, t, latents)
     has_nsfw_concept = False
