@@ -99,6 +99,24 @@ def test_vae_host_logic_through_emulated_kernels(monkeypatch, nb, size):
     assert got.shape == want.shape == (nb, size, size, 3) and abs(got - want).max() < 3e-2
 
 
+def test_vae_scratch_is_bounded_across_shapes(monkeypatch):
+    cfg = TINY_VAE
+    monkeypatch.setattr(vmod, "ops", emu)
+    monkeypatch.setattr(vmod, "_require_cuda", lambda dev: None)
+    emu.reset()
+    eng = vmod.VAEEngine(init_state_dict(cfg, 0), cfg, device="cpu")
+    sizes = []
+    for k in range(1, 9):
+        eng.encode_moments(torch.zeros(1, 3, 64, 64 * k))
+        sizes.append(eng.scratch_bytes())
+    assert list(eng._pools) == [("encode", 1, 64, 64 * k) for k in range(5, 9)]      # the four most recent signatures
+    assert sizes[3] < sizes[7] < sizes[3] * 3              # grows with the image size, not with the number of shapes seen
+    first = eng.encode_moments(torch.zeros(1, 3, 64, 512))[0]          # most recent signature: same buffers again
+    n = eng.scratch_bytes()
+    eng.encode_moments(torch.zeros(1, 3, 64, 512))
+    assert eng.scratch_bytes() == n and first.shape == (1, 4, 8, 64)
+
+
 def test_vae_engine_refuses_cpu():
     from view_neti_b200._abi import VNError
     with pytest.raises(VNError):

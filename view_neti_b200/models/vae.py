@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import math
 import os
+from collections import OrderedDict
 from dataclasses import dataclass
 from types import SimpleNamespace
 from typing import Dict, List, Optional, Tuple
@@ -155,6 +156,7 @@ class VAEEngine:
         self.dev = torch.device(device)
         _require_cuda(self.dev)
         self.ws = ops.Workspace(8192, 8192, self.dev)
+        self._pools: "OrderedDict[tuple, Dict[tuple, torch.Tensor]]" = OrderedDict()   # call signature -> scratch
         self._bufs: Dict[tuple, torch.Tensor] = {}
         self._prep(state_dict)
         n_gn = 2 * len(self.res) + 4
@@ -248,9 +250,15 @@ class VAEEngine:
             t = self._bufs[key] = torch.empty(tuple(shape), dtype=dtype, device=self.dev)
         return t
 
-    def _begin(self, nb: int) -> None:
+    MAX_POOLS = 4          # scratch is kept for the last few (map, batch, height, width) signatures only
+
+    def _begin(self, nb: int, sig: tuple = ()) -> None:
         if nb > self._stats.shape[1]:
             raise ops._abi.VNError(f"VAEEngine: batch {nb} > {self._stats.shape[1]}")
+        pool = self._pools.pop(sig, None)
+        self._pools[sig] = self._bufs = pool if pool is not None else {}
+        while len(self._pools) > self.MAX_POOLS:       # stream-ordered allocator: freeing under in-flight kernels is safe
+            self._pools.popitem(last=False)
         self._stats.zero_()
         ops.memset(self._parts, 0xFF)
         self._gn_i = 0
@@ -345,7 +353,7 @@ class VAEEngine:
         if cin != cfg.in_channels or H % cfg.downscale or W % cfg.downscale:
             raise ops._abi.VNError(f"VAE encode: bad input shape {tuple(pixel_values.shape)}")
         x_in = pixel_values.detach().to(device=self.dev, dtype=F32).contiguous()
-        self._begin(nb)
+        self._begin(nb, ("encode", nb, H, W))
         ch = cfg.block_out_channels
         x = self._buf("x0", (nb, H * W, ch[0]))
         self._conv_in(x_in, self.enc_in, self.enc_in_g, x, H, W)
@@ -379,7 +387,7 @@ class VAEEngine:
         z = z.detach().to(device=self.dev, dtype=F32)
         # post_quant_conv: a 4 x 4 channel mix of 4 h w numbers (see _prep for why it is not folded into conv_in)
         z = (torch.einsum("ab,nbhw->nahw", self.post_quant[0], z) + self.post_quant[1].view(1, -1, 1, 1)).contiguous()
-        self._begin(nb)
+        self._begin(nb, ("decode", nb, H, W))
         ch = cfg.block_out_channels
         rev = tuple(reversed(ch))
         x = self._buf("x0", (nb, H * W, rev[0]))
@@ -402,7 +410,7 @@ class VAEEngine:
         return self._conv_out(a, self.dec_out, self.dec_out_g, H, W)
 
     def scratch_bytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in self._bufs.values())
+        return sum(t.numel() * t.element_size() for pool in self._pools.values() for t in pool.values())
 
 
 # ---- drop-in surface ---------------------------------------------------------------------------------
