@@ -117,6 +117,44 @@ def test_vae_scratch_is_bounded_across_shapes(monkeypatch):
     assert eng.scratch_bytes() == n and first.shape == (1, 4, 8, 64)
 
 
+def test_vae_from_pretrained_and_key_layouts(monkeypatch, tmp_path):
+    from safetensors.torch import save_file
+    from view_neti_b200._abi import VNError
+    cfg = TINY_VAE
+    monkeypatch.setattr(vmod, "ops", emu)
+    monkeypatch.setattr(vmod, "_require_cuda", lambda dev: None)
+    emu.reset()
+    sd = init_state_dict(cfg, 5)
+    img = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(0)) * 2 - 1
+    want = vmod.AutoencoderKL(sd, cfg, "cpu").encode(img).latent_dist.mean
+    # diffusers >= 0.18 attention names and linear-shaped (squeezed) 1x1 weights are accepted, old-style .bin too
+    new = {}
+    for k, v in sd.items():
+        for old, nk in ((".query.", ".to_q."), (".key.", ".to_k."), (".value.", ".to_v."), (".proj_attn.", ".to_out.0.")):
+            k = k.replace(old, nk)
+        new[k] = (v.flatten(1) if k.endswith(("conv_shortcut.weight", "quant_conv.weight")) else v).contiguous()
+    (tmp_path / "a" / "vae").mkdir(parents=True)
+    save_file(new, str(tmp_path / "a" / "vae" / "diffusion_pytorch_model.safetensors"))
+    emu.reset()          # the emulator tracks written buffers by address; engines of this test come and go
+    got = vmod.AutoencoderKL.from_pretrained(str(tmp_path / "a"), subfolder="vae", revision=None, device="cpu", cfg=cfg)
+    assert torch.equal(got.encode(img).latent_dist.mean, want)
+    (tmp_path / "b").mkdir()
+    torch.save(sd, str(tmp_path / "b" / "diffusion_pytorch_model.bin"))
+    emu.reset()
+    got = vmod.AutoencoderKL.from_pretrained(str(tmp_path / "b"), device="cpu", cfg=cfg)
+    assert torch.equal(got.encode(img).latent_dist.mean, want)
+    with pytest.raises(FileNotFoundError):
+        vmod.AutoencoderKL.from_pretrained(str(tmp_path / "none"), subfolder="vae", device="cpu", cfg=cfg)
+    broken = dict(sd)
+    broken.pop("quant_conv.bias")
+    with pytest.raises(VNError, match="missing"):
+        vmod.AutoencoderKL(broken, cfg, "cpu")
+    broken = dict(sd)
+    broken["encoder.conv_in.weight"] = torch.zeros(64, 4, 3, 3)
+    with pytest.raises(VNError, match="shape mismatch"):
+        vmod.AutoencoderKL(broken, cfg, "cpu")
+
+
 def test_vae_engine_refuses_cpu():
     from view_neti_b200._abi import VNError
     with pytest.raises(VNError):

@@ -128,6 +128,33 @@ def init_state_dict(cfg: VAEConfig = SD21_VAE, seed: int = 0) -> Dict[str, torch
     return sd
 
 
+_ATTN_RENAMES = ((".to_q.", ".query."), (".to_k.", ".key."), (".to_v.", ".value."), (".to_out.0.", ".proj_attn."))
+
+
+def normalise_keys(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Checkpoints saved by diffusers >= 0.18 name the mid-block attention `to_q / to_k / to_v / to_out.0`; the
+    version range the reference runs on and the SD-2.1 hub files use `query / key / value / proj_attn`.
+    Both load; missing or unexpected keys are an error."""
+    out = {}
+    for k, v in sd.items():
+        if ".attentions." in k:
+            for new, old in _ATTN_RENAMES:
+                k = k.replace(new, old)
+        out[k] = v
+    return out
+
+
+def check_state_dict(sd: Dict[str, torch.Tensor], cfg: VAEConfig) -> None:
+    want = {n: s for n, s, _ in param_table(cfg)}
+    missing = sorted(set(want) - set(sd))
+    extra = sorted(set(sd) - set(want))
+    bad = [k for k in want if k in sd and tuple(sd[k].shape) != want[k]
+           and not (len(want[k]) == 4 and want[k][2:] == (1, 1) and tuple(sd[k].shape) == want[k][:2])]
+    if missing or extra or bad:
+        raise ops._abi.VNError(f"VAE state dict does not match the SD-2.1 layout: missing {missing[:3]} unexpected {extra[:3]} "
+                               f"shape mismatch {bad[:3]}")
+
+
 # ---- engine --------------------------------------------------------------------------------------
 def _require_cuda(dev: torch.device) -> None:
     if dev.type != "cuda":
@@ -158,6 +185,8 @@ class VAEEngine:
         self.ws = ops.Workspace(8192, 8192, self.dev)
         self._pools: "OrderedDict[tuple, Dict[tuple, torch.Tensor]]" = OrderedDict()   # call signature -> scratch
         self._bufs: Dict[tuple, torch.Tensor] = {}
+        state_dict = normalise_keys(state_dict)
+        check_state_dict(state_dict, cfg)
         self._prep(state_dict)
         n_gn = 2 * len(self.res) + 4
         self._stats = torch.zeros(n_gn, 64, cfg.norm_num_groups, 2, dtype=torch.float64, device=self.dev)
@@ -443,6 +472,22 @@ class AutoencoderKL(torch.nn.Module):
         sd = state_dict if state_dict is not None else init_state_dict(cfg, 0)
         self.engine = VAEEngine(sd, cfg, device)
         self.dtype = F32
+
+    @classmethod
+    def from_pretrained(cls, path: str, subfolder: Optional[str] = None, revision: Optional[str] = None, device="cuda",
+                        cfg: VAEConfig = SD21_VAE, **_) -> "AutoencoderKL":
+        """`AutoencoderKL.from_pretrained(pretrained_model_name_or_path, subfolder="vae", revision=...)` (reference
+        training/coach.py:628-633) for a LOCAL diffusers directory (no network here)."""
+        root = os.path.join(path, subfolder) if subfolder else path
+        for fn in ("diffusion_pytorch_model.safetensors", "diffusion_pytorch_model.bin", "diffusion_pytorch_model.pt"):
+            p = os.path.join(root, fn)
+            if not os.path.exists(p):
+                continue
+            if fn.endswith(".safetensors"):
+                from safetensors.torch import load_file
+                return cls(load_file(p), cfg, device)
+            return cls(torch.load(p, map_location="cpu"), cfg, device)
+        raise FileNotFoundError(f"no VAE checkpoint under {root} (AutoencoderKL(None) builds seeded synthetic weights)")
 
     def to(self, *args, **kwargs):           # weights live in kernel layout on the engine's device; dtype is advisory
         for a in list(args) + list(kwargs.values()):
