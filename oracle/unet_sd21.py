@@ -19,7 +19,7 @@ Call sites restated:
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional, Union
+from typing import Dict, Optional, Union
 
 import torch
 import torch.nn as nn

@@ -15,7 +15,7 @@ buffer (torch.cat never runs); norm / bias / time-embedding parameters fp32.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Tuple
 
 import torch
 

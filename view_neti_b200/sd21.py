@@ -11,8 +11,8 @@ Topology facts restated from the public SD-2.1 `unet/config.json` (SURVEY.md §8
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
-from typing import Dict, Iterator, List, Tuple
+from dataclasses import dataclass
+from typing import Dict, List, Tuple
 
 import torch
 

@@ -4,7 +4,7 @@ offline): token + position embeddings, the 23-layer CLIP encoder, one object map
 run whole train steps.  Used by bench.py (`full_step`) and scripts/full_step_bench.py."""
 from __future__ import annotations
 
-from typing import Dict, Tuple
+from typing import Dict
 
 import torch
 

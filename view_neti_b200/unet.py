@@ -26,7 +26,6 @@ from typing import Dict, List, Optional, Union
 
 import torch
 
-from . import ops
 from ._abi import VNError
 from .engine import UNetEngine
 from .sd21 import SD21, UNetConfig, init_state_dict
