@@ -159,3 +159,38 @@ def test_vae_engine_refuses_cpu():
     from view_neti_b200._abi import VNError
     with pytest.raises(VNError):
         vmod.VAEEngine(init_state_dict(TINY_VAE, 0), TINY_VAE, device="cpu")
+
+
+def test_emulation_covers_exactly_what_the_vae_launches():
+    """Guard against drift: every `ops.<name>` models/vae.py uses exists in the real ops module with the same
+    parameters as in the emulation the host-logic tests run on."""
+    import inspect
+    import re
+    from view_neti_b200 import ops as real
+    src = inspect.getsource(vmod)
+    used = sorted(set(re.findall(r"\bops\.([a-zA-Z_][a-zA-Z0-9_]*)", src)) - {"_abi"})
+    assert {"gemm", "conv3x3", "groupnorm_fwd", "softmax_rows", "im2col_thin", "im2col_s2_pad0", "upsample2x_fwd"} <= set(used)
+    for name in used:
+        assert hasattr(real, name) and hasattr(emu, name), name
+        if inspect.isclass(getattr(real, name)):
+            continue
+        pr, pe = inspect.signature(getattr(real, name)).parameters, inspect.signature(getattr(emu, name)).parameters
+        assert list(pr) == list(pe), (name, list(pr), list(pe))
+
+
+def test_pdl_off_restores_the_previous_state():
+    from view_neti_b200 import ops
+    assert ops._PDL is True
+    with ops.pdl_off():
+        assert ops._PDL is False
+        with ops.pdl_off():
+            assert ops._PDL is False
+        assert ops._PDL is False
+    assert ops._PDL is True
+    ops.set_pdl(False)
+    try:
+        with ops.pdl_off():
+            pass
+        assert ops._PDL is False                     # a user who switched PDL off keeps it off
+    finally:
+        ops.set_pdl(True)
