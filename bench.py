@@ -275,6 +275,58 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = world * k2 / (float(ms2) / 1e3)
+    e2e_note = "inputs copied at the start of their step"
+
+    # The same loop as a training job feeds it (pinned-memory loader with prefetch): the H2D copy of step i+1 is issued on
+    # a copy stream while step i computes.  Every timed step still copies one step's inputs and reads its loss back.
+    # Single-process only (no collective inside, so a failure here cannot desynchronise ranks); kept only if the loss is
+    # the same number and the loop is faster, else the figure above stands.
+    if world == 1:
+        try:
+            copy_stream = torch.cuda.Stream()
+            main_stream = torch.cuda.current_stream()
+
+            def stage():
+                with torch.cuda.stream(copy_stream):
+                    bufs = [h.to(dev, non_blocking=True) for h in (h_lat, h_t, h_tgt, h_ctx)]
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                for b in bufs:
+                    b.record_stream(main_stream)
+                return bufs, ev
+
+            staged = [stage()]
+
+            def e2e_step_prefetch():
+                (d_lat, d_t, d_tgt, d_all), ev = staged.pop()
+                main_stream.wait_event(ev)
+                d_ctx = {"this_idx": 0}
+                for i in range(nl):
+                    d_ctx[f"CONTEXT_TENSOR_{i}"] = d_all[0, i].detach().requires_grad_(True)
+                    d_ctx[f"CONTEXT_TENSOR_BYPASS_{i}"] = d_all[1, i].detach().requires_grad_(True)
+                pred = model(d_lat, d_t, d_ctx).sample
+                loss = F.mse_loss(pred.float(), d_tgt.float(), reduction="mean")
+                loss.backward()
+                staged.append(stage())                                    # next step's inputs travel under this step
+                return float(loss.detach().cpu())
+
+            for _ in range(3):
+                pf_loss = e2e_step_prefetch()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(k2):
+                pf_loss = e2e_step_prefetch()
+            e1.record()
+            torch.cuda.synchronize()
+            pf_value = k2 / (e0.elapsed_time(e1) / 1e3)
+            if abs(pf_loss - e2e_loss) <= 1e-6 * abs(e2e_loss) and pf_value > e2e_value:
+                e2e_note = ("inputs of step i+1 prefetched on a copy stream during step i (each step still copies one "
+                            "step's inputs and reads its loss); without prefetch: %.2f images/s" % e2e_value)
+                e2e_value = pf_value
+            else:
+                e2e_note += "; prefetch variant not used (%.2f images/s, loss %.6f)" % (pf_value, pf_loss)
+        except Exception as e:          # the plain figure stands
+            e2e_note += "; prefetch variant failed: " + f"{type(e).__name__}: {e}"[:120]
     api_plan = model.engine.plan(1, L, L)
     e2e_launches = api_plan.launches.get("fwd", 0) + api_plan.launches.get("bwd", 0)
 
@@ -378,7 +430,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                    "graph": "one CUDA graph per step"},
         "roofline": roofline, "cpu_baseline": cpu, "full_step": full_step,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "steps": k2, "api": "UNet2DConditionModel.__call__ + F.mse_loss + backward (CUDA-graph replay inside)"},
+                "steps": k2, "copies": e2e_note, "api": "UNet2DConditionModel.__call__ + F.mse_loss + backward (CUDA-graph replay inside)"},
         "gpu_launches": launches_per_step * args.steps + e2e_launches * k2 + e2e_launches_eager,
         "launches_per_step": launches_per_step,
         "clocks": clocks.summary(),
