@@ -12,8 +12,13 @@ of its published algorithm at the public `stabilityai/stable-diffusion-2-1` `vae
 block_out_channels [128, 256, 512, 512], layers_per_block 2, latent_channels 4, norm_num_groups 32, SiLU,
 GroupNorm eps 1e-6 throughout, one single-head attention block (head_dim = 512) in each mid block,
 encoder downsampling = zero-pad (0,1,0,1) + 3x3 stride-2 conv, decoder upsampling = nearest x2 + 3x3 conv.
-**Parity unpinned**: the reference holds no test vector for this path and diffusers cannot be imported; the structural
-pins are the parameter count (83 653 863) and the diffusers-0.14 state_dict key set, so real checkpoints stay loadable.
+Pinning: the reference holds no test vector for this path and diffusers cannot be imported, so parity against diffusers
+ITSELF is unpinned.  What pins this file instead (tests/test_vae_cpu.py): SD's VAE is the LDM / taming-transformers
+autoencoder and diffusers' AutoencoderKL is a re-keyed port of it; `transformers` (installed) ships verbatim ports of that
+Encoder / Decoder (ChameleonVQVAEEncoder, JanusVQVAEDecoder).  With the weights mapped the way diffusers' own LDM
+conversion maps them, `encode_moments` equals the Chameleon encoder + quant_conv and `decode` equals the Janus decoder
+(its three extra lowest-level attention blocks neutralised by a zero output projection) to 2e-5 at the SD-2.1 widths.
+Structural pins: parameter count 83 653 863 and the diffusers-0.14 state_dict key set, so real checkpoints stay loadable.
 """
 from __future__ import annotations
 

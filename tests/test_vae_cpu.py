@@ -194,3 +194,84 @@ def test_pdl_off_restores_the_previous_state():
         assert ops._PDL is False                     # a user who switched PDL off keeps it off
     finally:
         ops.set_pdl(True)
+
+
+# ---- the oracle against an independent implementation of the same published architecture -----------------
+# SD's VAE is the LDM / taming-transformers autoencoder (ddconfig ch 128, ch_mult [1,2,4,4], num_res_blocks 2,
+# attn_resolutions [], double_z, z_channels 4); diffusers' AutoencoderKL - which the reference calls and which is absent
+# here - is a re-keyed port of it.  transformers (installed) carries verbatim ports of that Encoder / Decoder for other
+# models: ChameleonVQVAEEncoder and JanusVQVAEDecoder.  Weight keys map the way diffusers' own LDM conversion maps them.
+def _ldm_keys(sd, side, n_levels, per_level):
+    out = {}
+
+    def put(dst, src, conv1x1=False):
+        for suffix in ("weight", "bias"):
+            t = sd[f"{src}.{suffix}"]
+            out[f"{dst}.{suffix}"] = t[:, :, None, None] if conv1x1 and suffix == "weight" and t.dim() == 2 else t
+
+    def resnet(dst, src):
+        for n in ("norm1", "conv1", "norm2", "conv2"):
+            put(f"{dst}.{n}", f"{src}.{n}")
+        if f"{src}.conv_shortcut.weight" in sd:
+            put(f"{dst}.nin_shortcut", f"{src}.conv_shortcut")
+
+    put("conv_in", f"{side}.conv_in")
+    for i in range(n_levels):
+        for j in range(per_level):
+            if side == "encoder":
+                resnet(f"down.{i}.block.{j}", f"encoder.down_blocks.{i}.resnets.{j}")
+            else:
+                resnet(f"up.{i}.block.{j}", f"decoder.up_blocks.{i}.resnets.{j}")
+        if i < n_levels - 1:
+            if side == "encoder":
+                put(f"down.{i}.downsample.conv", f"encoder.down_blocks.{i}.downsamplers.0.conv")
+            else:
+                put(f"up.{i}.upsample.conv", f"decoder.up_blocks.{i}.upsamplers.0.conv")
+    resnet("mid.block_1", f"{side}.mid_block.resnets.0")
+    resnet("mid.block_2", f"{side}.mid_block.resnets.1")
+    a = f"{side}.mid_block.attentions.0"
+    put("mid.attn_1.norm", f"{a}.group_norm")
+    for dst, src in (("q", "query"), ("k", "key"), ("v", "value"), ("proj_out", "proj_attn")):
+        put(f"mid.attn_1.{dst}", f"{a}.{src}", conv1x1=True)
+    put("norm_out", f"{side}.conv_norm_out")
+    put("conv_out", f"{side}.conv_out")
+    return out
+
+
+@pytest.mark.parametrize("cfg", [SD21_VAE, TINY_VAE], ids=["sd21", "tiny"])
+def test_vae_oracle_matches_the_ldm_autoencoder_ports_in_transformers(cfg):
+    from transformers.models.chameleon.modeling_chameleon import ChameleonVQVAEConfig, ChameleonVQVAEEncoder
+    from transformers.models.janus.modeling_janus import JanusVQVAEConfig, JanusVQVAEDecoder
+    ch = cfg.block_out_channels
+    mult = tuple(c // ch[0] for c in ch)
+    sd = init_state_dict(cfg, 11)
+    g = torch.Generator().manual_seed(0)
+    img = torch.rand(2, 3, 64, 96, generator=g) * 2 - 1
+    z = torch.randn(2, 4, 8, 12, generator=g)
+
+    enc = ChameleonVQVAEEncoder(ChameleonVQVAEConfig(double_latent=True, latent_channels=4, in_channels=3, base_channels=ch[0],
+                                                     channel_multiplier=mult, num_res_blocks=cfg.layers_per_block,
+                                                     attn_resolutions=None, attn_type="vanilla", dropout=0.0)).eval()
+    missing, unexpected = enc.load_state_dict(_ldm_keys(sd, "encoder", len(ch), cfg.layers_per_block), strict=True)
+    assert not missing and not unexpected
+    with torch.no_grad():
+        h = enc(img.clone())
+        m = F.conv2d(h, sd["quant_conv.weight"], sd["quant_conv.bias"])
+    mean, logvar = ovae.encode_moments(sd, cfg, img)
+    assert rel(mean, m[:, :4]) < 2e-5 and rel(logvar, m[:, 4:].clamp(-30, 20)) < 2e-5, (rel(mean, m[:, :4]), rel(logvar, m[:, 4:]))
+
+    dec = JanusVQVAEDecoder(JanusVQVAEConfig(latent_channels=4, out_channels=3, base_channels=ch[0], channel_multiplier=mult,
+                                             num_res_blocks=cfg.layers_per_block, dropout=0.0)).eval()
+    keys = _ldm_keys(sd, "decoder", len(ch), cfg.layers_per_block + 1)
+    # the Janus decoder has three attention blocks in its lowest-resolution level that the LDM config of SD
+    # (attn_resolutions = []) does not have: with a zero output projection each of them is the identity
+    full = dec.state_dict()
+    extra = [k for k in full if k not in keys]
+    assert extra and all(k.startswith("up.0.attn.") for k in extra), extra[:5]
+    for k in extra:
+        keys[k] = torch.zeros_like(full[k]) if ".proj_out." in k else full[k]
+    dec.load_state_dict(keys, strict=True)
+    with torch.no_grad():
+        want = dec(F.conv2d(z, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"]))
+    got = ovae.decode(sd, cfg, z)
+    assert got.shape == want.shape == (2, 3, 64, 96) and rel(got, want) < 2e-5, rel(got, want)
