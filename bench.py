@@ -276,6 +276,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = world * k2 / (float(ms2) / 1e3)
     e2e_note = "inputs copied at the start of their step"
+    pf_steps = 0
 
     # The same loop as a training job feeds it (pinned-memory loader with prefetch): the H2D copy of step i+1 is issued on
     # a copy stream while step i computes.  Every timed step still copies one step's inputs and reads its loss back.
@@ -312,10 +313,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
             for _ in range(3):
                 pf_loss = e2e_step_prefetch()
+                pf_steps += 1
             torch.cuda.synchronize()
             e0.record()
             for _ in range(k2):
                 pf_loss = e2e_step_prefetch()
+                pf_steps += 1
             e1.record()
             torch.cuda.synchronize()
             pf_value = k2 / (e0.elapsed_time(e1) / 1e3)
@@ -431,7 +434,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "roofline": roofline, "cpu_baseline": cpu, "full_step": full_step,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "steps": k2, "copies": e2e_note, "api": "UNet2DConditionModel.__call__ + F.mse_loss + backward (CUDA-graph replay inside)"},
-        "gpu_launches": launches_per_step * args.steps + e2e_launches * k2 + e2e_launches_eager,
+        "gpu_launches": launches_per_step * args.steps + e2e_launches * (k2 + pf_steps) + e2e_launches_eager,
         "launches_per_step": launches_per_step,
         "clocks": clocks.summary(),
         "loss": loss_dev, "e2e_loss": e2e_loss,
