@@ -66,10 +66,11 @@ typedef struct vn_gemm_desc {
   void*       D;  int64_t ldd;
   const float* bias;                /* [N] or NULL */
   const float* rowbias; int64_t ld_rowbias; int32_t rows_per_batch;   /* [nbatch,N] fp32 or NULL */
-  const void* R;  int64_t ldr;      /* residual [M,N] bf16 or NULL (may alias D) */
+  const void* R;  int64_t ldr;      /* residual [M,N] bf16 (fp32 when r_fp32) or NULL (may alias D) */
   int32_t out_fp32;
   void*   workspace; size_t workspace_bytes;
   int32_t force_bn, force_split;    /* tuning/test overrides; 0 = auto */
+  int32_t r_fp32;                   /* R holds fp32 (only with out_fp32: the fp32 residual stream of the text encoder) */
 } vn_gemm_desc;
 
 size_t vn_gemm_workspace_bytes(int max_M, int max_N);
@@ -125,6 +126,16 @@ int vn_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float
 int vn_layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* gamma,
                      const float* stats, const void* add, int64_t ldadd, void* dx, int64_t lddx,
                      int rows, int C, vn_stream_t s);
+
+/* fp32-stream forms (the CLIP text encoder keeps its residual stream in fp32, models/clip_encoder.py - transformers'
+ * CLIPEncoderLayer under reference models/neti_clip_text_encoder.py:101-108 runs in fp32): x / add / dx are fp32 rows, the
+ * normalised row y (a GEMM operand) stays bf16; bwd also writes a bf16 copy of dx (the A operand of the next dgrad GEMM)
+ * when dx_bf16 != NULL. */
+int vn_layernorm_fwd_f32(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
+                         void* y, int64_t ldy, float* stats, int rows, int C, vn_stream_t s);
+int vn_layernorm_bwd_f32(const float* x, int64_t ldx, const void* dy, int64_t lddy, const float* gamma,
+                         const float* stats, const float* add, int64_t ldadd, float* dx, int64_t lddx,
+                         void* dx_bf16, int64_t lddxb, int rows, int C, vn_stream_t s);
 
 /* GEGLU — diffusers GEGLU: h = [a | g] ([rows, 2F]);  y = a * gelu_erf(g). */
 int vn_geglu_fwd(const void* h, int64_t ldh, void* y, int64_t ldy, int rows, int F, vn_stream_t s);

@@ -160,6 +160,39 @@ def check_layernorm(rows, Cc):
             (f"layernorm {rows}x{Cc} bwd", rel(dx, xr.grad + add.float()), 8e-3)]
 
 
+def check_layernorm_f32(rows, Cc):
+    """fp32-stream forms (CLIP text encoder residual stream): fp32 x / add / dx, bf16 y and bf16 copy of dx."""
+    x = rnd(rows, Cc, seed=27) * 2 + 0.5
+    gamma, beta = 1 + 0.1 * rnd(Cc, seed=28), 0.1 * rnd(Cc, seed=29)
+    y = torch.empty(rows, Cc, dtype=BF, device=DEV)
+    stats = torch.empty(rows, 2, device=DEV)
+    ops.layernorm_fwd_f32(x, gamma, beta, 1e-5, y, stats, rows)
+    xr = x.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (Cc,), gamma, beta, 1e-5)
+    dy = rnd(rows, Cc, seed=30).to(BF)
+    yr.backward(dy.float())
+    add = rnd(rows, Cc, seed=31)
+    dx, dxb = torch.empty_like(x), torch.empty(rows, Cc, dtype=BF, device=DEV)
+    ops.layernorm_bwd_f32(x, dy, gamma, stats, dx, rows, add=add, dx_bf16=dxb)
+    dx2 = torch.empty_like(x)
+    ops.layernorm_bwd_f32(x, dy, gamma, stats, dx2, rows, add=None, dx_bf16=None)
+    return [(f"layernorm f32 {rows}x{Cc} fwd", rel(y, yr), 4e-3),
+            (f"layernorm f32 {rows}x{Cc} bwd", rel(dx, xr.grad + add), 2e-5),
+            (f"layernorm f32 {rows}x{Cc} bwd bf16 copy", rel(dxb, xr.grad + add), 4e-3),
+            (f"layernorm f32 {rows}x{Cc} bwd no add", rel(dx2, xr.grad), 2e-5)]
+
+
+def check_gemm_f32_residual(M, N, K, force_bn=0, force_split=0):
+    """fp32 output with an fp32 residual (direct epilogue; split-K finish)."""
+    A = rnd(M, K, seed=1).to(BF)
+    B = (rnd(N, K, seed=2) / math.sqrt(K)).to(BF)
+    bv, R = rnd(N, seed=3), rnd(M, N, seed=5) * 3
+    D = torch.empty(M, N, device=DEV)
+    ops.gemm(A, B, D, bias=bv, R=R, ws=ws(), force_bn=force_bn, force_split=force_split)
+    ref = A.float() @ B.float().t() + bv + R
+    return [(f"gemm f32 residual M{M} N{N} K{K} bn{force_bn} sp{force_split}", rel(D, ref), 2e-5)]
+
+
 def check_geglu(rows, Fd):
     h = rnd(rows, 2 * Fd, seed=22).to(BF)
     y = torch.empty(rows, Fd, dtype=BF, device=DEV)
@@ -386,6 +419,12 @@ def all_checks():
         L.append((check_groupnorm, dict(nb=nb, hw=hw, Cc=Cc, silu=silu, eps=1e-5 if silu else 1e-6)))
     for (rows, Cc) in [(4096, 320), (1024, 640), (77, 1280)]:
         L.append((check_layernorm, dict(rows=rows, Cc=Cc)))
+    for (rows, Cc) in [(1232, 1024), (77, 128), (300, 2048)]:
+        L.append((check_layernorm_f32, dict(rows=rows, Cc=Cc)))
+    L.append((check_gemm_f32_residual, dict(M=1232, N=1024, K=1024)))
+    L.append((check_gemm_f32_residual, dict(M=1232, N=1024, K=4096)))
+    L.append((check_gemm_f32_residual, dict(M=154, N=128, K=256, force_bn=64, force_split=2)))
+    L.append((check_gemm_f32_residual, dict(M=300, N=1024, K=1024, force_bn=128, force_split=1)))
     L.append((check_geglu, dict(rows=1024, Fd=2560)))
     for (nb, heads, n) in [(1, 5, 4096), (1, 10, 1024), (2, 20, 256), (1, 20, 64), (1, 4, 3072)]:
         L.append((check_attention, dict(nb=nb, heads=heads, nq=n, nk=n, strided=(n == 1024))))

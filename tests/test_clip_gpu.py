@@ -262,3 +262,37 @@ def test_object_only_conditioning_is_mode0_textual_inversion():
     first = cond(original_ti=True, **kw)
     assert torch.is_tensor(first) and first.shape == (2, 77, 128)
     assert rel(first, hs["CONTEXT_TENSOR_0"]) < 1e-6
+
+
+def _record(name, r):
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_figures.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **r}) + "\n")
+    except OSError:
+        pass
+
+
+def test_loss_to_mapper_gradient_parity_sd21_512px():
+    """The north-star contract end to end at the headline shape: MSE loss -> SD-2.1-width UNet dgrad (64x64 latents, B = 1)
+    -> FULL 23-layer CLIP-H-width text-encoder dgrad (16 stacked passes) -> the 283 392 parameters of M_o and M_v, against
+    the fp32 CPU oracles on identical inputs and weights (coach.py:186-214, 276-311).  eps-MSE < 1e-3 and relative L2 error
+    of the flat mapper gradient < 1e-2 (BASELINE.json north_star)."""
+    from tests.e2e_parity import run_e2e
+    from view_neti_b200.sd21 import SD21
+    r = run_e2e(SD21, 23, 16, 4096, 1, 64, 64)
+    _record("e2e_mapper_grad_sd21_512px", r)
+    assert r["eps_mse"] < 1e-3 and r["loss_rel"] < 2e-3, (r["eps_mse"], r["loss_rel"])
+    assert r["mapper_grad_flat_rel"] < 1e-2, r
+
+
+def test_loss_to_mapper_gradient_parity_tiny_matched_norm_bypass():
+    """Same chain on the narrow net, batch 2, with the norm-matched bypass mode (neti_clip_text_encoder.py:139-142)."""
+    from tests.e2e_parity import run_e2e
+    from view_neti_b200.sd21 import TINY
+    r = run_e2e(TINY, 2, 2, 256, 2, 16, 16, bypass_unconstrained=False)
+    _record("e2e_mapper_grad_tiny", r)
+    assert r["eps_mse"] < 1e-3 and r["mapper_grad_flat_rel"] < 3e-2, r       # narrow random-weight net: noisier gradients

@@ -176,3 +176,35 @@ def test_conditioning_oracle_matches_reference_golden():
             for key, gold in ((f"CONTEXT_TENSOR_{layer}", c["hs"][j]), (f"CONTEXT_TENSOR_BYPASS_{layer}", c["hs_bypass"][j])):
                 err = float((hs[key] - gold.float()).abs().max())
                 assert err < 4e-3, (name, key, err)          # fixture is stored in fp16 (|values| ~ 1-4)
+
+
+@pytest.mark.parametrize("kind", ["object", "view"])
+def test_mapper_oracle_matches_reference_golden(kind):
+    """oracle/neti_mapper.py against outputs and parameter gradients of the reference's own NeTIMapper
+    (tests/golden/neti_mapper.pt, generated by tests/golden/make_golden_mapper.py)."""
+    from oracle.neti_mapper import encode_inputs, mapper_forward
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "neti_mapper.pt"))
+    g = G[kind]
+    state = {k: v.clone().requires_grad_(True) for k, v in g["state"].items() if k != "encoder.w"}
+    vp = vmin = vmax = None
+    if kind == "view":
+        table = {i: [float(s.replace("p", ".")) for s in tok[6:-1].split("_")] for tok, i in zip(g["tokens"], g["ids"])}
+        allp = torch.tensor(list(table.values()))
+        vp = torch.tensor([table[int(i)][:2] for i in g["input_ids"]])                  # (theta, phi) degrees of freedom
+        vmin, vmax = allp.min(0).values.tolist(), allp.max(0).values.tolist()
+    x = encode_inputs(G["t"], G["l"], vp, vmin, vmax)
+    word, bypass = mapper_forward(state, g["w"], x, g["norm_scale"])
+    assert torch.allclose(word, g["word"], rtol=0, atol=2e-6) and torch.allclose(bypass, g["bypass"], rtol=0, atol=2e-6)
+    ((word * g["gw"]).sum() + (bypass * g["gb"]).sum()).backward()
+    for k, v in state.items():
+        assert torch.allclose(v.grad, g["grads"][k], rtol=1e-4, atol=1e-5), k
+
+
+def test_end_to_end_oracle_chain_runs_on_cpu():
+    """Oracle half of tests/e2e_parity.py (mappers -> conditioning -> CLIP -> UNet -> MSE -> mapper gradients) on the narrow
+    net: finite, non-zero gradients for all 2 x 10 mapper tensors (the GPU comparison is tests/test_clip_gpu.py)."""
+    from tests.e2e_parity import run_e2e
+    if torch.cuda.is_available():
+        pytest.skip("dry run of the oracle half is for CPU-only boxes")
+    r = run_e2e(TINY, 2, 2, 256, 2, 16, 16)
+    assert r["n"] == 2 * (64 * 64 * 2 + 64 * 6 + 2 * TINY.cross_attention_dim * 65) and r["mapper_grad_norm"] > 0

@@ -55,6 +55,38 @@ def test_unet_parity_sd21_dtu_default_48x64(sd_model):
     assert r["eps_mse"] < EPS_MSE_TOL and r["grad_flat_rel"] < GRAD_FLAT_TOL_SD21, (r["eps_mse"], r["grad_flat_rel"])
 
 
+def _record(name: str, r: dict) -> None:
+    """Keep the measured parity figures of the headline shapes (copied to profiles/ by hand after a GPU run)."""
+    import json
+    out = os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_figures.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **{k: v for k, v in r.items() if k != "per_grad"}}) + "\n")
+    except OSError:
+        pass
+
+
+def test_unet_parity_sd21_512px(sd_model):
+    """BASELINE config 2, the headline shape: 512^2 => 64x64 latents, B = 1, SD-2.1 widths, forward AND backward against
+    the fp32 oracle (coach.py:197-214).  The 64^2 shapes select their own rows of gemm_tuning.json (CTA pairs, BN 160 / 192),
+    so this is the only test in which exactly the benchmarked kernel instantiations run together."""
+    r = run_parity(SD21, 1, 64, 64, model=sd_model)
+    _record("sd21_512px_b1", r)
+    assert r["eps_mse"] < EPS_MSE_TOL and r["loss_rel"] < 2e-3, (r["eps_mse"], r["loss_rel"])
+    assert r["grad_flat_rel"] < GRAD_FLAT_TOL_SD21, r["grad_flat_rel"]
+    assert r["grad_worst_rel"] < 3e-2, r["grad_worst_rel"]
+    assert r["this_idx"] == 0
+
+
+def test_unet_parity_sd21_512px_batch2(sd_model):
+    """Same shape at per-GPU batch 2 (the reference trains at micro-batch <= 3, training/config.py:269-271)."""
+    r = run_parity(SD21, 2, 64, 64, seed=2, model=sd_model)
+    _record("sd21_512px_b2", r)
+    assert r["eps_mse"] < EPS_MSE_TOL and r["loss_rel"] < 2e-3, (r["eps_mse"], r["loss_rel"])
+    assert r["grad_flat_rel"] < GRAD_FLAT_TOL_SD21, r["grad_flat_rel"]
+
+
 def test_forward_only_cfg_batch_72x96(sd_model):
     """Inference shape of BASELINE config 5: 768x576 => 72x96 latents, uncond + cond batched as B = 2 (forward only)."""
     from oracle.unet_sd21 import UNetOracle

@@ -36,6 +36,7 @@ class GemmDesc(C.Structure):
         ("out_fp32", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("force_bn", C.c_int32), ("force_split", C.c_int32),
+        ("r_fp32", C.c_int32),
     ]
 
 
@@ -82,6 +83,8 @@ SIGNATURES = {
     "vn_set_groupnorm_fused": (None, [C.c_int]),
     "vn_layernorm_fwd": (C.c_int, [_P, _L, _P, _P, _F, _P, _L, _P, _I, _I, _P]),
     "vn_layernorm_bwd": (C.c_int, [_P, _L, _P, _L, _P, _P, _P, _L, _P, _L, _I, _I, _P]),
+    "vn_layernorm_fwd_f32": (C.c_int, [_P, _L, _P, _P, _F, _P, _L, _P, _I, _I, _P]),
+    "vn_layernorm_bwd_f32": (C.c_int, [_P, _L, _P, _L, _P, _P, _P, _L, _P, _L, _P, _L, _I, _I, _P]),
     "vn_geglu_fwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _P]),
     "vn_geglu_bwd": (C.c_int, [_P, _L, _P, _L, _P, _L, _I, _I, _P]),
     "vn_gelu_fwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _P]),

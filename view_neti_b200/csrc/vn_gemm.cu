@@ -61,6 +61,7 @@ struct GemmParams {
   const float* bias;
   const float* rowbias; long long ld_rowbias; int rows_per_batch;
   const bf16* R; long long ldr;
+  int r_fp32;           // R holds fp32 (direct epilogue only: fp32 outputs)
   int out_fp32;
   int use_tma_epilogue;
   int nbimg;            // images (conv mode); tiles of a padded cluster slot may decode to img >= nbimg
@@ -192,7 +193,13 @@ __device__ __forceinline__ void store8(const GemmParams& p, float (&o)[8], long 
     o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
     o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
   }
-  if (p.R) {
+  if (p.R && p.r_fp32) {
+    const float* rf = reinterpret_cast<const float*>(p.R) + gm * p.ldr + n;
+    const float4 r0 = *reinterpret_cast<const float4*>(rf);
+    const float4 r1 = *reinterpret_cast<const float4*>(rf + 4);
+    o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w;
+    o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
+  } else if (p.R) {
     const uint4 r = *reinterpret_cast<const uint4*>(p.R + gm * p.ldr + n);
     float2 t;
     t = unpack_bf162(r.x); o[0] += t.x; o[1] += t.y;
@@ -853,7 +860,7 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
   VN_CHECK(d->N % 8 == 0, "vn_gemm: N=%d must be a multiple of 8", d->N);
   VN_CHECK(d->lda % 8 == 0 && d->ldb % 8 == 0 && d->ldd % 8 == 0, "vn_gemm: lda/ldb/ldd must be multiples of 8");
   VN_CHECK(d->ldb >= d->K, "vn_gemm: ldb < K");
-  VN_CHECK(!d->R || d->ldr % 8 == 0, "vn_gemm: ldr must be a multiple of 8");
+  VN_CHECK(!d->R || d->r_fp32 || d->ldr % 8 == 0, "vn_gemm: ldr must be a multiple of 8");
   VN_CHECK((reinterpret_cast<uintptr_t>(d->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->B) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(d->D) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->R) & 15) == 0,
            "vn_gemm: A/B/D/R must be 16-byte aligned");
@@ -867,6 +874,9 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
   p.rowbias = d->rowbias; p.ld_rowbias = d->ld_rowbias; p.rows_per_batch = d->rows_per_batch;
   p.R = reinterpret_cast<const bf16*>(d->R); p.ldr = d->ldr;
   p.out_fp32 = d->out_fp32;
+  p.r_fp32 = d->R ? d->r_fp32 : 0;
+  VN_CHECK(!p.r_fp32 || d->out_fp32, "vn_gemm: an fp32 residual needs an fp32 output (direct epilogue)");
+  VN_CHECK(!p.r_fp32 || d->ldr % 4 == 0, "vn_gemm: ldr of an fp32 residual must be a multiple of 4");
 
   CUtensorMap ta, tb, td, tr;
   memset(&td, 0, sizeof(td));

@@ -722,13 +722,20 @@ bool gn_fused_enabled() {
 // ---------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, the row lives in registers as NV 16-byte vectors per lane (C <= 256*NV).
 // ---------------------------------------------------------------------------------------------
-template <int MODE, int NV>
-__global__ void __launch_bounds__(256) ln_kernel(const bf16* __restrict__ x, long long ldx,
+// F32 (the CLIP text encoder's fp32 residual stream, models/clip_encoder.py): x and add are fp32 rows; MODE 0 still
+// writes the normalised row in bf16 (it is a GEMM operand), MODE 1 writes dx in fp32 to y32 AND a bf16 copy to y (the
+// gradient stream is both the next residual input and the A operand of the next dgrad GEMM).
+template <int MODE, int NV, bool F32 = false>
+__global__ void __launch_bounds__(256) ln_kernel(const void* __restrict__ x_, long long ldx,
                                                  const bf16* __restrict__ dy, long long lddy,
                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                 float eps, float* __restrict__ stats, const bf16* __restrict__ add,
-                                                 long long ldadd, bf16* __restrict__ y, long long ldy, int rows,
-                                                 int C) {
+                                                 float eps, float* __restrict__ stats, const void* __restrict__ add_,
+                                                 long long ldadd, bf16* __restrict__ y, long long ldy,
+                                                 float* __restrict__ y32, long long ldy32, int rows, int C) {
+  const bf16* x = reinterpret_cast<const bf16*>(x_);
+  const bf16* add = reinterpret_cast<const bf16*>(add_);
+  const float* x32 = reinterpret_cast<const float*>(x_);
+  const float* add32 = reinterpret_cast<const float*>(add_);
   pdl_trigger();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -756,14 +763,31 @@ __global__ void __launch_bounds__(256) ln_kernel(const bf16* __restrict__ x, lon
   const bf16* xr = x + (long long)row * ldx;
   float xf[NV][8];
   uint4 raw[NV], draw[NV], araw[NV];
+  float af[F32 ? NV : 1][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int v = lane + i * 32;
     if (v < vecs) {
-      raw[i] = ld16(xr + v * 8);
+      if (F32) {
+        const float4 a0 = *reinterpret_cast<const float4*>(x32 + (long long)row * ldx + v * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(x32 + (long long)row * ldx + v * 8 + 4);
+        xf[i][0] = a0.x; xf[i][1] = a0.y; xf[i][2] = a0.z; xf[i][3] = a0.w;
+        xf[i][4] = a1.x; xf[i][5] = a1.y; xf[i][6] = a1.z; xf[i][7] = a1.w;
+      } else {
+        raw[i] = ld16(xr + v * 8);
+      }
       if (MODE == 1) {
         draw[i] = ld16(dy + (long long)row * lddy + v * 8);
-        if (add) araw[i] = ld16(add + (long long)row * ldadd + v * 8);
+        if (add_) {
+          if (F32) {
+            const float4 a0 = *reinterpret_cast<const float4*>(add32 + (long long)row * ldadd + v * 8);
+            const float4 a1 = *reinterpret_cast<const float4*>(add32 + (long long)row * ldadd + v * 8 + 4);
+            af[F32 ? i : 0][0] = a0.x; af[F32 ? i : 0][1] = a0.y; af[F32 ? i : 0][2] = a0.z; af[F32 ? i : 0][3] = a0.w;
+            af[F32 ? i : 0][4] = a1.x; af[F32 ? i : 0][5] = a1.y; af[F32 ? i : 0][6] = a1.z; af[F32 ? i : 0][7] = a1.w;
+          } else {
+            araw[i] = ld16(add + (long long)row * ldadd + v * 8);
+          }
+        }
       }
     }
   }
@@ -771,7 +795,7 @@ __global__ void __launch_bounds__(256) ln_kernel(const bf16* __restrict__ x, lon
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     if (lane + i * 32 < vecs) {
-      unpack8(raw[i], xf[i]);
+      if (!F32) unpack8(raw[i], xf[i]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += xf[i][j];
     }
@@ -827,13 +851,23 @@ __global__ void __launch_bounds__(256) ln_kernel(const bf16* __restrict__ x, lon
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = rstd * (dh[i][j] - c1 - xf[i][j] * c2);
-        if (add) {
-          float t[8];
-          unpack8(araw[i], t);
+        if (add_) {
+          if (F32) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += t[j];
+            for (int j = 0; j < 8; ++j) o[j] += af[F32 ? i : 0][j];
+          } else {
+            float t[8];
+            unpack8(araw[i], t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += t[j];
+          }
         }
-        *reinterpret_cast<uint4*>(yr + v * 8) = pack8(o);
+        if (F32) {
+          float* d32 = y32 + (long long)row * ldy32 + v * 8;
+          *reinterpret_cast<float4*>(d32) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(d32 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+        if (y) *reinterpret_cast<uint4*>(yr + v * 8) = pack8(o);
       }
     }
   }
@@ -891,17 +925,18 @@ int gn_check(int C, int groups, long long ldx) {
   return 0;
 }
 
-template <int MODE>
-int ln_launch(const bf16* x, long long ldx, const bf16* dy, long long lddy, const float* gamma, const float* beta,
-              float eps, float* stats, const bf16* add, long long ldadd, bf16* y, long long ldy, int rows, int C,
-              cudaStream_t s) {
+template <int MODE, bool F32 = false>
+int ln_launch(const void* x, long long ldx, const bf16* dy, long long lddy, const float* gamma, const float* beta,
+              float eps, float* stats, const void* add, long long ldadd, bf16* y, long long ldy, int rows, int C,
+              cudaStream_t s, float* y32 = nullptr, long long ldy32 = 0) {
   VN_CHECK(C % 8 == 0 && C <= 2048, "layernorm: C=%d unsupported (C %% 8 == 0, C <= 2048)", C);
-  VN_CHECK(ldx % 8 == 0 && ldy % 8 == 0 && lddy % 8 == 0 && ldadd % 8 == 0, "layernorm: strides must be multiples of 8");
+  VN_CHECK(ldx % (F32 ? 4 : 8) == 0 && ldy % 8 == 0 && lddy % 8 == 0 && ldadd % (F32 ? 4 : 8) == 0 && ldy32 % 4 == 0,
+           "layernorm: strides must be multiples of 8 (bf16) / 4 (fp32)");
   const int nv = (C / 8 + 31) / 32;
   const int grid = vn_cdiv(rows, 8);
 #define VN_LN_CASE(NV)                                                                                              \
   case NV:                                                                                                          \
-    VN_LAUNCH((ln_kernel<MODE, NV>), grid, 256, 0, s, x, ldx, dy, lddy, gamma, beta, eps, stats, add, ldadd, y, ldy, rows, C); \
+    VN_LAUNCH((ln_kernel<MODE, NV, F32>), grid, 256, 0, s, x, ldx, dy, lddy, gamma, beta, eps, stats, add, ldadd, y, ldy, y32, ldy32, rows, C); \
     break;
   switch (nv) {
     VN_LN_CASE(1) VN_LN_CASE(2) VN_LN_CASE(3) VN_LN_CASE(4) VN_LN_CASE(5) VN_LN_CASE(6) VN_LN_CASE(7) VN_LN_CASE(8)
@@ -1033,6 +1068,20 @@ extern "C" int vn_layernorm_bwd(const void* x, int64_t ldx, const void* dy, int6
                                 int C, vn_stream_t s) {
   return ln_launch<1>((const bf16*)x, ldx, (const bf16*)dy, lddy, gamma, nullptr, 0.f, const_cast<float*>(stats),
                       (const bf16*)add, ldadd, (bf16*)dx, lddx, rows, C, (cudaStream_t)s);
+}
+
+extern "C" int vn_layernorm_fwd_f32(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y,
+                                    int64_t ldy, float* stats, int rows, int C, vn_stream_t s) {
+  VN_CHECK(ldx % 4 == 0, "layernorm f32: row stride must be a multiple of 4");
+  return ln_launch<0, true>(x, ldx, nullptr, 0, gamma, beta, eps, stats, nullptr, 0, (bf16*)y, ldy, rows, C, (cudaStream_t)s);
+}
+
+extern "C" int vn_layernorm_bwd_f32(const float* x, int64_t ldx, const void* dy, int64_t lddy, const float* gamma,
+                                    const float* stats, const float* add, int64_t ldadd, float* dx, int64_t lddx,
+                                    void* dx_bf16, int64_t lddxb, int rows, int C, vn_stream_t s) {
+  VN_CHECK(ldx % 4 == 0 && ldadd % 4 == 0 && lddx % 4 == 0 && dx != nullptr, "layernorm f32: strides must be multiples of 4");
+  return ln_launch<1, true>(x, ldx, (const bf16*)dy, lddy, gamma, nullptr, 0.f, const_cast<float*>(stats), add, ldadd,
+                            (bf16*)dx_bf16, lddxb, rows, C, (cudaStream_t)s, dx, lddx);
 }
 
 extern "C" int vn_geglu_fwd(const void* h, int64_t ldh, void* y, int64_t ldy, int rows, int F, vn_stream_t s) {

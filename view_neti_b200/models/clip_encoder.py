@@ -130,18 +130,22 @@ class _ClipPlan:
         self.rows = rows
         self.ws = ops.Workspace(rows, I, dev)
         self.x_in = z(nseq, L, C, dt=F32)            # inputs_embeds (fp32, as the reference hands them over)
-        self.y_out = z(nseq, L, C, dt=F32)
         self.dy_in = z(nseq, L, C, dt=F32)
         self.dx_out = z(nseq, L, C, dt=F32)
         # train: kept per layer for the backward (both LayerNorm inputs + statistics, q/k/v, attention output, lse, fc1
         # output).  inference (no gradient wanted): every layer reuses ONE set of buffers, the stream ping-pongs between two.
         per = (lambda mk, n: [mk() for _ in range(n)]) if train else (lambda mk, n: [mk()] * n)      # noqa: E731
+        # The residual stream (x: layer inputs, xm: after the attention branch) is kept in FP32: it is rounded twice per
+        # layer, 46 times over the 23 layers, and in bf16 those roundings alone cost ~8e-3 of relative error in the mapper
+        # gradient (measured: 1.08e-2 end to end against the 1e-2 contract, profiles/r2_parity_figures.jsonl).  Branch
+        # tensors (GEMM operands) stay bf16.  x[0] is the fp32 input itself.
         if train:
-            self.x = [z(nseq, L, C) for _ in range(nl + 1)]
+            self.x = [self.x_in] + [z(nseq, L, C, dt=F32) for _ in range(nl)]
         else:
-            pp = [z(nseq, L, C), z(nseq, L, C)]
-            self.x = [pp[i % 2] for i in range(nl + 1)]
-        self.xm = per(lambda: z(nseq, L, C), nl)
+            pp = [z(nseq, L, C, dt=F32), z(nseq, L, C, dt=F32)]
+            self.x = [self.x_in] + [pp[i % 2] for i in range(nl)]
+        self.xm = per(lambda: z(nseq, L, C, dt=F32), nl)
+        self.y_out = self.x[-1]                      # last_hidden_state (before the text model's final LayerNorm)
         self.st1 = per(lambda: z(rows, 2, dt=F32), nl)
         self.st2 = per(lambda: z(rows, 2, dt=F32), nl)
         self.qkv = per(lambda: z(nseq, L, 3 * C), nl)
@@ -154,9 +158,10 @@ class _ClipPlan:
         self.g = z(nseq, L, I)
         if train:
             self.dq = z(nseq, L, 3 * C)
-            self.da = z(nseq, L, C)
-            self.db = z(nseq, L, C)
-            self.dc = z(nseq, L, C)
+            # gradient of the residual stream: fp32, with a bf16 copy of each tensor (the dgrad GEMMs' A operand).
+            # da / da32: d(layer output), overwritten in place by d(layer input); db / db32: d(xm)
+            self.da, self.db = z(nseq, L, C), z(nseq, L, C)
+            self.da32, self.db32 = z(nseq, L, C, dt=F32), z(nseq, L, C, dt=F32)
         self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self._saved = False
 
@@ -165,10 +170,9 @@ class _ClipPlan:
         eng, cfg = self.eng, self.eng.cfg
         C, heads, rows = cfg.hidden_size, cfg.num_attention_heads, self.rows
         scale = cfg.head_dim ** -0.5
-        ops.cast_f32_bf16(self.x_in, self.x[0])
         for i, l in enumerate(eng.layers):
             x, xm, qkv = self.x[i], self.xm[i], self.qkv[i]
-            ops.layernorm_fwd(x, l.ln1[0], l.ln1[1], cfg.layer_norm_eps, self.n, self.st1[i], rows)
+            ops.layernorm_fwd_f32(x, l.ln1[0], l.ln1[1], cfg.layer_norm_eps, self.n, self.st1[i], rows)
             ops.gemm(self.n, l.qkv_f, qkv, bias=l.qkv_bias, ws=self.ws)
             if eng.attn_impl == "tc":
                 ops.attention_fwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.o[i], self.lse[i], heads,
@@ -177,11 +181,10 @@ class _ClipPlan:
                 ops.seq_attention_fwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.o[i], self.lse[i], heads,
                                       scale=scale, causal=True)
             ops.gemm(self.o[i], l.o_f, xm, bias=l.o_bias, R=x, ws=self.ws)
-            ops.layernorm_fwd(xm, l.ln2[0], l.ln2[1], cfg.layer_norm_eps, self.n, self.st2[i], rows)
+            ops.layernorm_fwd_f32(xm, l.ln2[0], l.ln2[1], cfg.layer_norm_eps, self.n, self.st2[i], rows)
             ops.gemm(self.n, l.fc1_f, self.h1[i], bias=l.fc1_bias, ws=self.ws)
             ops.gelu_fwd(self.h1[i], self.g, rows)
             ops.gemm(self.g, l.fc2_f, self.x[i + 1], bias=l.fc2_bias, R=xm, ws=self.ws)
-        ops.cast_bf16_f32(self.x[-1], self.y_out)
         self._saved = True
         return self.y_out
 
@@ -192,15 +195,17 @@ class _ClipPlan:
         eng, cfg = self.eng, self.eng.cfg
         C, heads, rows = cfg.hidden_size, cfg.num_attention_heads, self.rows
         scale = cfg.head_dim ** -0.5
-        dy, dxm, dx = self.da, self.db, self.dc
-        ops.cast_f32_bf16(self.dy_in, dy)
+        # (dy32, dy): gradient of the layer's output stream in fp32 and its bf16 copy
+        dy32, dy = self.dy_in, self.da
+        dxm32, dxm = self.db32, self.db
+        ops.cast_f32_bf16(dy32, dy)
         for i in range(cfg.num_hidden_layers - 1, -1, -1):
             l = eng.layers[i]
             qkv = self.qkv[i]
             ops.gemm(dy, l.fc2_b, self.g, ws=self.ws)                        # d gelu-out
             ops.gelu_bwd(self.h1[i], self.g, self.g, rows)                   # d fc1-out (in place)
             ops.gemm(self.g, l.fc1_b, self.n, ws=self.ws)                    # d LN2-out
-            ops.layernorm_bwd(self.xm[i], self.n, l.ln2[0], self.st2[i], dxm, rows, add=dy)
+            ops.layernorm_bwd_f32(self.xm[i], self.n, l.ln2[0], self.st2[i], dxm32, rows, add=dy32, dx_bf16=dxm)
             ops.gemm(dxm, l.o_b, self.n, ws=self.ws)                         # d attention-out
             if eng.attn_impl == "tc":
                 ops.attention_bwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.o[i], self.lse[i], self.n,
@@ -211,9 +216,11 @@ class _ClipPlan:
                                       self.dq[..., :C], self.dq[..., C:2 * C], self.dq[..., 2 * C:], heads, scale=scale,
                                       causal=True)
             ops.gemm(self.dq, l.qkv_b, self.n, ws=self.ws)                   # d LN1-out
-            ops.layernorm_bwd(self.x[i], self.n, l.ln1[0], self.st1[i], dx, rows, add=dxm)
-            dy, dx = dx, dy
-        ops.cast_bf16_f32(dy, self.dx_out)
+            # d(layer input) overwrites d(layer output): both dy32 and dy were consumed above (stream order)
+            last = i == 0
+            dy32 = self.dx_out if last else self.da32
+            ops.layernorm_bwd_f32(self.x[i], self.n, l.ln1[0], self.st1[i], dy32, rows, add=dxm32,
+                                  dx_bf16=None if last else dy)
         return self.dx_out
 
     # ------------------------------------------------------------------------------------------------

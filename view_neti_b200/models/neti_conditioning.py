@@ -74,39 +74,40 @@ class NeTIConditioning(torch.nn.Module):
         out[rows, pos] = new.to(state.dtype)
         return out
 
-    def forward(self, input_ids: torch.Tensor = None, timesteps: torch.Tensor = None,
-                input_ids_placeholder_object=None, input_ids_placeholder_view=None, device=None,
-                original_ti: bool = False, **_) -> Dict:
+    def set_mapper(self, mapper_object_lookup: Optional[Dict[int, NeTIMapper]], mapper_view: Optional[NeTIMapper],
+                   device=None) -> None:
+        """net_clip_text_embedding.py:25-32 (`embeddings.set_mapper`): install / replace the mappers."""
+        dev = self.token_embedding.device if device is None else device
+        self.mapper_object_lookup = torch.nn.ModuleDict({str(k): v.to(dev) for k, v in (mapper_object_lookup or {}).items()})
+        self.mapper_view = mapper_view.to(dev) if mapper_view is not None else None
+
+    def encode(self, input_ids: torch.Tensor, timesteps: torch.Tensor, unet_layers: torch.Tensor, ph_o, ph_v,
+               use_mappers: bool = True):
+        """One stacked text-encoder pass over N = len(unet_layers) sequences: row r is prompt `input_ids[r]` at
+        (timesteps[r], unet_layers[r]).  Returns the final-LayerNorm'ed plain states and bypass states ([N, L, C] each, the
+        latter None without a bypass).  `use_mappers=False` is the plain CLIP text model (negative prompt,
+        sd_pipeline_call.py:36-41)."""
         dev = self.token_embedding.device
-        input_ids = torch.as_tensor(input_ids, device=dev)
-        timesteps = torch.as_tensor(timesteps, device=dev)
-        B, L = input_ids.shape
-        nl = 1 if original_ti else self.n_layers
-        N = nl * B
+        N, L = input_ids.shape
         C = self.token_embedding.shape[1]
-        t_rep = timesteps.float().repeat(nl)                                   # layer-major: row = layer * B + b
-        l_rep = torch.arange(nl, device=dev).repeat_interleave(B).float()
         rows = torch.arange(N, device=dev)
-        emb = self.token_embedding[input_ids].repeat(nl, 1, 1)                 # [N, L, C] (a fresh tensor: written below)
+        emb = self.token_embedding[input_ids]                                  # [N, L, C] (a fresh tensor: written below)
         obj = view = None
         ok = []
-        ph_o = self._as_list(input_ids_placeholder_object)
-        ph_v = self._as_list(input_ids_placeholder_view)
-        if len(self.mapper_object_lookup) > 0 and ph_o is not None and ph_o[0] != -1:
+        t_rep, l_rep = timesteps.float(), unet_layers.float()
+        if use_mappers and len(self.mapper_object_lookup) > 0 and ph_o is not None and ph_o[0] != -1:
             if any(v != ph_o[0] for v in ph_o):
                 raise VNError("one object per batch (net_clip_text_embedding.py:67-68)")
             mapper = self.mapper_object_lookup[str(ph_o[0])]
             out = mapper(timestep=t_rep, unet_layer=l_rep, input_ids_placeholder_view=None, truncation_idx=None)
             pos_o, good = self._positions(input_ids, torch.tensor(ph_o, device=dev))
             ok.append(good)
-            pos_o = pos_o.repeat(nl)
             emb[rows, pos_o] = out.word_embedding.to(emb.dtype)
             obj = (out, pos_o)
-        if self.mapper_view is not None and ph_v is not None and not all(v == -1 for v in ph_v):   # net_clip_text_embedding.py:105-106
-            out = self.mapper_view(timestep=t_rep, unet_layer=l_rep, input_ids_placeholder_view=ph_v * nl, truncation_idx=None)
+        if use_mappers and self.mapper_view is not None and ph_v is not None and not all(v == -1 for v in ph_v):   # :105-106
+            out = self.mapper_view(timestep=t_rep, unet_layer=l_rep, input_ids_placeholder_view=ph_v, truncation_idx=None)
             pos_v, good = self._positions(input_ids, torch.tensor(ph_v, device=dev))
             ok.append(good)
-            pos_v = pos_v.repeat(nl)
             emb[rows, pos_v] = out.word_embedding.to(emb.dtype)
             view = (out, pos_v)
         if ok and not bool(torch.stack(ok).all()):              # one synchronisation for both checks
@@ -121,14 +122,30 @@ class NeTIConditioning(torch.nn.Module):
                 with_bypass = self._inject_bypass(base, rows, pos, out.bypass_output.to(last.dtype), out.bypass_unconstrained,
                                                   out.output_bypass_alpha)
         ln = lambda s: F.layer_norm(s, (C,), self.final_ln_weight, self.final_ln_bias, self.eps).to(self.weight_dtype)   # noqa: E731
-        last_n = ln(last)
+        return ln(last), (ln(with_bypass) if with_bypass is not None else None)
+
+    def forward(self, input_ids: torch.Tensor = None, timesteps: torch.Tensor = None,
+                input_ids_placeholder_object=None, input_ids_placeholder_view=None, device=None,
+                original_ti: bool = False, **_) -> Dict:
+        """All 16 UNet layers of `Coach.get_text_conditioning` (coach.py:276-311) as ONE stacked pass (row = layer * B + b)."""
+        dev = self.token_embedding.device
+        input_ids = torch.as_tensor(input_ids, device=dev)
+        timesteps = torch.as_tensor(timesteps, device=dev)
+        B, L = input_ids.shape
+        nl = 1 if original_ti else self.n_layers
+        C = self.token_embedding.shape[1]
+        ph_o = self._as_list(input_ids_placeholder_object)
+        ph_v = self._as_list(input_ids_placeholder_view)
+        last_n, bypass_n = self.encode(input_ids.repeat(nl, 1), timesteps.repeat(nl),
+                                       torch.arange(nl, device=dev).repeat_interleave(B),
+                                       ph_o * nl if ph_o is not None else None, ph_v * nl if ph_v is not None else None)
         if original_ti:
             return last_n[:B]                                                  # coach.py:307-309
         hs: Dict = {"this_idx": 0}
         # unbind, not 16 slices: its backward is ONE stack of the 16 context gradients instead of 16 zero-filled
         # full-size tensors that autograd would have to add up
         plain = last_n.view(nl, B, L, C).unbind(0)
-        bypass = ln(with_bypass).view(nl, B, L, C).unbind(0) if with_bypass is not None else None
+        bypass = bypass_n.view(nl, B, L, C).unbind(0) if bypass_n is not None else None
         for i in range(nl):
             hs[f"CONTEXT_TENSOR_{i}"] = plain[i]
             if bypass is not None:

@@ -101,6 +101,9 @@ def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, bias=None, rowbia
         d.rowbias, d.ld_rowbias, d.rows_per_batch = ptr(rowbias), rowbias.stride(0), rows_per_batch
     if R is not None:
         d.R, d.ldr = ptr(R), _ld(R)
+        if R.dtype == torch.float32:
+            assert D.dtype == torch.float32, "an fp32 residual needs an fp32 output"
+            d.r_fp32 = 1
     if ws is not None:
         d.workspace, d.workspace_bytes = ptr(ws.buf), ws.bytes
     if not force_bn and not force_split:
@@ -199,6 +202,22 @@ def layernorm_bwd(x, dy, gamma, stats, dx, rows, add=None):
     check(_abi.load().vn_layernorm_bwd(ptr(x), _ld(x), ptr(dy), _ld(dy), ptr(gamma), ptr(stats), ptr(add),
                                        _ld(add) if add is not None else 0, ptr(dx), _ld(dx), rows, x.shape[-1],
                                        stream()), "ln_bwd")
+
+
+def layernorm_fwd_f32(x, gamma, beta, eps, y, stats, rows):
+    """fp32 rows in, bf16 normalised rows out (the text encoder's fp32 residual stream)."""
+    assert x.dtype == torch.float32 and y.dtype == BF16
+    check(_abi.load().vn_layernorm_fwd_f32(ptr(x), _ld(x), ptr(gamma), ptr(beta), eps, ptr(y), _ld(y), ptr(stats), rows,
+                                           x.shape[-1], stream()), "ln_fwd_f32")
+
+
+def layernorm_bwd_f32(x, dy, gamma, stats, dx, rows, add=None, dx_bf16=None):
+    """dx (fp32) = LN^T(dy) (+ add, fp32); optionally also a bf16 copy of dx (A operand of the next dgrad GEMM)."""
+    assert x.dtype == torch.float32 and dx.dtype == torch.float32 and (add is None or add.dtype == torch.float32)
+    check(_abi.load().vn_layernorm_bwd_f32(ptr(x), _ld(x), ptr(dy), _ld(dy), ptr(gamma), ptr(stats), ptr(add),
+                                           _ld(add) if add is not None else 0, ptr(dx), _ld(dx), ptr(dx_bf16),
+                                           _ld(dx_bf16) if dx_bf16 is not None else 0, rows, x.shape[-1], stream()),
+          "ln_bwd_f32")
 
 
 def geglu_fwd(h, y, rows):
