@@ -296,3 +296,49 @@ def test_loss_to_mapper_gradient_parity_tiny_matched_norm_bypass():
     r = run_e2e(TINY, 2, 2, 256, 2, 16, 16, bypass_unconstrained=False)
     _record("e2e_mapper_grad_tiny", r)
     assert r["eps_mse"] < 1e-3 and r["mapper_grad_flat_rel"] < 3e-2, r       # narrow random-weight net: noisier gradients
+
+
+@pytest.mark.parametrize("mode,cam", [(2, "dtu-12d"), (3, "spherical"), (0, "spherical")])
+def test_coach_from_runconfig_trains(mode, cam, tmp_path):
+    """`Coach(cfg).train()` as reference scripts/train.py:23-24 runs it: every component built from the RunConfig (seeded
+    narrow models, synthetic data in the reference's item format), micro-batch 2 x accumulation 2, checkpoints written in
+    the reference's layout and read back."""
+    from view_neti_b200.checkpoint_handler import CheckpointHandler
+    from view_neti_b200.training.coach import Coach
+    from view_neti_b200.training.config import from_dict
+    objs = [f"<o{i}>" for i in range(3)]
+    cfg = from_dict({
+        "learnable_mode": mode, "seed": 3,
+        "log": {"exp_dir": str(tmp_path), "save_steps": 2},
+        "data": {"train_data_dir": "synthetic", "placeholder_object_token": "<statue>", "dataloader_num_workers": 0,
+                 "camera_representation": cam, "resolution": 128, "repeats": 16,
+                 **({"placeholder_object_tokens": objs, "super_category_object_tokens": ["object"] * 3,
+                     "train_data_subsets": ["a", "b", "c"]} if mode == 3 else {})},
+        "model": {"pretrained_model_name_or_path": "synthetic-tiny", "word_embedding_dim": 128, "arch_mlp_hidden_dims": 64,
+                  "use_nested_dropout": False, "arch_view_net": 15, "arch_view_disable_tl": False,
+                  "normalize_view_mapper_output": True, "bypass_unconstrained_object": True, "bypass_unconstrained_view": True},
+        "optim": {"max_train_steps": 3, "train_batch_size": 2, "gradient_accumulation_steps": 2, "learning_rate": 1e-3,
+                  "scale_lr": True, "seed": 1},
+    })
+    coach = Coach(cfg)
+    n_obj = 3 if mode == 3 else 1
+    assert len(coach.text_encoder.text_model.embeddings.mapper_object_lookup) == n_obj
+    assert (coach.text_encoder.text_model.embeddings.mapper_view is None) == (mode == 0)
+    assert coach.optimizer.defaults["lr"] == pytest.approx(1e-3 * 2 * 2)                 # scale_lr (coach.py:728-733)
+    before = [p.detach().clone() for p in coach.conditioning.parameters()]
+    losses = coach.train()
+    assert coach.global_step == 3 and coach.micro_step == 6 and len(losses) == 6
+    assert all(math.isfinite(float(l)) for l in losses)
+    moved = [not torch.equal(p.detach(), b) for p, b in zip(coach.conditioning.parameters(), before)]
+    assert any(moved)
+    import os
+    files = sorted(os.listdir(tmp_path))
+    assert "mapper-steps-2_object.pt" in files and "mapper-final_object.pt" in files and "learned_embeds-final.bin" in files
+    assert ("mapper-final_view.pt" in files) == (mode != 0)
+    _, loaded = CheckpointHandler.load_mapper(tmp_path / "mapper-final_object.pt", "object",
+                                              placeholder_object_tokens=coach.placeholder_object_tokens,
+                                              placeholder_object_token_ids=coach.placeholder_object_token_ids)
+    assert sorted(loaded) == sorted(coach.placeholder_object_token_ids)
+    tid = coach.placeholder_object_token_ids[0]
+    ours = coach.text_encoder.text_model.embeddings.mapper_object_lookup[tid]
+    assert torch.equal(loaded[tid].output_layer[0].weight.cpu(), ours.output_layer[0].weight.detach().cpu())

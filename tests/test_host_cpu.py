@@ -146,15 +146,24 @@ def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(0)
-    a, b, c = (torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2)))
+    a, b, c, d = (torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2)),
+                  torch.nn.Parameter(torch.zeros(3)))
     a.grad = torch.full((3, 4), float(rank + 1))
-    b.grad = torch.arange(5.0) * (rank + 1)          # c.grad stays None on every rank -> zeros
-    red = FlatGradAllReducer([a, b, c])
+    b.grad = torch.arange(5.0) * (rank + 1)          # c.grad stays None on every rank -> must stay None (AdamW skips it)
+    if rank == 1:
+        d.grad = torch.full((3,), 4.0)               # used on one rank only -> every rank gets the mean (the other counts as 0)
+    red = FlatGradAllReducer([a, b, c, d])
     flat = red.allreduce_()
+    # the caller names the parameters a step used (mode 3: M_v + the object mapper rank 0 drew): only those travel
+    e, f = torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(4))
+    e.grad = torch.full((4,), float(2 * rank))
+    red2 = FlatGradAllReducer([e, f])
+    part = red2.allreduce_(active=[e])
     # construction-time broadcast (DDP semantics): ranks start from rank 0's values whatever their local init was
     w = torch.nn.Parameter(torch.full((4,), float(10 + rank)))
     FlatGradAllReducer([w]).broadcast_parameters_(0)
-    q.put((rank, a.grad.clone(), b.grad.clone(), c.grad.clone(), flat.numel(), w.detach().clone()))
+    q.put((rank, a.grad.clone(), b.grad.clone(), c.grad, d.grad.clone(), flat.numel(), w.detach().clone(), e.grad.clone(),
+           f.grad, part.numel()))
     dist.destroy_process_group()
 
 
@@ -170,12 +179,32 @@ def test_flat_gradient_allreduce_gloo_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, a, b, c, n, w in res:
+    for rank, a, b, c, d, n, w, e, f, npart in res:
         assert torch.equal(w, torch.full((4,), 10.0))
-        assert n == 12 + 5 + 2
+        assert n == 12 + 5 + 2 + 3
         assert torch.allclose(a, torch.full((3, 4), 1.5))            # mean of 1 and 2
         assert torch.allclose(b, torch.arange(5.0) * 1.5)
-        assert torch.equal(c, torch.zeros(2))
+        assert c is None                                              # unused on every rank: no gradient appears
+        assert torch.allclose(d, torch.full((3,), 2.0))               # mean of (missing = 0) and 4
+        assert torch.allclose(e, torch.full((4,), 1.0)) and f is None and npart == 4
+
+
+def test_reducer_is_a_no_op_in_one_process_and_leaves_unused_mappers_alone():
+    """with one process nothing is reduced and no zero gradients are invented, so AdamW neither decays
+    nor moves a mapper that took no part in the step (reference coach.py:736-757 after zero_grad)."""
+    from view_neti_b200.training.dist import FlatGradAllReducer
+    used, unused = torch.nn.Linear(4, 4), torch.nn.Linear(4, 4)
+    params = list(used.parameters()) + list(unused.parameters())
+    opt = torch.optim.AdamW(params, lr=0.1, weight_decay=0.5)
+    before = [p.detach().clone() for p in unused.parameters()]
+    red = FlatGradAllReducer(params)
+    for _ in range(3):
+        used(torch.ones(2, 4)).sum().backward()
+        assert red.allreduce_() is None
+        assert all(p.grad is None for p in unused.parameters())
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+    assert all(torch.equal(p.detach(), b) for p, b in zip(unused.parameters(), before))      # bit-identical
 
 
 def test_synthetic_conditioning_emits_xti_dict():

@@ -35,11 +35,22 @@ class _ReferenceObject:
         self.__dict__.update(state if isinstance(state, dict) else {"_state": state})
 
 
+_SAFE_MODULE_ROOTS = ("torch", "collections", "numpy", "pathlib", "_codecs")
+_SAFE_BUILTINS = {"set", "frozenset", "slice", "complex", "dict", "list", "tuple", "int", "float", "str", "bool", "bytes",
+                  "bytearray", "range", "object"}
+
+
 class _Unpickler(pickle.Unpickler):
+    """Classes from the reference's own packages become inert attribute holders; everything else must come from a short
+    allowlist (tensors, containers, numpy scalars, paths) - a checkpoint cannot name arbitrary callables."""
+
     def find_class(self, module: str, name: str):
-        if module.split(".")[0] in _REFERENCE_PACKAGES:
+        root = module.split(".")[0]
+        if root in _REFERENCE_PACKAGES:
             return type(name, (_ReferenceObject,), {"__module__": "reference." + module})
-        return super().find_class(module, name)
+        if root in _SAFE_MODULE_ROOTS or (module == "builtins" and name in _SAFE_BUILTINS):
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f"checkpoint names {module}.{name}, which is not on the allowlist of this loader")
 
 
 class _PickleModule:
@@ -71,7 +82,7 @@ class CheckpointHandler:
     def __init__(self, cfg: Optional[Dict] = None, placeholder_view_tokens: Optional[List[str]] = None,
                  placeholder_view_token_ids: Optional[List[int]] = None, placeholder_object_tokens: Optional[List[str]] = None,
                  placeholder_object_token_ids: Optional[List[int]] = None, save_root: Union[str, Path] = "."):
-        self.cfg = cfg or {}
+        self.cfg = self._encode_cfg(cfg)
         self.placeholder_view_tokens = list(placeholder_view_tokens or [])
         self.placeholder_view_token_ids = list(placeholder_view_token_ids or [])
         self.placeholder_object_tokens = list(placeholder_object_tokens or [])
@@ -79,6 +90,28 @@ class CheckpointHandler:
         self.placeholder_tokens = self.placeholder_view_tokens + self.placeholder_object_tokens
         self.placeholder_token_ids = self.placeholder_view_token_ids + self.placeholder_object_token_ids
         self.save_root = Path(save_root)
+
+    @staticmethod
+    def _encode_cfg(cfg) -> Optional[Dict]:
+        """The reference stores `pyrallis.encode(cfg)` (checkpoint_handler.py:69): a plain nested dict.  A RunConfig is
+        encoded the same way; a dict is taken as is; None is allowed for handlers that only load."""
+        if cfg is None:
+            return None
+        import dataclasses
+        if dataclasses.is_dataclass(cfg):
+            from .training.config import to_dict
+            return to_dict(cfg)
+        if not isinstance(cfg, dict):
+            raise VNError("CheckpointHandler: cfg must be a RunConfig or the nested dict it encodes to")
+        return cfg
+
+    def _cfg_for_saving(self) -> Dict:
+        cfg = self.cfg
+        if not isinstance(cfg, dict) or not isinstance(cfg.get("model"), dict) or not isinstance(cfg.get("data"), dict):
+            raise VNError("CheckpointHandler.save_mapper: cfg must be a nested dict with 'model' and 'data' sections (it is what "
+                          "load_mapper rebuilds the mapper from, checkpoint_handler.py:143-198); construct the handler with the "
+                          "RunConfig of the run")
+        return cfg
 
     # ---- writing (checkpoint_handler.py:34-97) ---------------------------------------------------------
     def save_model(self, conditioning, embeds_save_name: str, mapper_save_name: str) -> None:
@@ -99,11 +132,12 @@ class CheckpointHandler:
     def save_mapper(self, mapper_object_lookup: Optional[Dict[int, NeTIMapper]], mapper_view: Optional[NeTIMapper],
                     save_name: str) -> None:
         stem, suffix = Path(save_name).stem, Path(save_name).suffix
+        cfg = self._cfg_for_saving()
         if mapper_object_lookup is not None:
-            ckpt = {"cfg": self.cfg, "mappers": {k: self._entry(m, m.placeholder_object_token) for k, m in mapper_object_lookup.items()}}
+            ckpt = {"cfg": cfg, "mappers": {k: self._entry(m, m.placeholder_object_token) for k, m in mapper_object_lookup.items()}}
             torch.save(ckpt, os.path.join(self.save_root, stem + "_object" + suffix))
         if mapper_view is not None:
-            ckpt = {"cfg": self.cfg, "mappers": {"dummy_key": self._entry(mapper_view, "dummy")}}
+            ckpt = {"cfg": cfg, "mappers": {"dummy_key": self._entry(mapper_view, "dummy")}}
             torch.save(ckpt, os.path.join(self.save_root, stem + "_view" + suffix))
 
     # ---- reading (checkpoint_handler.py:130-230) ------------------------------------------------------
@@ -111,7 +145,8 @@ class CheckpointHandler:
     def load_mapper(mapper_path: Union[str, Path], embedding_type: str = "object",
                     placeholder_view_tokens: Optional[List[str]] = None, placeholder_view_token_ids: Optional[List[int]] = None,
                     placeholder_object_tokens: Optional[List[str]] = None, placeholder_object_token_ids: Optional[List[int]] = None,
-                    device: Union[str, torch.device] = "cpu") -> Tuple[Dict, Union[NeTIMapper, Dict[int, NeTIMapper]]]:
+                    device: Union[str, torch.device] = "cpu", cam_mins: Optional[torch.Tensor] = None,
+                    cam_maxs: Optional[torch.Tensor] = None) -> Tuple[Dict, Union[NeTIMapper, Dict[int, NeTIMapper]]]:
         """Returns (cfg dict, view mapper) or (cfg dict, {placeholder token id: object mapper}) like the reference; mappers
         land on `device` (their forward needs CUDA, loading does not)."""
         ckpt = torch.load(mapper_path, map_location="cpu", weights_only=False, pickle_module=_PickleModule)
@@ -152,7 +187,7 @@ class CheckpointHandler:
                            arch_view_net=get("arch_view_net"), arch_view_mix_streams=get("arch_view_mix_streams", 0),
                            arch_view_disable_tl=get("arch_view_disable_tl"), original_ti=get("original_ti", False),
                            output_bypass=output_bypass, output_bypass_alpha=alpha, placeholder_object_token=token,
-                           bypass_unconstrained=unconstrained)
+                           bypass_unconstrained=unconstrained, cam_mins=cam_mins, cam_maxs=cam_maxs)
             state = {k: v for k, v in entry["state_dict"].items() if k != "encoder.w"}     # a Parameter only on CPU runs
             m.load_state_dict(state, strict=True)
             w = entry["state_dict"].get("encoder.w")

@@ -164,6 +164,7 @@ class _ClipPlan:
             self.da32, self.db32 = z(nseq, L, C, dt=F32), z(nseq, L, C, dt=F32)
         self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self._saved = False
+        self.generation = 0           # bumped by every training forward; a backward checks that it is still its own
 
     # ------------------------------------------------------------------------------------------------
     def forward(self) -> torch.Tensor:
@@ -262,13 +263,18 @@ class _ClipEncoderFn(torch.autograd.Function):
     def forward(ctx, x: torch.Tensor, plan: _ClipPlan, use_graphs: bool) -> torch.Tensor:
         plan.x_in.copy_(x)
         y = plan.run_forward(use_graphs)
-        ctx.plan = plan
+        plan.generation += 1
+        ctx.plan, ctx.gen = plan, plan.generation
         ctx.in_dtype = x.dtype
         return y.to(x.dtype, copy=True)
 
     @staticmethod
     def backward(ctx, dy: torch.Tensor):
         plan = ctx.plan
+        if ctx.gen != plan.generation:
+            raise ops._abi.VNError("backward() after another forward of the same shape through this CLIPEncoder: the static "
+                                   "activation plan was overwritten (run each backward before the next training forward - "
+                                   "gradient accumulation works micro-step by micro-step, coach.py:158-218)")
         plan.dy_in.copy_(dy)
         dx = plan.run_backward()
         return dx.to(ctx.in_dtype, copy=True), None, None

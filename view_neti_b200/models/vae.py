@@ -452,7 +452,9 @@ class DiagonalGaussianDistribution:
         self.var = torch.exp(logvar)
 
     def sample(self, generator: Optional[torch.Generator] = None) -> torch.Tensor:
-        noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        # diffusers' randn_tensor: draw on the generator's device (a CPU generator is legal), then move
+        gdev = generator.device if generator is not None else self.mean.device
+        noise = torch.randn(self.mean.shape, generator=generator, device=gdev, dtype=self.mean.dtype).to(self.mean.device)
         return self.mean + self.std * noise
 
     def mode(self) -> torch.Tensor:

@@ -351,9 +351,17 @@ def timestep_sinusoid(t, out):
     check(_abi.load().vn_timestep_sinusoid(ptr(t), ptr(out), out.shape[0], out.shape[1], stream()), "timestep")
 
 
+GEMV_MAX_BATCH = 8          # kGemvMaxB in csrc/vn_small.cu: rows of x one launch keeps in registers
+
+
 def gemv(x, W, bias, y, silu_in=False):
-    check(_abi.load().vn_gemv(ptr(x), x.stride(0), ptr(W), ptr(bias), ptr(y), y.stride(0), x.shape[0], W.shape[0],
-                              W.shape[1], int(silu_in), stream()), "gemv")
+    """y[b] = W @ (silu?)(x[b]) + bias for a handful of rows (time embedding).  Batches beyond the kernel's 8 rows per
+    launch (training batches > 8, CFG batches of sd_pipeline_call with num_images_per_prompt > 4) go in chunks."""
+    lib = _abi.load()
+    for b0 in range(0, x.shape[0], GEMV_MAX_BATCH):
+        xb, yb = x[b0:b0 + GEMV_MAX_BATCH], y[b0:b0 + GEMV_MAX_BATCH]
+        check(lib.vn_gemv(ptr(xb), xb.stride(0), ptr(W), ptr(bias), ptr(yb), yb.stride(0), xb.shape[0], W.shape[0],
+                          W.shape[1], int(silu_in), stream()), "gemv")
 
 
 def cast_f32_bf16(x, y):
