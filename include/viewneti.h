@@ -219,6 +219,9 @@ int vn_mse_loss(const float* pred, const float* target, int64_t n, float loss_sc
  * latents fp32 [n] updated in place.  acp_t / acp_prev = alphas_cumprod at t / t_prev; vpred: 0 eps, 1 v. */
 int vn_cfg_ddim_step(float* latents, const float* eps_uncond, const float* eps_cond, int64_t n,
                      float guidance, float acp_t, float acp_prev, int vpred, vn_stream_t s);
+/* [nb, hw, ldin] fp32 (the first Ct channels of every pixel) -> [nb, Ct, hw] fp32: NCHW view of the result of a thin conv_out
+ * computed as an N-padded implicit GEMM (diffusers UNet2DConditionModel.conv_out, 320 -> 4, under reference coach.py:197). */
+int vn_nhwc_to_nchw_thin(const float* in, int64_t ldin, float* out, int nb, int Ct, int64_t hw, vn_stream_t s);
 /* the same fused step for DPM-Solver++(2M), the scheduler the reference's inference scripts install (reference
  * training/validate.py:568, training/inference_dtu.py:304): m = u + g (c - u); x0 = p x + q m;
  * latents = A x + B0 x0 + B1 x0_prev;  x0_prev = x0.  (p, q, A, B0, B1) per step from the host scheduler; B1 = 0 on

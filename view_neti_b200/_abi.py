@@ -85,6 +85,7 @@ SIGNATURES = {
     "vn_layernorm_bwd": (C.c_int, [_P, _L, _P, _L, _P, _P, _P, _L, _P, _L, _I, _I, _P]),
     "vn_layernorm_fwd_f32": (C.c_int, [_P, _L, _P, _P, _F, _P, _L, _P, _I, _I, _P]),
     "vn_layernorm_bwd_f32": (C.c_int, [_P, _L, _P, _L, _P, _P, _P, _L, _P, _L, _P, _L, _I, _I, _P]),
+    "vn_nhwc_to_nchw_thin": (C.c_int, [_P, _L, _P, _I, _I, _L, _P]),
     "vn_geglu_fwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _P]),
     "vn_geglu_bwd": (C.c_int, [_P, _L, _P, _L, _P, _L, _I, _I, _P]),
     "vn_gelu_fwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _P]),

@@ -294,37 +294,60 @@ __global__ void timestep_sinusoid_kernel(const long long* __restrict__ t, float*
 }
 
 // y[b,n] = bias[n] + sum_k act(x[b,k]) * W[n,k]; one warp per output n, all (<= 8) batch rows at once.
+// The activations (SiLU applied ONCE per CTA, not once per output) are staged in shared memory; every lane has all of its
+// 16-byte weight loads of a row in flight before the first one is consumed, so the launch streams W at HBM rate (the
+// per-ResBlock time-embedding projection reads 38 MB of weights: 39 us -> ~8 us on B200).
 constexpr int kGemvMaxB = 8;
+constexpr int kGemvMaxK = 2048;
 __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, long long ldx,
                                                    const bf16* __restrict__ Wt, const float* __restrict__ bias,
                                                    float* __restrict__ y, long long ldy, int nb, int N, int K,
                                                    int silu_in) {
   pdl_trigger();
-  pdl_wait();
+  extern __shared__ float sx[];                  // [nb][K]
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  // the weights are frozen: this lane's slice of row n is requested ahead of the grid dependency
+  constexpr int kMaxIter = kGemvMaxK / 256;
+  uint4 wv[kMaxIter];
+  const int iters = (K + 255) >> 8;
+  const bf16* wr = Wt + (long long)min(n, N - 1) * K;
+#pragma unroll
+  for (int i = 0; i < kMaxIter; ++i) {
+    const int k = lane * 8 + i * 256;
+    wv[i] = (i < iters && k < K) ? __ldg(reinterpret_cast<const uint4*>(wr + k)) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  pdl_wait();
+  for (int i = threadIdx.x; i < nb * K; i += blockDim.x) {
+    const int b = i / K, k = i - b * K;
+    float v = x[(long long)b * ldx + k];
+    if (silu_in) v = silu_f(v);
+    sx[i] = v;
+  }
+  __syncthreads();
   if (n >= N) return;
   float acc[kGemvMaxB];
 #pragma unroll
   for (int b = 0; b < kGemvMaxB; ++b) acc[b] = 0.f;
-  const bf16* wr = Wt + (long long)n * K;
-  for (int k = lane * 8; k < K; k += 256) {
-    const uint4 wv = *reinterpret_cast<const uint4*>(wr + k);
-    float wf[8];
-    float2 t;
-    t = unpack_bf162(wv.x); wf[0] = t.x; wf[1] = t.y;
-    t = unpack_bf162(wv.y); wf[2] = t.x; wf[3] = t.y;
-    t = unpack_bf162(wv.z); wf[4] = t.x; wf[5] = t.y;
-    t = unpack_bf162(wv.w); wf[6] = t.x; wf[7] = t.y;
 #pragma unroll
-    for (int b = 0; b < kGemvMaxB; ++b) {
-      if (b < nb) {
-        const float* xr = x + (long long)b * ldx + k;
+  for (int i = 0; i < kMaxIter; ++i) {
+    const int k = lane * 8 + i * 256;
+    if (i < iters && k < K) {
+      float wf[8];
+      float2 t;
+      t = unpack_bf162(wv[i].x); wf[0] = t.x; wf[1] = t.y;
+      t = unpack_bf162(wv[i].y); wf[2] = t.x; wf[3] = t.y;
+      t = unpack_bf162(wv[i].z); wf[4] = t.x; wf[5] = t.y;
+      t = unpack_bf162(wv[i].w); wf[6] = t.x; wf[7] = t.y;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float xv = xr[j];
-          if (silu_in) xv = silu_f(xv);
-          acc[b] = fmaf(xv, wf[j], acc[b]);
+      for (int b = 0; b < kGemvMaxB; ++b) {
+        if (b < nb) {
+          const float4 x0 = *reinterpret_cast<const float4*>(sx + b * K + k);
+          const float4 x1 = *reinterpret_cast<const float4*>(sx + b * K + k + 4);
+          acc[b] = fmaf(x0.x, wf[0], acc[b]); acc[b] = fmaf(x0.y, wf[1], acc[b]);
+          acc[b] = fmaf(x0.z, wf[2], acc[b]); acc[b] = fmaf(x0.w, wf[3], acc[b]);
+          acc[b] = fmaf(x1.x, wf[4], acc[b]); acc[b] = fmaf(x1.y, wf[5], acc[b]);
+          acc[b] = fmaf(x1.z, wf[6], acc[b]); acc[b] = fmaf(x1.w, wf[7], acc[b]);
         }
       }
     }
@@ -335,6 +358,20 @@ __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, 
       const float s = warp_sum(acc[b]);
       if (lane == 0) y[(long long)b * ldy + n] = s + (bias ? bias[n] : 0.f);
     }
+  }
+}
+
+// [nb, H*W, ldin] fp32 (first Ct channels of every pixel) -> [nb, Ct, H*W] fp32: the NCHW view of a thin conv_out result
+__global__ void __launch_bounds__(256) nhwc_to_nchw_thin_kernel(const float* __restrict__ in, int ldin, float* __restrict__ out,
+                                                                int Ct, long long hw, long long total) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i % hw;
+    const long long nc = i / hw;
+    const int c = (int)(nc % Ct);
+    const long long n = nc / Ct;
+    out[i] = in[(n * hw + p) * ldin + c];
   }
 }
 
@@ -525,8 +562,21 @@ extern "C" int vn_timestep_sinusoid(const int64_t* t, float* out, int nb, int di
 extern "C" int vn_gemv(const float* x, int64_t ldx, const void* W, const float* bias, float* y, int64_t ldy, int nb,
                        int N, int K, int silu_in, vn_stream_t s) {
   VN_CHECK(nb >= 1 && nb <= kGemvMaxB, "gemv: batch %d not in [1,%d]", nb, kGemvMaxB);
-  VN_CHECK(K % 8 == 0, "gemv: K must be a multiple of 8");
-  VN_LAUNCH(gemv_kernel, vn_cdiv(N, 8), 256, 0, (cudaStream_t)s, x, ldx, (const bf16*)W, bias, y, ldy, nb, N, K, silu_in);
+  VN_CHECK(K % 8 == 0 && K <= kGemvMaxK, "gemv: K must be a multiple of 8 and <= %d", kGemvMaxK);
+  const int smem = nb * K * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    VN_CUDA(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvMaxB * kGemvMaxK * (int)sizeof(float)));
+    configured = true;
+  }
+  VN_LAUNCH(gemv_kernel, vn_cdiv(N, 8), 256, smem, (cudaStream_t)s, x, ldx, (const bf16*)W, bias, y, ldy, nb, N, K, silu_in);
+  return 0;
+}
+
+extern "C" int vn_nhwc_to_nchw_thin(const float* in, int64_t ldin, float* out, int nb, int Ct, int64_t hw, vn_stream_t s) {
+  VN_CHECK(nb > 0 && Ct > 0 && hw > 0 && ldin >= Ct, "nhwc_to_nchw_thin: bad arguments");
+  const long long total = (long long)nb * Ct * hw;
+  VN_LAUNCH(nhwc_to_nchw_thin_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)s, in, (int)ldin, out, Ct, (long long)hw, total);
   return 0;
 }
 

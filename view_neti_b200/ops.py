@@ -347,6 +347,13 @@ def conv_out_bwd(dy, w, dx):
           "conv_out_bwd")
 
 
+def nhwc_to_nchw_thin(src, out):
+    """src fp32 [nb, H, W, Cpad] (first Ct channels used) -> out fp32 [nb, Ct, H, W]."""
+    nb, Ct, H, W = out.shape
+    assert src.dtype == torch.float32 and out.dtype == torch.float32 and out.is_contiguous() and src.stride(-1) == 1
+    check(_abi.load().vn_nhwc_to_nchw_thin(ptr(src), _pix_ld(src), ptr(out), nb, Ct, H * W, stream()), "nhwc_to_nchw_thin")
+
+
 def timestep_sinusoid(t, out):
     check(_abi.load().vn_timestep_sinusoid(ptr(t), ptr(out), out.shape[0], out.shape[1], stream()), "timestep")
 
