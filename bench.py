@@ -434,8 +434,61 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         del coach, cond
     except Exception as e:          # the headline metric above must survive a failure of the widened path
         full_step = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    # ---- BASELINE config 4 (mode 3 multi-scene pretraining, train_m3.yaml): shared M_v + 14 per-scene M_o resident, ONE object
+    # active per step and the same one on every rank (rank 0 draws, everybody follows), all-reduce of M_v + that M_o only -----
+    mode3 = None
+    try:
+        from types import SimpleNamespace
+        from view_neti_b200.training.coach import Coach
+        from view_neti_b200.training.synthetic import build_conditioning, object_token_id, synthetic_prompt
+        n_obj = 14
+        cond3 = build_conditioning(dev, n_objects=n_obj)
+
+        class _Objects:            # the part of the mode-3 dataset the step needs: which object the next batch shows
+            learnable_mode = 3
+
+            def __init__(self):
+                self.g = torch.Generator().manual_seed(5 + rank)
+                self.current_object_idx = 0
+
+            def reset_sampled_object(self, idx=None):
+                self.current_object_idx = int(torch.randint(0, n_obj, (1,), generator=self.g)) if idx is None else int(idx)
+                return self.current_object_idx
+
+        coach3 = Coach(cfg=SimpleNamespace(learnable_mode=3), unet=model, conditioning=cond3,
+                       optimizer=torch.optim.AdamW(cond3.parameters(), lr=1e-3),
+                       generator=torch.Generator(device=dev).manual_seed(2 + rank), train_dataset=_Objects())
+        prompts = [synthetic_prompt(1, dev, object_id=object_token_id(i)) for i in range(n_obj)]
+        lat3 = torch.randn(1, 4, L, L, device=dev)
+        seen = []
+
+        def step3():
+            i = coach3.reset_sampled_object()
+            seen.append(i)
+            return coach3.train_step(lat3, prompts[i])
+
+        for _ in range(4):
+            step3()
         if world > 1:
-            raise                   # (a rank that fell out of step with the others must not hang them silently)
+            dist.barrier()
+        k3 = max(3, min(args.steps, 20))
+        m3 = torch.tensor([_time_replays(step3, k3, e0, e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(m3, op=dist.ReduceOp.MAX)
+        mode3 = {"value": world * 1e3 / float(m3), "unit": "images/s", "ms_per_step": float(m3), "steps": k3, "n_gpus": world,
+                 "object_mappers": n_obj, "objects_visited": len(set(seen)),
+                 "trainable_params": sum(p.numel() for p in cond3.parameters()),
+                 "what": "Coach.train_step in learnable mode 3: 14 object mappers + 1 view mapper resident, the step's object drawn on "
+                         "rank 0 and broadcast, gradients of M_v + the active M_o all-reduced (283 392 floats), inactive mappers untouched"}
+        if world > 1:
+            chk = torch.cat([p.detach().reshape(-1) for p in cond3.parameters()]).double().sum().reshape(1)
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            mode3["params_identical_across_ranks"] = bool(float(lo) == float(hi))
+        del coach3, cond3
+    except Exception as e:
+        mode3 = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank != 0:
         if world > 1:
@@ -544,6 +597,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                    "graph": "one CUDA graph per step"},
         "sustained": sustained,
         "roofline": roofline, "forward": forward_leg, "batch3": batch3, "cpu_baseline": cpu, "full_step": full_step,
+        "mode3": mode3,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "steps": k2, "copies": e2e_note, "api": "UNet2DConditionModel.__call__ + F.mse_loss + backward (CUDA-graph replay inside)"},
         "gpu_launches": launches_per_step * (args.steps + n_long) + e2e_launches * (k2 + pf_steps) + e2e_launches_eager + extra_launches,

@@ -169,7 +169,17 @@ typedef struct vn_attn_desc {
   void* dv; int64_t lddv, bsdv;
   double* dkv_acc;                        /* NULL or zeroed scratch, see above */
   int32_t causal;                         /* 1: key j is visible to query i only if j <= i (CLIP text encoder) */
+  void*   ws; int64_t ws_bytes;           /* fwd: scratch of vn_attention_fwd_workspace_bytes() bytes, or NULL (see below) */
 } vn_attn_desc;
+/* Forward work balancing: when the (query tile, head, image) items do not fill whole waves of SMs (64x64 latents at B = 1:
+ * 160 items on 148 SMs), the leftover items are split along the keys over all SMs and merged by a second small launch;
+ * the partial results live in `ws` (caller-owned, contents irrelevant on entry).  ws == NULL, or a shape for which
+ * vn_attention_fwd_workspace_bytes returns 0, runs one CTA per item.  Results agree to fp32 rounding. */
+size_t vn_attention_fwd_workspace_bytes(int nb, int heads, int nq, int nk);
+/* Same for the backward (dK/dV + dQ items; has_dq = 0 when dq is pruned): persistent CTAs run whole items back to back and
+ * the leftover items are split along their loops; `ws` holds plain fp32 partial tiles that a second small launch adds up in a
+ * fixed order. */
+size_t vn_attention_bwd_workspace_bytes(int nb, int heads, int nq, int nk, int has_dq);
 int vn_attention_fwd(const vn_attn_desc* d, vn_stream_t s);
 int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s);
 

@@ -238,6 +238,14 @@ def check_attention(nb, heads, nq, nk, bwd=True, use_acc=False, strided=False, c
     oref, lseref = attn_ref(qr, kr, vr, heads, 0.125, causal=causal)
     lab = f"attn nb{nb} h{heads} nq{nq} nk{nk} acc{int(use_acc)} st{int(strided)} causal{int(causal)}"
     out = [(lab + " o", rel(o, oref), 8e-3), (lab + " lse", rel(lse, lseref), 1e-4)]
+    # the balanced schedule (leftover items split along the keys, merged by the fix-up launch) against the plain one
+    need = ops.attention_fwd_workspace_bytes(nb, heads, nq, nk)
+    if need > 0:
+        wsb = torch.full((need,), 0xFF, dtype=torch.uint8, device=DEV)          # NaN bit patterns: every slot must be written
+        o2, lse2 = torch.full_like(o, float("nan")), torch.full_like(lse, float("nan"))
+        ops.attention_fwd(q, k, v, o2, lse2, heads, causal=causal, ws=wsb)
+        out += [(lab + " o (balanced vs reference)", rel(o2, oref), 8e-3), (lab + " lse (balanced)", rel(lse2, lseref), 1e-4),
+                (lab + " o (balanced vs plain)", rel(o2, o), 4e-3)]
     if bwd:
         d_o = rnd(nb, nq, Cc, seed=28).to(BF)
         oref.backward(d_o.float())
@@ -249,9 +257,24 @@ def check_attention(nb, heads, nq, nk, bwd=True, use_acc=False, strided=False, c
         ops.attention_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, heads, dkv_acc=acc, causal=causal)
         out += [(lab + " dq", rel(dq, qr.grad), 1.2e-2), (lab + " dk", rel(dk, kr.grad), 1.2e-2),
                 (lab + " dv", rel(dv, vr.grad), 1.2e-2)]
+        # the persistent schedule (whole items back to back per CTA, leftover items split, parts added by the fix-up launch)
+        needb = ops.attention_bwd_workspace_bytes(nb, heads, nq, nk, True)
+        if needb > 0 and not use_acc:
+            wsb = torch.full((needb,), 0xFF, dtype=torch.uint8, device=DEV)
+            dq2, dk2, dv2 = (torch.full_like(t, float("nan")) for t in (dq, dk, dv))
+            ops.attention_bwd(q, k, v, o, lse, d_o, delta, dq2, dk2, dv2, heads, causal=causal, ws=wsb)
+            out += [(lab + " dq (persistent)", rel(dq2, qr.grad), 1.2e-2), (lab + " dk (persistent)", rel(dk2, kr.grad), 1.2e-2),
+                    (lab + " dv (persistent)", rel(dv2, vr.grad), 1.2e-2), (lab + " dq persistent vs plain", rel(dq2, dq), 4e-3)]
+            needp = ops.attention_bwd_workspace_bytes(nb, heads, nq, nk, False)          # dq pruned: only dK/dV items
+            if needp > 0:
+                wsp = torch.full((needp,), 0xFF, dtype=torch.uint8, device=DEV)
+                dk3, dv3 = torch.full_like(dk, float("nan")), torch.full_like(dv, float("nan"))
+                ops.attention_bwd(q, k, v, o, lse, d_o, delta, None, dk3, dv3, heads, causal=causal, ws=wsp)
+                out += [(lab + " dk (persistent, dq pruned)", rel(dk3, kr.grad), 1.2e-2),
+                        (lab + " dv (persistent, dq pruned)", rel(dv3, vr.grad), 1.2e-2)]
         if use_acc:
             torch.cuda.synchronize()
-            out.append((lab + " acc-clean", float(ws().dkv.abs().max()), 0.0))
+            out.append((lab + " acc-clean", float(acc.abs().max()), 0.0))
     return out
 
 
@@ -428,6 +451,13 @@ def all_checks():
     L.append((check_geglu, dict(rows=1024, Fd=2560)))
     for (nb, heads, n) in [(1, 5, 4096), (1, 10, 1024), (2, 20, 256), (1, 20, 64), (1, 4, 3072)]:
         L.append((check_attention, dict(nb=nb, heads=heads, nq=n, nk=n, strided=(n == 1024))))
+    # shapes whose work items leave a small last wave on 148 SMs: balanced forward schedule (key-split leftover items)
+    L.append((check_attention, dict(nb=3, heads=5, nq=4096, nk=4096, bwd=False)))           # 480 items: 3 rounds + 36 left
+    L.append((check_attention, dict(nb=1, heads=5, nq=4000, nk=4000)))                      # ragged last tiles, 160 items
+    L.append((check_attention, dict(nb=2, heads=10, nq=1024, nk=1024, strided=True)))       # 160 items, 8 key blocks
+    L.append((check_attention, dict(nb=1, heads=10, nq=1024, nk=1024)))                     # bwd: 80 + 80 items = 148 + 12
+    L.append((check_attention, dict(nb=1, heads=3, nq=3200, nk=3200, causal=True)))         # causal across key / query parts
+    L.append((check_attention, dict(nb=10, heads=16, nq=128, nk=1024, bwd=False, causal=True)))  # causal + key parts with no visible key
     for (nb, heads, n) in [(1, 5, 4096), (2, 10, 1024), (1, 20, 256), (1, 20, 64)]:
         L.append((check_attention, dict(nb=nb, heads=heads, nq=n, nk=77, use_acc=True)))
     L.append((check_attention, dict(nb=1, heads=2, nq=200, nk=77, use_acc=False)))

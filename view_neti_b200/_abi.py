@@ -56,6 +56,7 @@ class AttnDesc(C.Structure):
         ("dv", C.c_void_p), ("lddv", C.c_int64), ("bsdv", C.c_int64),
         ("dkv_acc", C.c_void_p),
         ("causal", C.c_int32),
+        ("ws", C.c_void_p), ("ws_bytes", C.c_int64),
     ]
 
 
@@ -86,6 +87,8 @@ SIGNATURES = {
     "vn_layernorm_fwd_f32": (C.c_int, [_P, _L, _P, _P, _F, _P, _L, _P, _I, _I, _P]),
     "vn_layernorm_bwd_f32": (C.c_int, [_P, _L, _P, _L, _P, _P, _P, _L, _P, _L, _P, _L, _I, _I, _P]),
     "vn_nhwc_to_nchw_thin": (C.c_int, [_P, _L, _P, _I, _I, _L, _P]),
+    "vn_attention_fwd_workspace_bytes": (C.c_size_t, [_I, _I, _I, _I]),
+    "vn_attention_bwd_workspace_bytes": (C.c_size_t, [_I, _I, _I, _I, _I]),
     "vn_geglu_fwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _P]),
     "vn_geglu_bwd": (C.c_int, [_P, _L, _P, _L, _P, _L, _I, _I, _P]),
     "vn_gelu_fwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _P]),

@@ -13,7 +13,14 @@
 // Two kernels (S recomputed twice) instead of one with global atomics on dQ: results stay deterministic.
 // Cross-attention (nk = 77) has a single key tile: the dKV kernel then splits the query range over CTAs and adds its
 // partial dK / dV into an fp64 scratch (order-independent), finished by a small conversion kernel.
+// PERSISTENT schedule (self-attention whose 2 * tiles * heads * images work items do not fill whole waves of SMs - 64x64
+// latents at B = 1: 160 dK/dV + 160 dQ items on 148 SMs = 2.16 waves, i.e. three): grid = #SMs, CTA c runs the whole items
+// c, c + #SMs, ... one after the other and then one PART of a leftover item (the leftover items' loops are cut into equal
+// ranges spread over all CTAs); a part leaves a plain fp32 partial tile in a caller-provided scratch and
+// attn_bwd_fixup_kernel adds the parts of each leftover item up in a fixed order (deterministic, no atomics).
 #include "vn_tma.cuh"
+
+#include <stdlib.h>
 
 namespace {
 
@@ -35,6 +42,10 @@ struct BwdParams {
   int qsplits, qtiles_per_split;
   int n_dkv, ktiles, qtiles;        // fused-grid decomposition
   int causal;                       // key j visible to query i only if j <= i
+  // persistent schedule: items [0, n_dkv) are dK/dV items, [n_dkv, items) dQ items; the last n_left items are split
+  int persistent, items, rounds, n_left, parts;
+  int left_dkv;                     // how many of the n_left split items are dK/dV items (the rest are dQ items)
+  float* part;                      // [n_left * parts][2][128][64] fp32 partial tiles (dQ: [0]; dK/dV: [0] = dV, [1] = dK)
 };
 
 __device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr) {
@@ -50,6 +61,11 @@ __host__ __device__ constexpr uint32_t idesc(int m, int n, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// a persistent CTA runs several bodies with different shared-memory layouts: a body retires its barrier words before the next
+// one may reuse the bytes for data
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -87,11 +103,15 @@ __device__ __forceinline__ void store_row8(uint8_t* row, int chunk, int r, const
 // dK, dV
 // =================================================================================================
 constexpr int DKV_STAGE_BYTES = 2 * TILE_BYTES + 2 * T * 4;        // Q, dO, lse, delta
-constexpr int DKV_SMEM = 2 * TILE_BYTES /*K,V*/ + 2 * DKV_STAGE_BYTES + 2 * 2 * TILE_BYTES /*P^T, dS^T*/ + 256 + 1024;
+constexpr int kMaxSegments = 4;                    // bodies a persistent CTA may run (each on its own block of 16 barrier words)
+constexpr int DKV_SMEM = 2 * TILE_BYTES /*K,V*/ + 2 * DKV_STAGE_BYTES + 2 * 2 * TILE_BYTES /*P^T, dS^T*/ + kMaxSegments * 128 + 1024;
 
+// seg: which barrier block of the CTA to use (a persistent CTA runs several bodies one after the other, each on fresh
+// mbarriers); t_count > 0: loop over query tiles [t_begin, t_begin + t_count) only; slot >= 0: leave fp32 partial tiles
 template <bool ATOMIC>
 __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
-                                         const CUtensorMap& tmdO, const BwdParams& p, int bx, int by, int bz) {
+                                         const CUtensorMap& tmdO, const BwdParams& p, uint32_t tmem_base, int bx, int by, int bz,
+                                         int seg = 0, int t_begin = 0, int t_count = 0, int slot = -1) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
@@ -99,21 +119,20 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
   uint8_t* sP = sV + TILE_BYTES;                     // P^T  : two [128 keys x 64 queries] blocks
   uint8_t* sdS = sP + 2 * TILE_BYTES;                // dS^T : same
   uint8_t* sStage = sdS + 2 * TILE_BYTES;            // 2 x {Q tile, dO tile, lse[128], delta[128]}
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 2 * DKV_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 2 * DKV_STAGE_BYTES) + seg * 16;
   uint64_t* kv_full = bars;
   uint64_t* st_full = bars + 1;                      // [2]
   uint64_t* st_empty = bars + 3;                     // [2]
   uint64_t* s_full = bars + 5;                       // [2] per 64-query half
   uint64_t* p_full = bars + 7;                       // [2]
   uint64_t* acc_full = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = bx * T, h = by;
   const int b = bz / p.qsplits, split = bz % p.qsplits;
   const int total_qt = (p.nq + T - 1) / T;
-  const int qt_begin = split * p.qtiles_per_split;
-  const int nt = min(total_qt, qt_begin + p.qtiles_per_split) - qt_begin;      // host guarantees >= 1
+  const int qt_begin = t_count > 0 ? t_begin : split * p.qtiles_per_split;
+  const int nt = t_count > 0 ? t_count : min(total_qt, qt_begin + p.qtiles_per_split) - qt_begin;   // host guarantees >= 1
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
@@ -125,11 +144,9 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
     mbar_init(acc_full, 1);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();                                   // barrier words initialised (TMEM is allocated once per CTA by the kernel)
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
   const uint32_t tST = tmem_base, tdPT = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320;
   const long long sidx = ((long long)b * p.heads + h) * p.nq;
   pdl_wait();
@@ -265,7 +282,13 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
     tmem_ld_wait();
     tc_fence_before();
     const int krow = k0 + r;
-    if (krow < p.nk) {
+    if (slot >= 0) {
+      float* dst = p.part + (((long long)slot * 2 + (hf == 0 ? 0 : 1)) * T + r) * D;
+#pragma unroll
+      for (int c = 0; c < 64; c += 4)
+        *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(acc[c]), __uint_as_float(acc[c + 1]),
+                                                          __uint_as_float(acc[c + 2]), __uint_as_float(acc[c + 3]));
+    } else if (krow < p.nk) {
       if (ATOMIC) {
         const long long C = (long long)p.heads * D;
         double* dst = p.dkv_acc + (hf == 0 ? (long long)p.nb * p.nk * C : 0) + ((long long)b * p.nk + krow) * C + h * D;
@@ -288,37 +311,39 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (p.persistent) {
+    if (threadIdx.x == 0)
+      for (int i = 0; i < 10; ++i) mbar_inval(bars + i);
+    __syncthreads();
   }
 }
 
 // =================================================================================================
 // dQ
 // =================================================================================================
-constexpr int DQ_SMEM = 2 * TILE_BYTES /*Q,dO*/ + 2 * 2 * TILE_BYTES /*K,V x 2 stages*/ + 2 * TILE_BYTES /*dS*/ + 256 + 1024;
+constexpr int DQ_SMEM = 2 * TILE_BYTES /*Q,dO*/ + 2 * 2 * TILE_BYTES /*K,V x 2 stages*/ + 2 * TILE_BYTES /*dS*/ + kMaxSegments * 128 + 1024;
 
 __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
-                                        const CUtensorMap& tmdO, const BwdParams& p, int bx, int by, int bz) {
+                                        const CUtensorMap& tmdO, const BwdParams& p, uint32_t tmem_base, int bx, int by, int bz,
+                                        int seg = 0, int t_begin = 0, int t_count = 0, int slot = -1) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sdO = sQ + TILE_BYTES;
   uint8_t* sdS = sdO + TILE_BYTES;                   // two [128 queries x 64 keys] blocks
   uint8_t* sKV = sdS + 2 * TILE_BYTES;               // stage s: K at s*2*TILE, V right after
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + 4 * TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + 4 * TILE_BYTES) + seg * 16;
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;                      // [2]
   uint64_t* kv_empty = bars + 3;                     // [2]
   uint64_t* s_full = bars + 5;                       // [2] per 64-key half
   uint64_t* p_full = bars + 7;                       // [2]
   uint64_t* acc_full = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = bx * T, h = by, b = bz;
-  const int nt = (p.nk + T - 1) / T;
+  const int kt0 = t_count > 0 ? t_begin : 0;                                   // first key tile of this body's range
+  const int nt = t_count > 0 ? t_count : (p.nk + T - 1) / T;                   // key tiles in the range
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
@@ -330,11 +355,9 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
     mbar_init(acc_full, 1);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();                                   // barrier words initialised (TMEM is allocated once per CTA by the kernel)
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdQ = tmem_base + 256;
   pdl_wait();
 
@@ -347,8 +370,8 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
         const int s = j & 1;
         mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-        tma_load_3d(sKV + s * 2 * TILE_BYTES, &tmK, &kv_full[s], h * D, j * T, b);
-        tma_load_3d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &tmV, &kv_full[s], h * D, j * T, b);
+        tma_load_3d(sKV + s * 2 * TILE_BYTES, &tmK, &kv_full[s], h * D, (kt0 + j) * T, b);
+        tma_load_3d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &tmV, &kv_full[s], h * D, (kt0 + j) * T, b);
       }
     }
     __syncwarp();
@@ -403,7 +426,7 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
         tmem_ld32(tS + lane_addr + cbase, sv);
         tmem_ld32(tdP + lane_addr + cbase, dp);
         tmem_ld_wait();
-        const int kvalid = p.nk - j * T - cbase;
+        const int kvalid = p.nk - (kt0 + j) * T - cbase;
         uint8_t* drow = sdS + hh * TILE_BYTES + r * 128;
         const float2 sl2v = make_float2(sl2, sl2), scv = make_float2(p.scale, p.scale);
         const float2 nlv = make_float2(nlse2, nlse2), ndv = make_float2(ndl, ndl);
@@ -424,7 +447,7 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
               if (g * 8 + c >= kvalid) de[c] = 0.f;
           }
           if (p.causal) {                              // keys after this query row are masked
-            const int klast = row - (j * T + cbase + g * 8);
+            const int klast = row - ((kt0 + j) * T + cbase + g * 8);
 #pragma unroll
             for (int c = 0; c < 8; ++c)
               if (c > klast) de[c] = 0.f;
@@ -442,7 +465,13 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
     tmem_ld32(tdQ + lane_addr + hf * 32, acc);
     tmem_ld_wait();
     tc_fence_before();
-    if (row < p.nq) {
+    if (slot >= 0) {
+      float* dst = p.part + (((long long)slot * 2) * T + r) * D + hf * 32;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4)
+        *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(acc[c]), __uint_as_float(acc[c + 1]),
+                                                          __uint_as_float(acc[c + 2]), __uint_as_float(acc[c + 3]));
+    } else if (row < p.nq) {
       bf16* dst = p.dq + (long long)b * p.bsdq + (long long)row * p.lddq + h * D + hf * 32;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -457,10 +486,24 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (p.persistent) {
+    if (threadIdx.x == 0)
+      for (int i = 0; i < 10; ++i) mbar_inval(bars + i);
+    __syncthreads();
   }
+}
+
+// Persistent schedule, position in the work order -> item id (id < n_dkv: dK/dV item, else dQ item id - n_dkv).  Order:
+// whole dK/dV items, whole dQ items, then the split items (left_dkv dK/dV items, the rest dQ items): a dK/dV item takes
+// ~1.5x as long as a dQ item (four products per tile pair against three), so every CTA should get one of each kind in its
+// whole rounds and the split items should come from both kinds.
+__device__ __forceinline__ int item_at(const BwdParams& p, int pos) {
+  const int n_dq = p.items - p.n_dkv;
+  const int A = p.n_dkv - p.left_dkv, B = n_dq - (p.n_left - p.left_dkv);
+  if (pos < A) return pos;
+  if (pos < A + B) return p.n_dkv + (pos - A);
+  if (pos < A + B + p.left_dkv) return A + (pos - A - B);
+  return p.n_dkv + B + (pos - A - B - p.left_dkv);
 }
 
 // One launch for both directions: CTAs [0, n_dkv) run the dK/dV body, the rest the dQ body.  With ~160 work items of each
@@ -473,17 +516,121 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
                                                                    const __grid_constant__ CUtensorMap tmdO,
                                                                    const BwdParams p) {
   pdl_trigger();
-  int id = blockIdx.x;
-  if (id < p.n_dkv) {
-    const int bx = id % p.ktiles; id /= p.ktiles;
-    const int by = id % p.heads;
-    dkv_body<ATOMIC>(tmQ, tmK, tmV, tmdO, p, bx, by, id / p.heads);
-  } else {
-    id -= p.n_dkv;
-    const int bx = id % p.qtiles; id /= p.qtiles;
-    const int by = id % p.heads;
-    dq_body(tmQ, tmK, tmV, tmdO, p, bx, by, id / p.heads);
+  // TMEM is allocated ONCE per CTA (the permit is relinquished right after, so a second tcgen05.alloc would be illegal);
+  // both bodies lay their accumulators out inside the same 512 columns
+  __shared__ uint32_t s_tmem;
+  if ((threadIdx.x >> 5) == 1) tmem_alloc<TMEM_COLS>(&s_tmem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+  auto release_tmem = [&]() {
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 1) {
+      tc_fence_after();
+      tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+  };
+  if (!p.persistent) {
+    int id = blockIdx.x;
+    if (id < p.n_dkv) {
+      const int bx = id % p.ktiles; id /= p.ktiles;
+      const int by = id % p.heads;
+      dkv_body<ATOMIC>(tmQ, tmK, tmV, tmdO, p, tmem_base, bx, by, id / p.heads);
+    } else {
+      id -= p.n_dkv;
+      const int bx = id % p.qtiles; id /= p.qtiles;
+      const int by = id % p.heads;
+      dq_body(tmQ, tmK, tmV, tmdO, p, tmem_base, bx, by, id / p.heads);
+    }
+    release_tmem();
+    return;
   }
+  // persistent: whole items blockIdx.x + seg * gridDim.x, then (CTAs below n_left * parts) one part of a leftover item
+  const int nseg = p.rounds + ((int)blockIdx.x < p.n_left * p.parts ? 1 : 0);
+  for (int seg = 0; seg < nseg; ++seg) {
+    int id, t_begin = 0, t_count = 0, slot = -1;
+    if (seg < p.rounds) {
+      id = item_at(p, (int)blockIdx.x + seg * (int)gridDim.x);
+    } else {
+      const int li = (int)blockIdx.x / p.parts, part = (int)blockIdx.x - li * p.parts;
+      id = item_at(p, p.items - p.n_left + li);
+      const int tiles = id < p.n_dkv ? p.qtiles : p.ktiles;          // the loop of a dK/dV item runs over query tiles
+      t_begin = part * tiles / p.parts;
+      t_count = (part + 1) * tiles / p.parts - t_begin;
+      slot = (int)blockIdx.x;
+    }
+    if (id < p.n_dkv) {
+      const int bx = id % p.ktiles; id /= p.ktiles;
+      const int by = id % p.heads;
+      dkv_body<false>(tmQ, tmK, tmV, tmdO, p, tmem_base, bx, by, id / p.heads, seg, t_begin, t_count, slot);
+    } else {
+      id -= p.n_dkv;
+      const int bx = id % p.qtiles; id /= p.qtiles;
+      const int by = id % p.heads;
+      dq_body(tmQ, tmK, tmV, tmdO, p, tmem_base, bx, by, id / p.heads, seg, t_begin, t_count, slot);
+    }
+  }
+  release_tmem();
+}
+
+// Adds the parts of every leftover item of the persistent schedule (fixed order) and writes the bf16 rows:
+// thread = (tile row, 8 columns), 16 rows per CTA, 8 CTAs per leftover item.
+__global__ void __launch_bounds__(128) attn_bwd_fixup_kernel(const BwdParams p) {
+  pdl_trigger();
+  pdl_wait();
+  const int li = (int)blockIdx.x >> 3;
+  const int r = (((int)blockIdx.x & 7) << 4) + ((int)threadIdx.x >> 3), cg = threadIdx.x & 7;
+  int id = item_at(p, p.items - p.n_left + li);
+  const bool is_dkv = id < p.n_dkv;
+  if (!is_dkv) id -= p.n_dkv;
+  const int tiles = is_dkv ? p.ktiles : p.qtiles;
+  const int bx = id % tiles; id /= tiles;
+  const int h = id % p.heads, b = id / p.heads;
+  const int row = bx * T + r;
+  if (row >= (is_dkv ? p.nk : p.nq)) return;
+  const int nplanes = is_dkv ? 2 : 1;
+  for (int pl = 0; pl < nplanes; ++pl) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 4
+    for (int q = 0; q < p.parts; ++q) {
+      const float* src = p.part + ((((long long)li * p.parts + q) * 2 + pl) * T + r) * D + cg * 8;
+      const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+      acc[0] += v0.x; acc[1] += v0.y; acc[2] += v0.z; acc[3] += v0.w;
+      acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
+    }
+    uint4 w;
+    w.x = pack_bf162(acc[0], acc[1]); w.y = pack_bf162(acc[2], acc[3]);
+    w.z = pack_bf162(acc[4], acc[5]); w.w = pack_bf162(acc[6], acc[7]);
+    bf16* dst = !is_dkv ? p.dq + (long long)b * p.bsdq + (long long)row * p.lddq
+                        : (pl == 0 ? p.dv + (long long)b * p.bsdv + (long long)row * p.lddv
+                                   : p.dk + (long long)b * p.bsdk + (long long)row * p.lddk);
+    *reinterpret_cast<uint4*>(dst + h * D + cg * 8) = w;
+  }
+}
+
+// Persistent-schedule decision shared by vn_attention_bwd and vn_attention_bwd_workspace_bytes.
+void bwd_split(int nb, int heads, int nq, int nk, int has_dq, int* n_left, int* parts) {
+  *n_left = 0; *parts = 0;
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("VN_ATTN_SPLIT"); enabled = e ? atoi(e) : 1; }
+  if (!enabled) return;
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  const int ktiles = vn_cdiv(nk, T), qtiles = vn_cdiv(nq, T);
+  const int items = ktiles * heads * nb + (has_dq ? qtiles * heads * nb : 0);
+  const int left = items % sms;
+  const int tiles = ktiles < qtiles ? ktiles : qtiles;
+  if (items <= sms || left == 0 || left > sms / 2 || tiles < 4 || items / sms + 1 > kMaxSegments) return;
+  int q = sms / left;
+  if (q > tiles / 2) q = tiles / 2;               // at least two tiles per part
+  if (q < 2) return;
+  *n_left = left; *parts = q;
 }
 
 // delta[b,h,n] = sum_d dO * O : one 16-byte vector per lane, 8 lanes per (row, head)
@@ -603,8 +750,30 @@ extern "C" int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s) {
   p.ktiles = ktiles; p.qtiles = qtiles;
   p.n_dkv = ktiles * d->heads * d->nb * splits;
   const int n_dq = d->dq ? qtiles * d->heads * d->nb : 0;
-  const unsigned grid = (unsigned)(p.n_dkv + n_dq);
-  if (splits > 1) {
+  unsigned grid = (unsigned)(p.n_dkv + n_dq);
+  if (splits == 1 && base_ctas >= 148) {
+    int n_left = 0, parts = 0;
+    bwd_split(d->nb, d->heads, d->nq, d->nk, d->dq != nullptr, &n_left, &parts);
+    const size_t need = (size_t)n_left * parts * 2 * T * D * sizeof(float);
+    if (parts > 0 && d->ws != nullptr && (size_t)d->ws_bytes >= need) {
+      int sms = 0, dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      p.persistent = 1;
+      p.items = (int)grid;
+      p.rounds = p.items / sms;
+      p.n_left = n_left; p.parts = parts;
+      p.left_dkv = n_dq > 0 ? n_left / 2 : n_left;
+      if (p.left_dkv > p.n_dkv) p.left_dkv = p.n_dkv;
+      if (n_left - p.left_dkv > n_dq) p.left_dkv = n_left - n_dq;
+      p.part = reinterpret_cast<float*>(d->ws);
+      grid = (unsigned)sms;
+    }
+  }
+  if (p.persistent) {
+    VN_LAUNCH(attn_bwd_tc_kernel<false>, grid, kThreads, SMEM, st, tq, tk, tv, tdo, p);
+    VN_LAUNCH(attn_bwd_fixup_kernel, p.n_left * 8, 128, 0, st, p);
+  } else if (splits > 1) {
     VN_LAUNCH(attn_bwd_tc_kernel<true>, grid, kThreads, SMEM, st, tq, tk, tv, tdo, p);
     const long long pairs = (long long)d->nb * d->nk * d->heads * D / 2;
     int blocks = (int)vn_cdiv64(pairs, 256);
@@ -614,4 +783,10 @@ extern "C" int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s) {
     VN_LAUNCH(attn_bwd_tc_kernel<false>, grid, kThreads, SMEM, st, tq, tk, tv, tdo, p);
   }
   return 0;
+}
+
+extern "C" size_t vn_attention_bwd_workspace_bytes(int nb, int heads, int nq, int nk, int has_dq) {
+  int n_left = 0, parts = 0;
+  bwd_split(nb, heads, nq, nk, has_dq, &n_left, &parts);
+  return (size_t)n_left * parts * 2 * T * D * sizeof(float);
 }

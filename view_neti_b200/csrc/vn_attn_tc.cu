@@ -3,7 +3,11 @@
 // Same contract as the reference's attention core (models/xti_attention_processor.py:44-50: head split, fp32 logits
 // with alpha = scale, softmax, bmm, head merge), with K and V taken from different tensors (XTI).
 //
-// CTA = one (128-query tile, head, image), one CTA per SM.
+// Work item = one (128-query tile, head, image); one CTA per SM.  When the items do not fill whole waves (64x64 latents,
+// B = 1: 160 items on 148 SMs = two waves, the second one 8 % full) the launch is PERSISTENT over #SMs CTAs: every CTA
+// runs items / #SMs whole items and the items % #SMs leftover ones are split along the KEYS into equal parts that are
+// spread over all CTAs; a part leaves an unnormalised partial (O, m, l) in a caller-provided scratch and
+// attn_fwd_fixup_kernel merges the parts of each leftover item (log-sum-exp) - 2 waves become ~1.1.
 //   warp 0     TMA producer : Q tile once, then (K, V) tiles of 128 keys through a 3-stage ring (3-D tensor maps
 //                             {64 d, rows, image}: rows beyond nq / nk are zero-filled, head picked by the column offset)
 //   warp 1     MMA issuer   : S(j) = Q K(j)^T  (tcgen05.mma 128x128x16, operands K-major) -> TMEM S[j&1]   (2 x 128 columns)
@@ -20,6 +24,8 @@
 //                             (log-sum-exp merge through shared memory).  Two softmax warps per scheduler hide the ALU /
 //                             MUFU latencies that a single warp cannot.
 #include "vn_tma.cuh"
+
+#include <stdlib.h>
 
 namespace {
 
@@ -39,7 +45,36 @@ struct FwdParams {
   float scale;
   bf16* o; long long ldo, bso;
   float* lse;
+  // work decomposition: CTA c runs the whole items c, c + grid, ... (`rounds` of them) and then, if c < n_left * parts,
+  // key part c % parts of leftover item (items - n_left + c / parts)
+  int nqt, items, rounds, n_left, parts;
+  float* part_o;        // [n_left * parts][128][64] unnormalised partial outputs
+  float* part_ml;       // [n_left * parts][128][2]  (running max in the log2 domain, running sum)
 };
+
+struct Segment {
+  int q0, h, b;         // query-tile origin, head, image
+  int kb0, kb1;         // key blocks [kb0, kb1)
+  int slot;             // partial slot, -1 for a whole item
+};
+__device__ __forceinline__ int num_segments(const FwdParams& p) {
+  return p.rounds + ((int)blockIdx.x < p.n_left * p.parts ? 1 : 0);
+}
+__device__ __forceinline__ Segment segment(const FwdParams& p, int seg, int nt) {
+  Segment g;
+  int item;
+  if (seg < p.rounds) {
+    item = (int)blockIdx.x + seg * (int)gridDim.x;
+    g.kb0 = 0; g.kb1 = nt; g.slot = -1;
+  } else {
+    const int li = (int)blockIdx.x / p.parts, part = (int)blockIdx.x - li * p.parts;
+    item = p.items - p.n_left + li;
+    g.kb0 = part * nt / p.parts; g.kb1 = (part + 1) * nt / p.parts; g.slot = (int)blockIdx.x;
+  }
+  const int qt = item % p.nqt, hb = item / p.nqt;
+  g.q0 = qt * 128; g.h = hb % p.heads; g.b = hb / p.heads;
+  return g;
+}
 
 // MN-major shared-memory operand descriptor, 128B swizzle: rows are K (128 B apart), 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
@@ -79,15 +114,17 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
   uint64_t* s_full = kv_empty + KV_STAGES;                 // [2]
   uint64_t* p_full = s_full + 2;                           // [2]
   uint64_t* pv_full = p_full + 2;                          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + 2);
+  uint64_t* q_empty = pv_full + 2;                         // every S product of a segment has read the Q tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const int nt = (p.nk + BKV - 1) / BKV;
+  const int nseg = num_segments(p);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 256); mbar_init(&pv_full[s], 1); }
     mbar_fence_init();
@@ -101,14 +138,19 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, TILE_BYTES);
-      tma_load_3d(sQ, &tmQ, q_full, h * D, q0, b);
-      for (int j = 0; j < nt; ++j) {
-        const int s = j % KV_STAGES;
-        mbar_wait(&kv_empty[s], ((j / KV_STAGES) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-        tma_load_3d(sKV + s * 2 * TILE_BYTES, &tmK, &kv_full[s], h * D, j * BKV, b);
-        tma_load_3d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &tmV, &kv_full[s], h * D, j * BKV, b);
+      int it = 0;                                  // iterations issued so far, over all segments (barrier phases run on)
+      for (int seg = 0; seg < nseg; ++seg) {
+        const Segment g = segment(p, seg, nt);
+        if (seg > 0) mbar_wait(q_empty, (seg - 1) & 1);      // the previous segment's S products are done with sQ
+        mbar_expect_tx(q_full, TILE_BYTES);
+        tma_load_3d(sQ, &tmQ, q_full, g.h * D, g.q0, g.b);
+        for (int kb = g.kb0; kb < g.kb1; ++kb, ++it) {
+          const int s = it % KV_STAGES;
+          mbar_wait(&kv_empty[s], ((it / KV_STAGES) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+          tma_load_3d(sKV + s * 2 * TILE_BYTES, &tmK, &kv_full[s], g.h * D, kb * BKV, g.b);
+          tma_load_3d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &tmV, &kv_full[s], g.h * D, kb * BKV, g.b);
+        }
       }
     }
     __syncwarp();
@@ -117,7 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
       constexpr uint32_t idesc_s = idesc_bf16(BQ, BKV, 0);
       constexpr uint32_t idesc_pv = idesc_bf16(BQ, D, 1);
       const uint32_t aQ = smem_u32(sQ);
-      auto issue_s = [&](int j) {
+      auto issue_s = [&](int j, bool last_of_segment) {
         // S[j&1] is free: the softmax threads arrived on p_full(j-2) before PV(j-2) was issued (program order below)
         const int s = j % KV_STAGES;
         mbar_wait(&kv_full[s], (j / KV_STAGES) & 1);
@@ -129,11 +171,17 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
           umma_bf16(tS, umma_desc_k_sw128(aQ) + (uint64_t)(k * 2), umma_desc_k_sw128(aK) + (uint64_t)(k * 2), idesc_s,
                     k ? 1u : 0u);
         umma_commit(&s_full[j & 1]);
+        if (last_of_segment) umma_commit(q_empty);
       };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      for (int j = 0; j < nt; ++j) {
-        if (j + 1 < nt) issue_s(j + 1);
+      int it0 = 0;
+      for (int seg = 0; seg < nseg; ++seg) {
+      const Segment g = segment(p, seg, nt);
+      const int n = g.kb1 - g.kb0;
+      mbar_wait(q_full, seg & 1);
+      issue_s(it0, n == 1);
+      for (int jj = 0; jj < n; ++jj) {
+        const int j = it0 + jj;                    // iteration index over all segments: buffer parities and phases
+        if (jj + 1 < n) issue_s(j + 1, jj + 2 == n);
         // PV(j) = P(j) V(j)
         const int s = j % KV_STAGES;
         mbar_wait(&p_full[j & 1], (j >> 1) & 1);
@@ -151,6 +199,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
         umma_commit(&kv_empty[s]);           // K(j) (read by S(j), issued earlier) and V(j) are no longer needed
         umma_commit(&pv_full[j & 1]);
       }
+      it0 += n;
+      }
     }
     __syncwarp();
   } else {
@@ -160,6 +210,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
     const int r = qd * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     const float sl2 = p.scale * kLog2e;
+    int it0 = 0;
+    for (int seg = 0; seg < nseg; ++seg) {
+    const Segment g = segment(p, seg, nt);
+    const int q0 = g.q0, h = g.h, b = g.b;
+    const int nloc = g.kb1 - g.kb0;
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
     float o[D];
 #pragma unroll
@@ -182,7 +237,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
       }
     };
 
-    for (int j = 0; j < nt; ++j) {
+    for (int jj = 0; jj < nloc; ++jj) {
+      const int j = it0 + jj;                      // iteration index over all segments (buffer parities, phases)
+      const int kb = g.kb0 + jj;                   // key block
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t tS = tmem_base + (uint32_t)((j & 1) * BKV + hf * 64) + lane_addr;
@@ -193,8 +250,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
         tmem_ld32(tS, c0); tmem_ld32(tS + 32, c1);
         tmem_ld_wait();
       }
-      int kvalid = p.nk - j * BKV - hf * 64;           // keys of this half-tile that exist (may be <= 0 on the last tile)
-      if (p.causal) kvalid = min(kvalid, q0 + r + 1 - j * BKV - hf * 64);   // ... and that query row q0 + r may see
+      int kvalid = p.nk - kb * BKV - hf * 64;          // keys of this half-tile that exist (may be <= 0 on the last tile)
+      if (p.causal) kvalid = min(kvalid, q0 + r + 1 - kb * BKV - hf * 64);  // ... and that query row q0 + r may see
       if (kvalid < 64) {
 #pragma unroll
         for (int i = 0; i < 64; ++i)
@@ -233,10 +290,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
       tc_fence_before();                 // my TMEM reads of S(j) are done
       fence_async_smem();                // my P writes are visible to the tensor core (async proxy)
       mbar_arrive(&p_full[j & 1]);
-      if (j > 0) accumulate_pv(j - 1, alpha_prev);     // overlaps PV(j) / S(j+1) on the tensor pipe
+      if (jj > 0) accumulate_pv(j - 1, alpha_prev);    // overlaps PV(j) / S(j+1) on the tensor pipe
       alpha_prev = alpha;
     }
-    accumulate_pv(nt - 1, alpha_prev);
+    accumulate_pv(it0 + nloc - 1, alpha_prev);
     tc_fence_before();
     // ---- merge the two key halves of each row: half 1 parks (O, m, l) in shared memory (the P tiles are dead now) ----
     float* xch = reinterpret_cast<float*>(sP);          // [128 rows][67] fp32, odd stride => conflict-free
@@ -249,7 +306,18 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const int row = q0 + r;
-    if (hf == 0 && row < p.nq) {
+    if (hf == 0 && g.slot >= 0) {
+      // key part of a leftover item: park the merged, UNNORMALISED (O, m, l) of this row; attn_fwd_fixup_kernel finishes
+      const float m1 = xch[r * 67 + 64], l1 = xch[r * 67 + 65];
+      const float m = fmaxf(m_run, m1);                // -inf if this part holds no key the row may see (causal)
+      const float a0 = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m), a1 = (m1 == -INFINITY) ? 0.f : ex2_approx(m1 - m);
+      float* po = p.part_o + ((long long)g.slot * BQ + r) * D;
+#pragma unroll
+      for (int i = 0; i < D; i += 4)
+        *reinterpret_cast<float4*>(po + i) = make_float4(o[i] * a0 + xch[r * 67 + i] * a1, o[i + 1] * a0 + xch[r * 67 + i + 1] * a1,
+                                                         o[i + 2] * a0 + xch[r * 67 + i + 2] * a1, o[i + 3] * a0 + xch[r * 67 + i + 3] * a1);
+      *reinterpret_cast<float2*>(p.part_ml + ((long long)g.slot * BQ + r) * 2) = make_float2(m, l_run * a0 + l1 * a1);
+    } else if (hf == 0 && row < p.nq) {
       const float m1 = xch[r * 67 + 64], l1 = xch[r * 67 + 65];
       const float m = fmaxf(m_run, m1);                // half 0 always holds key 0, so m is finite
       const float a0 = ex2_approx(m_run - m), a1 = (m1 == -INFINITY) ? 0.f : ex2_approx(m1 - m);
@@ -269,6 +337,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
       }
       if (p.lse) p.lse[((long long)b * p.heads + h) * p.nq + row] = (m + log2f(l)) / kLog2e;
     }
+    it0 += nloc;
+    if (seg + 1 < nseg) asm volatile("bar.sync 1, 256;" ::: "memory");   // xch aliases the P tiles of the next segment
+    }
   }
 
   tc_fence_before();
@@ -277,6 +348,76 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
+}
+
+// Merge the key parts of every leftover item: thread = (query row, 8 output columns), 16 rows per CTA (8 CTAs per item so
+// that the launch spreads over the SMs); all loads of a thread are independent and issued up front - the kernel is pure
+// latency otherwise (12 dependent round trips to L2 measured 15 us for what is 5 MB of traffic).
+constexpr int kMaxParts = 16;
+__global__ void __launch_bounds__(128) attn_fwd_fixup_kernel(const FwdParams p) {
+  pdl_trigger();
+  pdl_wait();
+  const int li = (int)blockIdx.x >> 3;
+  const int r = (((int)blockIdx.x & 7) << 4) + ((int)threadIdx.x >> 3), cg = threadIdx.x & 7;
+  const int item = p.items - p.n_left + li;
+  const int qt = item % p.nqt, hb = item / p.nqt;
+  const int h = hb % p.heads, b = hb / p.heads;
+  const int row = qt * BQ + r;
+  if (row >= p.nq) return;
+  const long long slot0 = (long long)li * p.parts;
+  float2 ml[kMaxParts];
+  float4 v0[kMaxParts], v1[kMaxParts];
+#pragma unroll
+  for (int q = 0; q < kMaxParts; ++q) {
+    ml[q] = make_float2(-INFINITY, 0.f);
+    v0[q] = v1[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < p.parts) {
+      ml[q] = *reinterpret_cast<const float2*>(p.part_ml + ((slot0 + q) * BQ + r) * 2);
+      const float* po = p.part_o + ((slot0 + q) * BQ + r) * D + cg * 8;
+      v0[q] = *reinterpret_cast<const float4*>(po);
+      v1[q] = *reinterpret_cast<const float4*>(po + 4);
+    }
+  }
+  float m = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < kMaxParts; ++q) m = fmaxf(m, ml[q].x);
+  float l = 0.f, acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int q = 0; q < kMaxParts; ++q) {
+    const float a = (ml[q].x == -INFINITY) ? 0.f : ex2_approx(ml[q].x - m);
+    l = fmaf(ml[q].y, a, l);
+    acc[0] = fmaf(v0[q].x, a, acc[0]); acc[1] = fmaf(v0[q].y, a, acc[1]); acc[2] = fmaf(v0[q].z, a, acc[2]); acc[3] = fmaf(v0[q].w, a, acc[3]);
+    acc[4] = fmaf(v1[q].x, a, acc[4]); acc[5] = fmaf(v1[q].y, a, acc[5]); acc[6] = fmaf(v1[q].z, a, acc[6]); acc[7] = fmaf(v1[q].w, a, acc[7]);
+  }
+  const float inv = l > 0.f ? 1.f / l : 0.f;
+  uint4 w;
+  w.x = pack_bf162(acc[0] * inv, acc[1] * inv); w.y = pack_bf162(acc[2] * inv, acc[3] * inv);
+  w.z = pack_bf162(acc[4] * inv, acc[5] * inv); w.w = pack_bf162(acc[6] * inv, acc[7] * inv);
+  *reinterpret_cast<uint4*>(p.o + (long long)b * p.bso + (long long)row * p.ldo + h * D + cg * 8) = w;
+  if (p.lse && cg == 0) p.lse[((long long)b * p.heads + h) * p.nq + row] = (m + log2f(l)) / kLog2e;
+}
+
+// Split decision shared by vn_attention_fwd and vn_attention_fwd_workspace_bytes: leftover items and key parts per item
+// (0 parts = every item whole, one CTA per item).
+void fwd_split(int nb, int heads, int nq, int nk, int* n_left, int* parts) {
+  *n_left = 0; *parts = 0;
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("VN_ATTN_SPLIT"); enabled = e ? atoi(e) : 1; }
+  if (!enabled) return;
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  const int items = vn_cdiv(nq, BQ) * heads * nb, nt = vn_cdiv(nk, BKV);
+  const int left = items % sms;
+  if (items <= sms || left == 0 || left > sms / 2 || nt < 4) return;
+  int q = sms / left;
+  if (q > nt / 2) q = nt / 2;                     // at least two key blocks per part
+  if (q > kMaxParts) q = kMaxParts;
+  if (q < 2) return;
+  *n_left = left; *parts = q;
 }
 
 // {64 d, rows, images} view of a [nb, rows, heads*64] tensor with row stride ld and image stride bs
@@ -311,7 +452,30 @@ extern "C" int vn_attention_fwd(const vn_attn_desc* d, vn_stream_t s) {
     VN_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  dim3 grid(vn_cdiv(d->nq, BQ), d->heads, d->nb);
+  p.nqt = vn_cdiv(d->nq, BQ);
+  p.items = p.nqt * d->heads * d->nb;
+  p.rounds = 1;
+  int grid = p.items;
+  int n_left = 0, parts = 0;
+  fwd_split(d->nb, d->heads, d->nq, d->nk, &n_left, &parts);
+  const size_t need = (size_t)n_left * parts * BQ * (D + 2) * sizeof(float);
+  if (parts > 0 && d->ws != nullptr && (size_t)d->ws_bytes >= need) {
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    grid = sms;
+    p.rounds = p.items / sms;
+    p.n_left = n_left; p.parts = parts;
+    p.part_o = reinterpret_cast<float*>(d->ws);
+    p.part_ml = p.part_o + (size_t)n_left * parts * BQ * D;
+  }
   VN_LAUNCH(attn_fwd_tc_kernel, grid, kThreads, SMEM_BYTES, (cudaStream_t)s, tq, tk, tv, p);
+  if (p.n_left > 0) VN_LAUNCH(attn_fwd_fixup_kernel, p.n_left * 8, 128, 0, (cudaStream_t)s, p);
   return 0;
+}
+
+extern "C" size_t vn_attention_fwd_workspace_bytes(int nb, int heads, int nq, int nk) {
+  int n_left = 0, parts = 0;
+  fwd_split(nb, heads, nq, nk, &n_left, &parts);
+  return (size_t)n_left * parts * BQ * (D + 2) * sizeof(float);
 }

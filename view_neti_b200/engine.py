@@ -68,6 +68,28 @@ class UNetEngine:
         self.conv_in_w, self.conv_in_b = f32("conv_in.weight"), f32("conv_in.bias")
         self.conv_out_w, self.conv_out_b = f32("conv_out.weight"), f32("conv_out.bias")
         self.norm_out = (f32("conv_norm_out.weight"), f32("conv_norm_out.bias"))
+        # The three few-channel edge convolutions on the tensor-core GEMM (as in models/vae.py): conv_in (4 -> C) and the
+        # dgrad of conv_out (4 -> C) as vn_im2col_thin (K = 9*4 zero-padded to one 64-wide k-block) + GEMM; conv_out
+        # (C -> 4) as the implicit 3x3 GEMM with N padded to 8 and an fp32 destination.  The CUDA-core thin-conv kernels
+        # they replace cost 39 / 26 / 72 us of a 7.6 ms step at 64x64 (profiles/r2_graph_timeline_v0.txt); VN_UNET_THIN_GEMM=0
+        # keeps them as a cross-check.
+        import os
+        self.thin_gemm = os.environ.get("VN_UNET_THIN_GEMM", "1") != "0"
+
+        def thin_in(w):             # [Cout, Ct, 3, 3] -> [Cout, 64], k = tap*Ct + ct
+            k = 9 * w.shape[1]
+            wk = torch.zeros(w.shape[0], (k + 63) // 64 * 64, dtype=BF, device=dev)
+            wk[:, :k] = w.permute(0, 2, 3, 1).reshape(w.shape[0], k).to(device=dev, dtype=BF)
+            return wk
+
+        w_in, w_out = sd["conv_in.weight"], sd["conv_out.weight"]
+        self.conv_in_g = thin_in(w_in)
+        self.conv_out_g = torch.zeros(8, 9 * w_out.shape[1], dtype=BF, device=dev)            # [8, 9*C], rows >= 4 zero
+        self.conv_out_g[: w_out.shape[0]] = w_out.permute(0, 2, 3, 1).reshape(w_out.shape[0], -1).to(device=dev, dtype=BF)
+        self.conv_out_gb = torch.zeros(8, dtype=F32, device=dev)
+        self.conv_out_gb[: w_out.shape[0]] = sd["conv_out.bias"].to(dev, F32)
+        # dgrad of conv_out = a 4 -> C convolution with the taps flipped and in / out channels swapped
+        self.conv_out_bwd_g = thin_in(w_out.flip(2, 3).permute(1, 0, 2, 3))
         self.te1 = (sd["time_embedding.linear_1.weight"].to(dev, BF).contiguous(), f32("time_embedding.linear_1.bias"))
         self.te2 = (sd["time_embedding.linear_2.weight"].to(dev, BF).contiguous(), f32("time_embedding.linear_2.bias"))
         self.res: Dict[str, _Res] = {}
@@ -191,6 +213,12 @@ class _Plan:
         # side stream: the 32 context projections (forward) and the 32 context-gradient GEMMs (backward) do not sit on
         # the UNet's dependency chain; they run concurrently with it and are joined by events (captured in the graph)
         self.side = torch.cuda.Stream(device=self.dev)
+        # scratch of the self-attention forward's work balancing (largest request over the attention levels of this plan)
+        need = max([max(ops.attention_fwd_workspace_bytes(nb, cfg.block_out_channels[i] // 64, (h >> i) * (w >> i), (h >> i) * (w >> i)),
+                        ops.attention_bwd_workspace_bytes(nb, cfg.block_out_channels[i] // 64, (h >> i) * (w >> i), (h >> i) * (w >> i)))
+                    for i in range(nlev)] + [0])
+        self.attn_ws = torch.empty(need, dtype=torch.uint8, device=self.dev) if need > 0 else None
+        self.ev_temb = torch.cuda.Event()
         self.ev_kv = [torch.cuda.Event() for _ in range(self.n_layers)]
         self.ev_dkv = [torch.cuda.Event() for _ in range(self.n_layers)]
         self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
@@ -315,7 +343,7 @@ class _Plan:
         ops.gemm(n1, t.qkvf, qkv, ws=self.ws)
         o1 = self.buf(name + ".o1", (nb, hw, c))
         ops.attention_fwd(qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:], o1,
-                          self.buf(name + ".lse1", (nb, heads, hw), F32), heads)
+                          self.buf(name + ".lse1", (nb, heads, hw), F32), heads, ws=self.attn_ws)
         t1 = self.buf(name + ".t1", (nb, hw, c))
         ops.gemm(o1, t.o1f, t1, bias=t.o1bias, R=t0, ws=self.ws)
         # --- attn2: XTI cross-attention, K from CONTEXT_TENSOR_i, V from CONTEXT_TENSOR_BYPASS_i (:16-22,38-42) ---
@@ -384,7 +412,7 @@ class _Plan:
         qkv = B[name + ".qkv"]
         dqkv = self.buf(name + ".dqkv", (nb, hw, 3 * c))
         ops.attention_bwd(qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:], B[name + ".o1"], B[name + ".lse1"], do1,
-                          B[name + ".delta"], dqkv[..., :c], dqkv[..., c:2 * c], dqkv[..., 2 * c:], heads)
+                          B[name + ".delta"], dqkv[..., :c], dqkv[..., c:2 * c], dqkv[..., 2 * c:], heads, ws=self.attn_ws)
         dn1 = dn3
         ops.gemm(dqkv, t.qkvb, dn1, ws=self.ws)
         dt0 = dt3
@@ -401,22 +429,25 @@ class _Plan:
         ch = cfg.block_out_channels
         nlev = len(ch)
         B = self.bufs
-        # time embedding: sinusoid -> Linear -> SiLU -> Linear, then all ResBlock projections in one launch
         self.stat_f.zero_()
         ops.memset(self.part_f, 0xFF)
-        sin = self.buf("temb.sin", (nb, ch[0]), F32)
-        ops.timestep_sinusoid(self.timesteps, sin)
-        e1 = self.buf("temb.e1", (nb, cfg.time_embed_dim), F32)
-        ops.gemv(sin, eng.te1[0], eng.te1[1], e1)
-        temb = self.buf("temb.e2", (nb, cfg.time_embed_dim), F32)
-        ops.gemv(e1, eng.te2[0], eng.te2[1], temb, silu_in=True)
-        ops.gemv(temb, eng.temb_w, eng.temb_b, self.buf("temb.proj", (nb, eng.temb_total), F32), silu_in=True)
-        ctxb = self.buf("ctx.bf16", tuple(self.ctx.shape))
-        ops.cast_f32_bf16(self.ctx, ctxb)
-        # K = to_k(CONTEXT_TENSOR_l), V = to_v(CONTEXT_TENSOR_BYPASS_l) for all 16 layers (xti_attention_processor.py:38-42)
+        # Side stream, concurrent with conv_in / the first GroupNorm: the time embedding (sinusoid -> Linear -> SiLU ->
+        # Linear, then all 22 ResBlock projections in one launch; first needed by the first ResBlock's conv1), the bf16 cast
+        # of the contexts and K = to_k(CONTEXT_TENSOR_l), V = to_v(CONTEXT_TENSOR_BYPASS_l) for all 16 layers
+        # (xti_attention_processor.py:38-42)
         main = torch.cuda.current_stream()
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
+            sin = self.buf("temb.sin", (nb, ch[0]), F32)
+            ops.timestep_sinusoid(self.timesteps, sin)
+            e1 = self.buf("temb.e1", (nb, cfg.time_embed_dim), F32)
+            ops.gemv(sin, eng.te1[0], eng.te1[1], e1)
+            temb = self.buf("temb.e2", (nb, cfg.time_embed_dim), F32)
+            ops.gemv(e1, eng.te2[0], eng.te2[1], temb, silu_in=True)
+            ops.gemv(temb, eng.temb_w, eng.temb_b, self.buf("temb.proj", (nb, eng.temb_total), F32), silu_in=True)
+            self.ev_temb.record(self.side)
+            ctxb = self.buf("ctx.bf16", tuple(self.ctx.shape))
+            ops.cast_f32_bf16(self.ctx, ctxb)
             for l, name in enumerate(self._xf_names()):
                 t = eng.xf[name]
                 ops.gemm(ctxb[0, l], t.k2f, self.buf(name + ".k2", (nb, self.L, t.c)), ws=self.ws)
@@ -443,7 +474,13 @@ class _Plan:
         self._cats = cats
         k = 0
         x = skip_home(k); k += 1
-        ops.conv_in_fwd(self.latents, eng.conv_in_w, eng.conv_in_b, x.unflatten(1, (h, w)))
+        if eng.thin_gemm:
+            col = self.buf("in.col", (nb * h * w, eng.conv_in_g.shape[1]))
+            ops.im2col_thin(self.latents, col)
+            ops.gemm(col, eng.conv_in_g, x, bias=eng.conv_in_b, ws=self.ws)
+        else:
+            ops.conv_in_fwd(self.latents, eng.conv_in_w, eng.conv_in_b, x.unflatten(1, (h, w)))
+        main.wait_event(self.ev_temb)          # the time-embedding projections are first read by the next block's conv1
         layer = 0
         H, W = h, w
         for i in range(nlev):
@@ -512,7 +549,12 @@ class _Plan:
         assert layer == self.n_layers and k == n_skips
         self._final_x = x
         y = self._gn("out.gn", x, eng.norm_out, cfg.norm_eps, True, H * W)
-        ops.conv_out_fwd(y.view(nb, H, W, ch[0]), eng.conv_out_w, eng.conv_out_b, self.eps)
+        if eng.thin_gemm:
+            e8 = self.buf("out.eps8", (nb, H, W, 8), F32)
+            ops.conv3x3(y.view(nb, H, W, ch[0]), eng.conv_out_g, e8, bias=eng.conv_out_gb, ws=self.ws, force_bn=64, force_split=4)
+            ops.nhwc_to_nchw_thin(e8, self.eps)
+        else:
+            ops.conv_out_fwd(y.view(nb, H, W, ch[0]), eng.conv_out_w, eng.conv_out_b, self.eps)
         self._saved = True
         return self.eps
 
@@ -530,7 +572,12 @@ class _Plan:
         self.stat_b.zero_()
         ops.memset(self.part_b, 0xFF)
         dy = self.buf("bwd.dy", (nb, H * W, ch[0]))
-        ops.conv_out_bwd(self.d_eps, eng.conv_out_w, dy.view(nb, H, W, ch[0]))
+        if eng.thin_gemm:
+            dcol = self.buf("bwd.eps.col", (nb * H * W, eng.conv_out_bwd_g.shape[1]))
+            ops.im2col_thin(self.d_eps, dcol)
+            ops.gemm(dcol, eng.conv_out_bwd_g, dy, ws=self.ws)
+        else:
+            ops.conv_out_bwd(self.d_eps, eng.conv_out_w, dy.view(nb, H, W, ch[0]))
         dcur = self.buf(f"bwd.up.{nlev - 1}.out", (nb, H * W, ch[0]))
         self._gn_bwd("out.gn", self._final_x, dy, eng.norm_out, cfg.norm_eps, True, H * W, dcur)
         layer = self.n_layers - 1

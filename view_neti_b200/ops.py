@@ -242,15 +242,31 @@ def _attn_desc(q, k, v, o, lse, heads, scale) -> AttnDesc:
     return d
 
 
-def attention_fwd(q, k, v, o, lse, heads, scale=0.125, causal=False):
+def attention_fwd_workspace_bytes(nb: int, heads: int, nq: int, nk: int) -> int:
+    """Scratch the forward wants for its leftover-item key split (0: the shape runs one CTA per item)."""
+    return int(_abi.load().vn_attention_fwd_workspace_bytes(nb, heads, nq, nk))
+
+
+def attention_fwd(q, k, v, o, lse, heads, scale=0.125, causal=False, ws: Optional[torch.Tensor] = None):
+    """ws: optional scratch (uint8 / any dtype, >= attention_fwd_workspace_bytes) that lets the kernel balance the work
+    items over the SMs; without it every item runs whole on its own CTA."""
     d = _attn_desc(q, k, v, o, lse, heads, scale)
     d.causal = int(causal)
+    if ws is not None:
+        d.ws, d.ws_bytes = ptr(ws), ws.numel() * ws.element_size()
     check(_abi.load().vn_attention_fwd(C.byref(d), stream()), "attention_fwd")
 
 
-def attention_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, heads, scale=0.125, dkv_acc=None, causal=False):
+def attention_bwd_workspace_bytes(nb: int, heads: int, nq: int, nk: int, has_dq: bool = True) -> int:
+    return int(_abi.load().vn_attention_bwd_workspace_bytes(nb, heads, nq, nk, int(has_dq)))
+
+
+def attention_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, heads, scale=0.125, dkv_acc=None, causal=False,
+                  ws: Optional[torch.Tensor] = None):
     d = _attn_desc(q, k, v, o, lse, heads, scale)
     d.causal = int(causal)
+    if ws is not None:
+        d.ws, d.ws_bytes = ptr(ws), ws.numel() * ws.element_size()
     d.d_o, d.lddo, d.bsdo = ptr(d_o), d_o.stride(1), d_o.stride(0)
     d.delta = ptr(delta)
     if dq is not None:

@@ -18,10 +18,12 @@ VIEW_TOKEN_IDS = [49409, 49410, 49411, 49412]
 VIEW_TOKENS = ["<view_0_10_1p2>", "<view_10_40_1p2>", "<view_20_70_1p2>", "<view_35_100_1p2>"]
 
 
-def build_conditioning(device="cuda", cfg: ClipEncoderConfig = SD21_TEXT, seed: int = 0) -> NeTIConditioning:
+def build_conditioning(device="cuda", cfg: ClipEncoderConfig = SD21_TEXT, seed: int = 0, n_objects: int = 1) -> NeTIConditioning:
+    """n_objects > 1: BASELINE config 4 (mode 3 multi-scene pretraining, train_m3.yaml): that many object mappers resident
+    under consecutive placeholder ids OBJECT_TOKEN_ID + 16 + i (one is active per step), one shared view mapper."""
     g = torch.Generator().manual_seed(seed)
     C = cfg.hidden_size
-    tok = torch.randn(49408 + 8, C, generator=g) * 0.02
+    tok = torch.randn(49408 + 8 + (16 + n_objects if n_objects > 1 else 0), C, generator=g) * 0.02
     pos = torch.randn(77, C, generator=g) * 0.01
     enc = CLIPEncoder(init_state_dict(cfg, seed), cfg, device)
     sig = PESigmas(sigma_t=0.03, sigma_l=2.0, sigma_theta=0.5, sigma_phi=0.5, sigma_r=0.5, sigma_dtu12=0.5)
@@ -32,17 +34,26 @@ def build_conditioning(device="cuda", cfg: ClipEncoderConfig = SD21_TEXT, seed: 
         mo = NeTIMapper(embedding_type="object", norm_scale=torch.tensor(0.3714), placeholder_object_token="<statue>", **kw).to(device)
         mv = NeTIMapper(embedding_type="view", norm_scale=torch.tensor(0.4102), placeholder_view_tokens=list(VIEW_TOKENS),
                         placeholder_view_token_ids=list(VIEW_TOKEN_IDS), **kw).to(device)
-    return NeTIConditioning(tok, pos, (torch.ones(C), torch.zeros(C)), enc, {OBJECT_TOKEN_ID: mo}, mv)
+        lookup = {OBJECT_TOKEN_ID: mo}
+        if n_objects > 1:
+            lookup = {object_token_id(i): NeTIMapper(embedding_type="object", norm_scale=torch.tensor(0.3714),
+                                                     placeholder_object_token=f"<scan{i}>", **kw).to(device) for i in range(n_objects)}
+    return NeTIConditioning(tok, pos, (torch.ones(C), torch.zeros(C)), enc, lookup, mv)
 
 
-def synthetic_prompt(batch: int, device="cuda", seed: int = 0) -> Dict[str, torch.Tensor]:
+def object_token_id(i: int) -> int:
+    """Placeholder id of object i of a multi-object (mode 3) synthetic conditioning stack."""
+    return OBJECT_TOKEN_ID + 16 + i
+
+
+def synthetic_prompt(batch: int, device="cuda", seed: int = 0, object_id: int = OBJECT_TOKEN_ID) -> Dict[str, torch.Tensor]:
     """`batch` prompts of 77 token ids holding the object placeholder and one view placeholder each."""
     g = torch.Generator().manual_seed(seed)
     ids = torch.randint(1000, 40000, (batch, 77), generator=g)
-    ids[:, 0], ids[:, 5] = 49406, OBJECT_TOKEN_ID
+    ids[:, 0], ids[:, 5] = 49406, object_id
     view = torch.tensor([VIEW_TOKEN_IDS[i % len(VIEW_TOKEN_IDS)] for i in range(batch)])
     ids[:, 3] = view
-    return {"input_ids": ids.to(device), "input_ids_placeholder_object": torch.full((batch,), OBJECT_TOKEN_ID, device=device),
+    return {"input_ids": ids.to(device), "input_ids_placeholder_object": torch.full((batch,), object_id, device=device),
             "input_ids_placeholder_view": view.to(device)}
 
 
