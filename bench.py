@@ -178,6 +178,27 @@ def profile_categories(plan):
     return ms, n, flops
 
 
+def _emit(line: dict, real_stdout) -> None:
+    """The ONE JSON line, on the process's original stdout (see run_ours for why fd 1 may have been redirected)."""
+    text = json.dumps(line) + "\n"
+    if real_stdout is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(real_stdout, text.encode())
+
+
+def _finish(world: int) -> None:
+    """End of a rank.  Multi-process runs leave without tearing the process group down: ncclCommDestroy with the step graph
+    (which holds the captured all-reduce) still alive blocked rank 0 for the whole 900 s limit of one test run, and nothing
+    after this point needs the communicator; buffers are flushed and the process exits with status 0."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        torch.cuda.synchronize()
+        os._exit(0)
+
+
 def _time_replays(graph_or_fn, n: int, e0, e1) -> float:
     """ms per call over n back-to-back calls (CUDA events on the current stream)."""
     call = graph_or_fn.replay if hasattr(graph_or_fn, "replay") else graph_or_fn
@@ -200,12 +221,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    real_stdout = None
     if world > 1:
-        # stdout carries ONE JSON line: NCCL's banner / INFO log goes to a file per rank (the driver reads the rank count there)
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(ROOT, "gpurun_out", "nccl_%h_%p.log"))
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        # stdout carries ONE JSON line, but NCCL writes its version banner and its NCCL_DEBUG=INFO log (which the driver reads
+        # the rank count from - it is left exactly as the environment sets it) to file descriptor 1.  For the whole run fd 1
+        # is therefore pointed at stderr; the JSON line is written to the saved original descriptor at the end.
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
+        os.environ["NCCL_DEBUG"] = "INFO"               # the communicator's own account of itself (nranks, NVLS, channels) -> stderr
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=dev)
+        print(f"bench.py: rank {rank} of {dist.get_world_size()} (backend {dist.get_backend()}) on cuda:{local_rank}", file=sys.stderr, flush=True)
     L = args.latent
     cfg = SD21
     model = UNet2DConditionModel(init_state_dict(cfg, 0), cfg, dev)
@@ -490,9 +517,64 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     except Exception as e:
         mode3 = {"error": f"{type(e).__name__}: {e}"[:300]}
 
+    # ---- BASELINE config 5 (single process): pretrained M_v FROZEN (requires_grad False: no gradient is computed for it) +
+    # learn M_o, then novel-view inference = PromptManager.embed_prompt over the 50 timesteps + sd_pipeline_call (50 steps x
+    # batched CFG UNet forward + fused guidance / sampler update + VAE decode) ---------------------------------------------
+    config5 = None
+    if world == 1:
+        try:
+            from view_neti_b200.models.vae import SD21_VAE, AutoencoderKL, init_state_dict as vae_init
+            from view_neti_b200.prompt_manager import PromptManager
+            from view_neti_b200.schedulers import DPMSolverMultistepScheduler
+            from view_neti_b200.sd_pipeline_call import ViewNeTIPipeline, sd_pipeline_call
+            from view_neti_b200.training.coach import Coach
+            from view_neti_b200.training.synthetic import OBJECT_TOKEN_ID, VIEW_TOKEN_IDS, build_conditioning, synthetic_prompt
+            cond5 = build_conditioning(dev)
+            cond5.mapper_view.requires_grad_(False)                     # mode 5 (coach.py:661-669): M_v loaded and frozen
+            coach5 = Coach(cfg=None, unet=model, conditioning=cond5,
+                           optimizer=torch.optim.AdamW([p for p in cond5.parameters() if p.requires_grad], lr=1e-3),
+                           generator=torch.Generator(device=dev).manual_seed(3))
+            prompt5 = synthetic_prompt(1, dev)
+            lat5 = torch.randn(1, 4, L, L, device=dev)
+            for _ in range(4):
+                coach5.train_step(lat5, prompt5)
+            k5 = max(3, min(args.steps, 20))
+            t5 = _time_replays(lambda: coach5.train_step(lat5, prompt5), k5, e0, e1)
+            n_inf = 50
+            sched = DPMSolverMultistepScheduler("v_prediction")           # what the reference's inference scripts install (validate.py:568)
+            sched.set_timesteps(n_inf)
+            pm = PromptManager(tokenizer=None, text_encoder=cond5, timesteps=[int(t) for t in sched.timesteps],
+                               placeholder_view_token_ids=VIEW_TOKEN_IDS, placeholder_object_token_ids=[OBJECT_TOKEN_ID], chunk=10)
+            vae5 = AutoencoderKL(vae_init(SD21_VAE, 0), SD21_VAE, dev)
+            neg = torch.randn(1, 77, 1024, generator=torch.Generator().manual_seed(3)).to(dev)
+            pipe = ViewNeTIPipeline(model, sched, negative_prompt_embeds=neg, vae=vae5)
+
+            def infer(seed):
+                emb = pm.embed_prompt(prompt5["input_ids"])
+                return sd_pipeline_call(pipe, emb, height=8 * L, width=8 * L, num_inference_steps=n_inf, guidance_scale=7.5,
+                                        generator=torch.Generator(device=dev).manual_seed(seed), output_type="np")
+
+            infer(0)
+            torch.cuda.synchronize()
+            t0 = time.time()
+            n_img = 2
+            for i in range(n_img):
+                img = infer(1 + i).images
+            torch.cuda.synchronize()
+            per_img = (time.time() - t0) / n_img
+            config5 = {"train": {"value": 1e3 / t5, "unit": "images/s", "ms_per_step": t5, "steps": k5,
+                                 "trainable_params": sum(p.numel() for p in cond5.parameters() if p.requires_grad),
+                                 "what": "Coach.train_step with the view mapper frozen (mode 5): only M_o receives gradient"},
+                       "inference": {"value": 1.0 / per_img, "unit": "images/s", "s_per_image": per_img, "images": n_img,
+                                     "steps": n_inf, "what": f"embed_prompt (50 timesteps x 16 layers, batched) + 50-step DPM-Solver++ CFG 7.5 "
+                                                             f"denoise at {8 * L}x{8 * L} + VAE decode, wall clock per image",
+                                     "finite": bool(torch.isfinite(torch.as_tensor(img)).all())}}
+            del coach5, cond5, vae5, pipe
+        except Exception as e:
+            config5 = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
 
     # ---- secondary legs (rank 0 of a single-process run) -----------------------------------------------------
@@ -597,7 +679,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                    "graph": "one CUDA graph per step"},
         "sustained": sustained,
         "roofline": roofline, "forward": forward_leg, "batch3": batch3, "cpu_baseline": cpu, "full_step": full_step,
-        "mode3": mode3,
+        "mode3": mode3, "config5": config5,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "steps": k2, "copies": e2e_note, "api": "UNet2DConditionModel.__call__ + F.mse_loss + backward (CUDA-graph replay inside)"},
         "gpu_launches": launches_per_step * (args.steps + n_long) + e2e_launches * (k2 + pf_steps) + e2e_launches_eager + extra_launches,
@@ -605,9 +687,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "clocks": clk,
         "loss": loss_dev, "e2e_loss": e2e_loss,
     }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _emit(line, real_stdout)
+    _finish(world)
 
 
 def main():
