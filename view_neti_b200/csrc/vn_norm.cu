@@ -5,6 +5,8 @@
 // BasicTransformerBlock, GEGLU — all on the coach.py:197-214 path.
 #include "vn_common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int kMaxC = 2560;       // widest GroupNorm input in SD-2.1 (concat 1280+1280)
@@ -917,6 +919,277 @@ __global__ void __launch_bounds__(256) geglu_kernel(const bf16* __restrict__ h, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// GroupNorm on thread-block CLUSTERS (round 2).  The one-launch kernel above slices the tensor by PIXELS, so every CTA
+// needs the statistics of all 32 groups and all <= 148 CTAs exchange partials through global memory (each one reads all
+// the others' slots: 5.6 MB of L2 traffic for a 2.6 MB tensor, and ~5 us of arrival / totals phases).  Here the tensor
+// is sliced by GROUPS first: a cluster of CS <= 8 CTAs owns G2 adjacent groups of one image and splits the pixels, so
+// statistics only travel between the CTAs of a cluster - through distributed shared memory, two cluster barriers, no
+// global memory, no flags to preset, fixed summation order (bit-reproducible).  The slab of a CTA ((hw / CS) pixels x
+// G2 * cpg channels) stays in registers between the two phases: thread t owns 4-byte words t, t + T, ... of the slab
+// (word = 2 channels; consecutive threads read consecutive words of a pixel's G2 * cpg * 2-byte run).
+// Clusters are independent of each other, so the grid may exceed the SM count (any batch size).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gn_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void gn_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void gn_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ double gn_ld_remote_f64(const double* local, uint32_t rank) {
+  uint32_t a;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_u32(local)), "r"(rank));
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+
+// MODE 0: y = GN(x) (+SiLU), stats_out = (sum x, sum x^2).   MODE 1: dx = GN^T(dy) (+add1) (+add2), stats_out = (sum dh, sum dh*xhat)
+template <int MODE, int NI, int T>
+__global__ void __launch_bounds__(T, 1) gn_cluster_kernel(const bf16* __restrict__ x, long long ldx,
+                                                          const bf16* __restrict__ dy, long long lddy,
+                                                          const double* __restrict__ stats_in,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float eps, int silu, double* __restrict__ stats_out,
+                                                          const bf16* __restrict__ add1, long long ld1,
+                                                          const bf16* __restrict__ add2, long long ld2,
+                                                          bf16* __restrict__ y, long long ldy, int hw, int C, int groups,
+                                                          int G2, int CS) {
+  pdl_trigger();
+  __shared__ float s_w[T / 32][4];                 // per-warp partial sums: [statistic 0 | 1] x [group 0 | 1]
+  __shared__ double s_part[4];                     // this CTA's partials, read by the whole cluster
+  __shared__ float s_c[2][4];                      // per group of the cluster: (mean, rstd, S1, S2); S1 / S2 in the backward only
+  const uint32_t rank = gn_cluster_rank();
+  const int cl = blockIdx.x / CS;                  // cluster index = image * (groups / G2) + group set
+  const int nsets = groups / G2;
+  const int b = cl / nsets, g0 = (cl - b * nsets) * G2;
+  const int cpg = C / groups;
+  const int Wd = (G2 * cpg) >> 1;                  // 4-byte words per pixel in this cluster's channel run
+  const int wpg = cpg >> 1;                        // words per group
+  const int ppc = (hw + CS - 1) / CS;
+  const int p0 = (int)rank * ppc, p1 = min(hw, p0 + ppc);
+  const int nitems = max(0, p1 - p0) * Wd;
+  const int c0 = g0 * cpg;
+  const double inv_n = 1.0 / ((double)cpg * (double)hw);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  // first item of this thread and the (pixel, word) step between its consecutive items
+  const int dpx = T / Wd, dw = T - dpx * Wd;
+  int px = t / Wd, w = t - px * Wd;
+  pdl_wait();                                      // activations / statistics only from here on
+  if (MODE == 1) {
+    if (t < G2) {
+      const double m = stats_in[((long long)b * groups + g0 + t) * 2] * inv_n;
+      const double var = fmax(fma(-m, m, stats_in[((long long)b * groups + g0 + t) * 2 + 1] * inv_n), 0.0);
+      s_c[t][0] = (float)m; s_c[t][1] = 1.0f / sqrtf((float)var + eps);
+    }
+    __syncthreads();
+  }
+  const bf16* xb = x + ((long long)b * hw + p0) * ldx + c0;
+  const bf16* db = MODE == 1 ? dy + ((long long)b * hw + p0) * lddy + c0 : xb;
+  uint32_t xr[NI], dr[MODE == 1 ? NI : 1];
+  // ---- phase 1: loads (all issued before the first use) and partial sums ----
+  {
+    int ppx = px, ww = w;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const bool ok = t + i * T < nitems;
+      xr[i] = 0u;
+      if (MODE == 1) dr[i] = 0u;
+      if (ok) {
+        xr[i] = __ldg(reinterpret_cast<const uint32_t*>(xb + (long long)ppx * ldx) + ww);
+        if (MODE == 1) dr[i] = __ldg(reinterpret_cast<const uint32_t*>(db + (long long)ppx * lddy) + ww);
+      }
+      ppx += dpx; ww += dw;
+      if (ww >= Wd) { ww -= Wd; ++ppx; }
+    }
+  }
+  float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;        // [statistic][group]
+  {
+    int ww = w;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      if (t + i * T < nitems) {
+        const float2 xf = unpack_bf162(xr[i]);
+        const int gi = ww >= wpg ? 1 : 0;
+        float u0, u1;
+        if (MODE == 0) {
+          u0 = xf.x + xf.y;
+          u1 = fmaf(xf.x, xf.x, xf.y * xf.y);
+        } else {
+          const float2 gm = __ldg(reinterpret_cast<const float2*>(gamma + c0) + ww);
+          const float2 bt = __ldg(reinterpret_cast<const float2*>(beta + c0) + ww);
+          const float2 df = unpack_bf162(dr[i]);
+          const float mean = s_c[gi][0], rstd = s_c[gi][1];
+          const float xh0 = (xf.x - mean) * rstd, xh1 = (xf.y - mean) * rstd;
+          float dz0 = df.x, dz1 = df.y;
+          if (silu) { dz0 *= dsilu_f(fmaf(xh0, gm.x, bt.x)); dz1 *= dsilu_f(fmaf(xh1, gm.y, bt.y)); }
+          const float dh0 = dz0 * gm.x, dh1 = dz1 * gm.y;
+          u0 = dh0 + dh1;
+          u1 = fmaf(dh0, xh0, dh1 * xh1);
+        }
+        if (gi) { a01 += u0; a11 += u1; } else { a00 += u0; a10 += u1; }
+      }
+      ww += dw;
+      if (ww >= Wd) ww -= Wd;
+    }
+  }
+  a00 = warp_sum(a00); a01 = warp_sum(a01); a10 = warp_sum(a10); a11 = warp_sum(a11);
+  if (lane == 0) { s_w[warp][0] = a00; s_w[warp][1] = a01; s_w[warp][2] = a10; s_w[warp][3] = a11; }
+  __syncthreads();
+  if (t < 4) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < T / 32; ++k) acc += (double)s_w[k][t];           // fixed order
+    s_part[t] = acc;
+  }
+  gn_cluster_arrive();                             // release: s_part is visible to the cluster
+  gn_cluster_wait();
+  if (t < 2 * G2) {
+    const int st = t / G2, gi = t - st * G2;       // statistic, group
+    double tot = 0.0;
+    for (int r = 0; r < CS; ++r) tot += gn_ld_remote_f64(&s_part[st * 2 + gi], (uint32_t)r);   // fixed order
+    if (rank == 0) stats_out[((long long)b * groups + g0 + gi) * 2 + st] = tot;
+    if (MODE == 0) {
+      // mean needs statistic 0, the variance both: park the totals (s_w is dead by now) and finish below
+      reinterpret_cast<double*>(s_w)[st * 2 + gi] = tot;
+    } else {
+      s_c[gi][2 + st] = (float)(tot * inv_n);      // S1 = sum dh / n, S2 = sum dh*xhat / n
+    }
+  }
+  gn_cluster_arrive();                             // my remote reads are done: peers may exit / reuse s_part
+  __syncthreads();
+  if (MODE == 0 && t < G2) {
+    const double* tot = reinterpret_cast<const double*>(s_w);
+    const double m = tot[0 * 2 + t] * inv_n;
+    const double var = fmax(fma(-m, m, tot[1 * 2 + t] * inv_n), 0.0);
+    s_c[t][0] = (float)m; s_c[t][1] = 1.0f / sqrtf((float)var + eps);
+  }
+  __syncthreads();
+  // ---- phase 2: normalise from registers ----
+  {
+    int ppx = px, ww = w;
+    bf16* yb = y + ((long long)b * hw + p0) * ldy + c0;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      if (t + i * T < nitems) {
+        const float2 xf = unpack_bf162(xr[i]);
+        const float2 gm = __ldg(reinterpret_cast<const float2*>(gamma + c0) + ww);
+        const float2 bt = __ldg(reinterpret_cast<const float2*>(beta + c0) + ww);
+        const int gi = ww >= wpg ? 1 : 0;
+        const float mean = s_c[gi][0], rstd = s_c[gi][1];
+        float o0, o1;
+        if (MODE == 0) {
+          const float z0 = fmaf((xf.x - mean) * rstd, gm.x, bt.x), z1 = fmaf((xf.y - mean) * rstd, gm.y, bt.y);
+          o0 = silu ? silu_f(z0) : z0;
+          o1 = silu ? silu_f(z1) : z1;
+        } else {
+          const float2 df = unpack_bf162(dr[i]);
+          const float S1 = s_c[gi][2], S2 = s_c[gi][3];
+          const float xh0 = (xf.x - mean) * rstd, xh1 = (xf.y - mean) * rstd;
+          float dz0 = df.x, dz1 = df.y;
+          if (silu) { dz0 *= dsilu_f(fmaf(xh0, gm.x, bt.x)); dz1 *= dsilu_f(fmaf(xh1, gm.y, bt.y)); }
+          o0 = rstd * (dz0 * gm.x - S1 - xh0 * S2);
+          o1 = rstd * (dz1 * gm.y - S1 - xh1 * S2);
+          if (add1) {
+            const float2 a = unpack_bf162(__ldg(reinterpret_cast<const uint32_t*>(add1 + ((long long)b * hw + p0 + ppx) * ld1 + c0) + ww));
+            o0 += a.x; o1 += a.y;
+          }
+          if (add2) {
+            const float2 a = unpack_bf162(__ldg(reinterpret_cast<const uint32_t*>(add2 + ((long long)b * hw + p0 + ppx) * ld2 + c0) + ww));
+            o0 += a.x; o1 += a.y;
+          }
+        }
+        reinterpret_cast<uint32_t*>(yb + (long long)ppx * ldy)[ww] = pack_bf162(o0, o1);
+      }
+      ppx += dpx; ww += dw;
+      if (ww >= Wd) { ww -= Wd; ++ppx; }
+    }
+  }
+  gn_cluster_wait();                               // no CTA leaves while a peer may still read its s_part
+}
+
+struct GNCluster {
+  int G2, CS, T, NI;
+};
+static int g_gn_cluster = -1;
+// Shapes the cluster kernel covers: even channels per group, at most two groups per cluster, the CTA's slab in <= 32 words
+// per thread.  Everything else (the VAE's 512 x 512 tensors) takes the pixel-sliced kernels.
+bool gn_cluster_geom(int nb, int hw, int C, int groups, GNCluster* g) {
+  if (g_gn_cluster < 0) {
+    const char* e = getenv("VN_GN_CLUSTER");
+    g_gn_cluster = e ? atoi(e) : 1;
+  }
+  if (!g_gn_cluster) return false;
+  const int cpg = C / groups;
+  if (cpg < 2 || (cpg & 1)) return false;
+  g->CS = hw >= 512 ? 8 : hw >= 128 ? 4 : hw >= 32 ? 2 : 1;
+  // two groups per cluster when the slab still fits (longer contiguous runs per pixel, fewer clusters); a CTA keeps at most
+  // 32 words per thread at 256 threads, 16 at 512 (register budget of the backward: x and dy words both stay live)
+  for (int g2 = (cpg <= 20 && groups % 2 == 0) ? 2 : 1; g2 >= 1; --g2) {
+    const int Wd = g2 * cpg / 2;
+    const int items = vn_cdiv(hw, g->CS) * Wd;
+    // Measured on B200 inside the step graph (profiles/r2_gn_cluster_notes.txt): slabs of <= 2048 words per CTA run in
+    // 5.4 / 7.1 us (forward / backward) against 7.3 / 8.9 us of the pixel-sliced kernel; larger slabs lose (4-byte items cost
+    // ~190 instructions each, 15 k-instruction unrolled bodies miss the instruction cache, 8 x 512-thread clusters start late),
+    // so they stay on the pixel-sliced kernel.  VN_GN_CLUSTER=2 lifts the limit (experiments).
+    if (items > (g_gn_cluster >= 2 ? 8192 : 2048)) continue;
+    g->G2 = g2;
+    g->T = items > 2048 ? 512 : 256;
+    if (Wd > g->T) return false;
+    const int ni = vn_cdiv(items, g->T);
+    g->NI = ni <= 8 ? 8 : ni <= 16 ? 16 : 32;
+    (void)nb;
+    return true;
+  }
+  return false;
+}
+
+template <int MODE, int NI, int T>
+int gn_cluster_launch(const GNCluster& g, const bf16* x, long long ldx, const bf16* dy, long long lddy, const double* stats_in,
+                      const float* gamma, const float* beta, float eps, int silu, double* stats_out, const bf16* add1,
+                      long long ld1, const bf16* add2, long long ld2, bf16* y, long long ldy, int nb, int hw, int C,
+                      int groups, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(nb * (groups / g.G2) * g.CS), 1, 1);
+  cfg.blockDim = dim3(T, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (vn_pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = (unsigned)g.CS; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+  ++na;
+  cfg.attrs = attr; cfg.numAttrs = na;
+  VN_CUDA(cudaLaunchKernelEx(&cfg, gn_cluster_kernel<MODE, NI, T>, x, ldx, dy, lddy, stats_in, gamma, beta, eps, silu, stats_out,
+                             add1, ld1, add2, ld2, y, ldy, hw, C, groups, g.G2, g.CS));
+  vn_count_launch();
+  return 0;
+}
+
+template <int MODE>
+int gn_cluster_dispatch(const GNCluster& g, const bf16* x, long long ldx, const bf16* dy, long long lddy, const double* stats_in,
+                        const float* gamma, const float* beta, float eps, int silu, double* stats_out, const bf16* add1,
+                        long long ld1, const bf16* add2, long long ld2, bf16* y, long long ldy, int nb, int hw, int C,
+                        int groups, cudaStream_t st) {
+#define VN_GNC(NI_, T_)                                                                                                  \
+  return gn_cluster_launch<MODE, NI_, T_>(g, x, ldx, dy, lddy, stats_in, gamma, beta, eps, silu, stats_out, add1, ld1, add2, \
+                                          ld2, y, ldy, nb, hw, C, groups, st)
+  if (g.T == 256) {
+    if (g.NI == 8) VN_GNC(8, 256);
+    if (g.NI == 16) VN_GNC(16, 256);
+    VN_GNC(32, 256);
+  }
+  if (g.NI == 8) VN_GNC(8, 512);
+  VN_GNC(16, 512);
+#undef VN_GNC
+}
+
 int gn_check(int C, int groups, long long ldx) {
   VN_CHECK(groups > 0 && groups <= kMaxGroups && C % groups == 0, "groupnorm: C=%d groups=%d", C, groups);
   VN_CHECK(C % 8 == 0 && C <= kMaxC * 4, "groupnorm: need C %% 8 == 0 (C=%d)", C);
@@ -1015,6 +1288,10 @@ extern "C" int vn_groupnorm_fwd(const void* x, int64_t ldx, const float* gamma, 
                                 float* partials, vn_stream_t s) {
   if (gn_check(C, groups, ldx)) return -1;
   VN_CHECK(ldy % 8 == 0, "groupnorm: ldy must be a multiple of 8");
+  GNCluster gc;
+  if (gn_fused_enabled() && gn_cluster_geom(nb, hw, C, groups, &gc))
+    return gn_cluster_dispatch<0>(gc, (const bf16*)x, ldx, nullptr, 0, nullptr, gamma, beta, eps, silu, stats, nullptr, 0,
+                                  nullptr, 0, (bf16*)y, ldy, nb, hw, C, groups, (cudaStream_t)s);
   GNGeom g;
   if (partials && groups <= 32 && gn_fused_enabled() && gn_fused_geom(nb, hw, C, 512, &g)) {
     dim3 grid(g.chunks, nb);
@@ -1039,6 +1316,11 @@ extern "C" int vn_groupnorm_bwd(const void* x, int64_t ldx, const void* dy, int6
                                 int C, int groups, double* red, float* partials, vn_stream_t s) {
   if (gn_check(C, groups, ldx)) return -1;
   VN_CHECK(lddy % 8 == 0 && lddx % 8 == 0 && ldadd1 % 8 == 0 && ldadd2 % 8 == 0, "groupnorm bwd: strides must be multiples of 8");
+  GNCluster gc;
+  if (gn_fused_enabled() && gn_cluster_geom(nb, hw, C, groups, &gc))
+    return gn_cluster_dispatch<1>(gc, (const bf16*)x, ldx, (const bf16*)dy, lddy, stats, gamma, beta, eps, silu, red,
+                                  (const bf16*)add1, ldadd1, (const bf16*)add2, ldadd2, (bf16*)dx, lddx, nb, hw, C, groups,
+                                  (cudaStream_t)s);
   GNGeom g;
   if (partials && groups <= 32 && gn_fused_enabled() && gn_fused_geom(nb, hw, C, 384, &g)) {
     dim3 grid(g.chunks, nb);
