@@ -233,7 +233,8 @@ def _mode3_worker(rank, world, port, q):
     unchanged = all(torch.equal(m.w, start[k]) for k, m in cond.mapper_object_lookup.items() if k not in used)
     moved = all(not torch.equal(cond.mapper_object_lookup[k].w, start[k]) for k in used)
     flat = torch.cat([p.detach().reshape(-1) for p in cond.parameters()])
-    q.put((rank, drawn, unchanged, moved, flat))
+    q.put((rank, drawn, unchanged, moved, flat.tolist()))        # plain lists: a tensor in the queue shares memory with a
+    #                                                              process that may be gone by the time the parent reads it
     dist.destroy_process_group()
 
 
@@ -254,4 +255,4 @@ def test_mode3_same_object_on_all_ranks_gloo_world2():
     (_, d0, u0, m0, f0), (_, d1, u1, m1, f1) = res
     assert d0 == d1 and len(set(d0)) > 1              # same object sequence on both ranks, more than one object visited
     assert u0 and u1 and m0 and m1                    # inactive mappers untouched, active ones trained
-    assert torch.equal(f0, f1)                        # bit-identical parameters across ranks after 6 steps
+    assert f0 == f1                                   # bit-identical parameters across ranks after 6 steps

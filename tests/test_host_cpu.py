@@ -162,7 +162,8 @@ def _worker(rank, world, port, q):
     # construction-time broadcast (DDP semantics): ranks start from rank 0's values whatever their local init was
     w = torch.nn.Parameter(torch.full((4,), float(10 + rank)))
     FlatGradAllReducer([w]).broadcast_parameters_(0)
-    q.put((rank, a.grad.clone(), b.grad.clone(), c.grad, d.grad.clone(), flat.numel(), w.detach().clone(), e.grad.clone(),
+    # plain lists, not tensors: a tensor in the queue shares memory with a process that may be gone when the parent reads it
+    q.put((rank, a.grad.tolist(), b.grad.tolist(), c.grad, d.grad.tolist(), flat.numel(), w.detach().tolist(), e.grad.tolist(),
            f.grad, part.numel()))
     dist.destroy_process_group()
 
@@ -180,6 +181,7 @@ def test_flat_gradient_allreduce_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, a, b, c, d, n, w, e, f, npart in res:
+        a, b, d, w, e = (torch.tensor(v) for v in (a, b, d, w, e))
         assert torch.equal(w, torch.full((4,), 10.0))
         assert n == 12 + 5 + 2 + 3
         assert torch.allclose(a, torch.full((3, 4), 1.5))            # mean of 1 and 2

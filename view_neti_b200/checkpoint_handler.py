@@ -48,7 +48,7 @@ class _Unpickler(pickle.Unpickler):
         root = module.split(".")[0]
         if root in _REFERENCE_PACKAGES:
             return type(name, (_ReferenceObject,), {"__module__": "reference." + module})
-        if root in _SAFE_MODULE_ROOTS or (module == "builtins" and name in _SAFE_BUILTINS):
+        if root in _SAFE_MODULE_ROOTS or (module in ("builtins", "__builtin__") and name in _SAFE_BUILTINS):
             return super().find_class(module, name)
         raise pickle.UnpicklingError(f"checkpoint names {module}.{name}, which is not on the allowlist of this loader")
 
