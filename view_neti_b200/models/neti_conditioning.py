@@ -56,6 +56,18 @@ class NeTIConditioning(torch.nn.Module):
             return None
         return [int(v) for v in (ids.tolist() if torch.is_tensor(ids) else ids)]
 
+    def _ids_on_device(self, ids) -> torch.Tensor:
+        """Placeholder ids (Python ints) as a device tensor.  Cached by value: an H2D copy from pageable memory drains the
+        stream first, i.e. every fresh `torch.tensor(list, device=cuda)` in the step would be a host stall."""
+        key = tuple(ids)
+        cache = self.__dict__.setdefault("_id_cache", {})
+        t = cache.get(key)
+        if t is None:
+            if len(cache) > 4096:
+                cache.clear()
+            t = cache[key] = torch.tensor(list(key), device=self.token_embedding.device)
+        return t
+
     @staticmethod
     def _positions(input_ids: torch.Tensor, placeholder: torch.Tensor):
         locs = input_ids == placeholder.unsqueeze(1)
@@ -73,6 +85,34 @@ class NeTIConditioning(torch.nn.Module):
         out = state.clone()
         out[rows, pos] = new.to(state.dtype)
         return out
+
+    def _check_placeholders_later(self, flag: torch.Tensor) -> None:
+        """net_clip_text_embedding.py:99,130 assert that every prompt holds its placeholder exactly once.  Reading the flag back
+        at once would stall the host until the device has drained (every step would start on an empty queue: ~2 ms of device
+        idle per step, scripts/full_step_profile.py); it travels to pinned host memory asynchronously instead and is looked at
+        as soon as it has landed - at the latest at the next call - where a bad prompt still raises."""
+        self._raise_if_bad_placeholders(block=False)
+        if flag.device.type != "cuda":
+            if not bool(flag):
+                raise VNError("every prompt must hold its placeholder token exactly once (net_clip_text_embedding.py:99,130)")
+            return
+        if getattr(self, "_ok_host", None) is None:
+            self._ok_host = torch.ones(1, dtype=torch.bool).pin_memory()
+            self._ok_event = torch.cuda.Event()
+        self._raise_if_bad_placeholders(block=True)          # (at most one check in flight: the previous one is read first)
+        self._ok_host.copy_(flag.reshape(1), non_blocking=True)
+        self._ok_event.record()
+        self._ok_pending = True
+
+    def _raise_if_bad_placeholders(self, block: bool) -> None:
+        if not getattr(self, "_ok_pending", False):
+            return
+        if not block and not self._ok_event.query():
+            return
+        self._ok_event.synchronize()
+        self._ok_pending = False
+        if not bool(self._ok_host[0]):
+            raise VNError("every prompt must hold its placeholder token exactly once (net_clip_text_embedding.py:99,130)")
 
     def set_mapper(self, mapper_object_lookup: Optional[Dict[int, NeTIMapper]], mapper_view: Optional[NeTIMapper],
                    device=None) -> None:
@@ -100,18 +140,18 @@ class NeTIConditioning(torch.nn.Module):
                 raise VNError("one object per batch (net_clip_text_embedding.py:67-68)")
             mapper = self.mapper_object_lookup[str(ph_o[0])]
             out = mapper(timestep=t_rep, unet_layer=l_rep, input_ids_placeholder_view=None, truncation_idx=None)
-            pos_o, good = self._positions(input_ids, torch.tensor(ph_o, device=dev))
+            pos_o, good = self._positions(input_ids, self._ids_on_device(ph_o))
             ok.append(good)
             emb[rows, pos_o] = out.word_embedding.to(emb.dtype)
             obj = (out, pos_o)
         if use_mappers and self.mapper_view is not None and ph_v is not None and not all(v == -1 for v in ph_v):   # :105-106
             out = self.mapper_view(timestep=t_rep, unet_layer=l_rep, input_ids_placeholder_view=ph_v, truncation_idx=None)
-            pos_v, good = self._positions(input_ids, torch.tensor(ph_v, device=dev))
+            pos_v, good = self._positions(input_ids, self._ids_on_device(ph_v))
             ok.append(good)
             emb[rows, pos_v] = out.word_embedding.to(emb.dtype)
             view = (out, pos_v)
-        if ok and not bool(torch.stack(ok).all()):              # one synchronisation for both checks
-            raise VNError("every prompt must hold its placeholder token exactly once (net_clip_text_embedding.py:99,130)")
+        if ok:
+            self._check_placeholders_later(torch.stack(ok).all())
         x = emb + self.position_embedding[:L]
         last = self.encoder(inputs_embeds=x)[0]
         with_bypass = None

@@ -157,17 +157,30 @@ class NeTIMapper(nn.Module):
         l = unet_layer.to(dev).float() / self.num_unet_layers * 2 - 1
         cols = [t, l]
         if self.embedding_type == "view":
-            ids = [int(i) for i in input_ids_placeholder_view]
-            vp = [self.view_tokenid_2_view_params[i] for i in ids]
-            if self.deg_freedom in ("phi", "theta-phi"):
-                th = self.scale_m1_1(torch.tensor([v[0] for v in vp], device=dev), self.theta_min, self.theta_max)
-                ph = self.scale_m1_1(torch.tensor([v[1] for v in vp], device=dev), self.phi_min, self.phi_max)
-                cols += [ph] if self.deg_freedom == "phi" else [th, ph]
-            else:
-                cam = torch.stack(vp).to(dev).float()
-                cam = self.scale_m1_1(cam, self.cam_mins.to(dev), self.cam_maxs.to(dev))
-                cols += list(cam.unbind(1))
+            cols += self._view_columns(tuple(int(i) for i in input_ids_placeholder_view), dev)
         return torch.stack(cols, dim=1).contiguous()
+
+    def _view_columns(self, ids: tuple, dev) -> list:
+        """Scaled camera parameters of the rows' view tokens as device columns.  Cached by the id tuple: they are built from
+        host numbers, and a host -> device copy from pageable memory drains the stream first (a stall per step otherwise)."""
+        cache = self.__dict__.setdefault("_view_cache", {})
+        key = (ids, str(dev), len(self.placeholder_view_token_ids))
+        cols = cache.get(key)
+        if cols is not None:
+            return cols
+        if len(cache) > 4096:
+            cache.clear()
+        vp = [self.view_tokenid_2_view_params[i] for i in ids]
+        if self.deg_freedom in ("phi", "theta-phi"):
+            th = self.scale_m1_1(torch.tensor([v[0] for v in vp], device=dev), self.theta_min, self.theta_max)
+            ph = self.scale_m1_1(torch.tensor([v[1] for v in vp], device=dev), self.phi_min, self.phi_max)
+            cols = [ph] if self.deg_freedom == "phi" else [th, ph]
+        else:
+            cam = torch.stack(vp).to(dev).float()
+            cam = self.scale_m1_1(cam, self.cam_mins.to(dev), self.cam_maxs.to(dev))
+            cols = [c.contiguous() for c in cam.unbind(1)]
+        cache[key] = cols
+        return cols
 
     def forward(self, timestep: torch.Tensor, unet_layer: torch.Tensor, input_ids_placeholder_view: torch.Tensor,
                 truncation_idx: int = None) -> MapperOutput:

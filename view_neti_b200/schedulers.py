@@ -29,7 +29,13 @@ class DDPMScheduler:
         self.alphas_cumprod = alphas_cumprod(num_train_timesteps)
 
     def _coef(self, timesteps, like):
-        acp = self.alphas_cumprod.to(device=like.device, dtype=like.dtype)[timesteps]
+        # the table is kept per (device, dtype): moving it from pageable host memory every call synchronises the stream
+        # (the runtime drains the stream before a pageable copy), which cost the train loop two full stalls per step
+        key = (like.device, like.dtype)
+        cache = self.__dict__.setdefault("_acp_cache", {})
+        if key not in cache:
+            cache[key] = self.alphas_cumprod.to(device=like.device, dtype=like.dtype)
+        acp = cache[key][timesteps]
         shape = (-1,) + (1,) * (like.ndim - 1)
         return (acp ** 0.5).reshape(shape), ((1 - acp) ** 0.5).reshape(shape)
 

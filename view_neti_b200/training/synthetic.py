@@ -53,8 +53,10 @@ def synthetic_prompt(batch: int, device="cuda", seed: int = 0, object_id: int = 
     ids[:, 0], ids[:, 5] = 49406, object_id
     view = torch.tensor([VIEW_TOKEN_IDS[i % len(VIEW_TOKEN_IDS)] for i in range(batch)])
     ids[:, 3] = view
-    return {"input_ids": ids.to(device), "input_ids_placeholder_object": torch.full((batch,), object_id, device=device),
-            "input_ids_placeholder_view": view.to(device)}
+    # the placeholder ids are host metadata, as the reference's dataloader yields them (CPU tensors): the conditioning path
+    # reads them as Python ints, and reading a CUDA tensor back would stall the host on the device every step
+    return {"input_ids": ids.to(device), "input_ids_placeholder_object": torch.full((batch,), object_id),
+            "input_ids_placeholder_view": view}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
