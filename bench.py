@@ -253,7 +253,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         # all-reduce, scale - three nodes after the backward, no host round trip.  (The REAL mapper gradients travel in the
         # `full_step` leg below, through Coach.train_step.)
         def exchange():
-            flat.copy_(plan.d_ctx.view(-1)[:MAPPER_GRAD_ELEMS])
+            flat.copy_(plan.d_ctx[:, :2].reshape(-1)[:MAPPER_GRAD_ELEMS])
             dist.all_reduce(flat)
             flat.mul_(1.0 / world)
 
