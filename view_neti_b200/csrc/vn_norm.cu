@@ -1109,8 +1109,210 @@ __global__ void __launch_bounds__(T, 1) gn_cluster_kernel(const bf16* __restrict
   gn_cluster_wait();                               // no CTA leaves while a peer may still read its s_part
 }
 
+// 16-byte items: the same cluster scheme with uint4 (8-channel) items, for channel runs that are whole 16-byte vectors
+// (G2 * cpg % 8 == 0 and cpg >= 8, i.e. every SD-2.1 width: cpg 10 -> 4 groups per cluster, 20 -> 2, 30 -> 4, 40 -> 1, 60 -> 2,
+// 80 -> 1).  A vector spans at most two groups; address arithmetic, parameter loads and the group lookup are paid once per 8
+// channels instead of once per 2 (the 4-byte kernel above spends ~190 instructions per item, profiles/r2_gn_cluster_notes.txt).
+template <int MODE, int NI, int T>
+__global__ void __launch_bounds__(T, 1) gn_cluster16_kernel(const bf16* __restrict__ x, long long ldx,
+                                                            const bf16* __restrict__ dy, long long lddy,
+                                                            const double* __restrict__ stats_in,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float eps, int silu, double* __restrict__ stats_out,
+                                                            const bf16* __restrict__ add1, long long ld1,
+                                                            const bf16* __restrict__ add2, long long ld2,
+                                                            bf16* __restrict__ y, long long ldy, int hw, int C, int groups,
+                                                            int G2, int CS) {
+  pdl_trigger();
+  __shared__ float s_w[T / 32][8];                 // per-warp partial sums: [statistic][group 0..3]
+  __shared__ double s_part[8];                     // this CTA's partials, read by the whole cluster
+  __shared__ double s_tot[8];
+  __shared__ float s_c[4][4];                      // per group of the cluster: (mean, rstd, S1, S2)
+  const uint32_t rank = gn_cluster_rank();
+  const int cl = blockIdx.x / CS;
+  const int nsets = groups / G2;
+  const int b = cl / nsets, g0 = (cl - b * nsets) * G2;
+  const int cpg = C / groups;
+  const int Wv = (G2 * cpg) >> 3;                  // 16-byte vectors per pixel in this cluster's channel run
+  const int ppc = (hw + CS - 1) / CS;
+  const int p0 = (int)rank * ppc, p1 = min(hw, p0 + ppc);
+  const int nitems = max(0, p1 - p0) * Wv;
+  const int c0 = g0 * cpg;
+  const double inv_n = 1.0 / ((double)cpg * (double)hw);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int dpx = T / Wv, dv = T - dpx * Wv;
+  const int px = t / Wv, v0 = t - px * Wv;
+  pdl_wait();
+  if (MODE == 1) {
+    if (t < G2) {
+      const double m = stats_in[((long long)b * groups + g0 + t) * 2] * inv_n;
+      const double var = fmax(fma(-m, m, stats_in[((long long)b * groups + g0 + t) * 2 + 1] * inv_n), 0.0);
+      s_c[t][0] = (float)m; s_c[t][1] = 1.0f / sqrtf((float)var + eps);
+    }
+    __syncthreads();
+  }
+  const bf16* xb = x + ((long long)b * hw + p0) * ldx + c0;
+  const bf16* db = MODE == 1 ? dy + ((long long)b * hw + p0) * lddy + c0 : xb;
+  uint4 xr[NI], dr[MODE == 1 ? NI : 1];
+  {
+    int ppx = px, vv = v0;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      xr[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (MODE == 1) dr[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (t + i * T < nitems) {
+        xr[i] = ld16(xb + (long long)ppx * ldx + vv * 8);
+        if (MODE == 1) dr[i] = ld16(db + (long long)ppx * lddy + vv * 8);
+      }
+      ppx += dpx; vv += dv;
+      if (vv >= Wv) { vv -= Wv; ++ppx; }
+    }
+  }
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;     // statistic 0 / 1 per group
+  {
+    int vv = v0;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      if (t + i * T < nitems) {
+        const int ch = vv * 8;
+        const int glo = ch / cpg;
+        const int split = (glo + 1) * cpg - ch;        // channels of this vector that belong to group glo (>= 1)
+        float xf[8];
+        unpack8(xr[i], xf);
+        float u0l = 0.f, u1l = 0.f, u0h = 0.f, u1h = 0.f;
+        if (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < split) { u0l += xf[j]; u1l = fmaf(xf[j], xf[j], u1l); }
+            else { u0h += xf[j]; u1h = fmaf(xf[j], xf[j], u1h); }
+          }
+        } else {
+          float df[8], gm[8], bt[8];
+          unpack8(dr[i], df);
+          *reinterpret_cast<float4*>(gm) = __ldg(reinterpret_cast<const float4*>(gamma + c0 + ch));
+          *reinterpret_cast<float4*>(gm + 4) = __ldg(reinterpret_cast<const float4*>(gamma + c0 + ch + 4));
+          *reinterpret_cast<float4*>(bt) = __ldg(reinterpret_cast<const float4*>(beta + c0 + ch));
+          *reinterpret_cast<float4*>(bt + 4) = __ldg(reinterpret_cast<const float4*>(beta + c0 + ch + 4));
+          const int ghi = min(glo + 1, 3);
+          const float ml = s_c[glo][0], rl = s_c[glo][1], mh = s_c[ghi][0], rh = s_c[ghi][1];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const bool lo = j < split;
+            const float xh = (xf[j] - (lo ? ml : mh)) * (lo ? rl : rh);
+            float dz = df[j];
+            if (silu) dz *= dsilu_f(fmaf(xh, gm[j], bt[j]));
+            const float dh = dz * gm[j];
+            if (lo) { u0l += dh; u1l = fmaf(dh, xh, u1l); } else { u0h += dh; u1h = fmaf(dh, xh, u1h); }
+          }
+        }
+        if (glo == 0) { a0 += u0l; q0 += u1l; a1 += u0h; q1 += u1h; }
+        else if (glo == 1) { a1 += u0l; q1 += u1l; a2 += u0h; q2 += u1h; }
+        else if (glo == 2) { a2 += u0l; q2 += u1l; a3 += u0h; q3 += u1h; }
+        else { a3 += u0l; q3 += u1l; }
+      }
+      vv += dv;
+      if (vv >= Wv) vv -= Wv;
+    }
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+  q0 = warp_sum(q0); q1 = warp_sum(q1); q2 = warp_sum(q2); q3 = warp_sum(q3);
+  if (lane == 0) {
+    s_w[warp][0] = a0; s_w[warp][1] = a1; s_w[warp][2] = a2; s_w[warp][3] = a3;
+    s_w[warp][4] = q0; s_w[warp][5] = q1; s_w[warp][6] = q2; s_w[warp][7] = q3;
+  }
+  __syncthreads();
+  if (t < 8) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < T / 32; ++k) acc += (double)s_w[k][t];           // fixed order
+    s_part[t] = acc;
+  }
+  gn_cluster_arrive();
+  gn_cluster_wait();
+  if (t < 8) {
+    const int st = t >> 2, gi = t & 3;
+    double tot = 0.0;
+    if (gi < G2) {
+      for (int r = 0; r < CS; ++r) tot += gn_ld_remote_f64(&s_part[t], (uint32_t)r);   // fixed order
+      if (rank == 0) stats_out[((long long)b * groups + g0 + gi) * 2 + st] = tot;
+    }
+    s_tot[t] = tot;
+  }
+  gn_cluster_arrive();                             // my remote reads are done
+  __syncthreads();
+  if (t < G2) {
+    if (MODE == 0) {
+      const double m = s_tot[t] * inv_n;
+      const double var = fmax(fma(-m, m, s_tot[4 + t] * inv_n), 0.0);
+      s_c[t][0] = (float)m; s_c[t][1] = 1.0f / sqrtf((float)var + eps);
+    } else {
+      s_c[t][2] = (float)(s_tot[t] * inv_n);       // S1 = sum dh / n
+      s_c[t][3] = (float)(s_tot[4 + t] * inv_n);   // S2 = sum dh*xhat / n
+    }
+  }
+  __syncthreads();
+  {
+    int ppx = px, vv = v0;
+    bf16* yb = y + ((long long)b * hw + p0) * ldy + c0;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      if (t + i * T < nitems) {
+        const int ch = vv * 8;
+        const int glo = ch / cpg;
+        const int split = (glo + 1) * cpg - ch;
+        const int ghi = min(glo + 1, 3);
+        float xf[8], gm[8], bt[8], o[8];
+        unpack8(xr[i], xf);
+        *reinterpret_cast<float4*>(gm) = __ldg(reinterpret_cast<const float4*>(gamma + c0 + ch));
+        *reinterpret_cast<float4*>(gm + 4) = __ldg(reinterpret_cast<const float4*>(gamma + c0 + ch + 4));
+        *reinterpret_cast<float4*>(bt) = __ldg(reinterpret_cast<const float4*>(beta + c0 + ch));
+        *reinterpret_cast<float4*>(bt + 4) = __ldg(reinterpret_cast<const float4*>(beta + c0 + ch + 4));
+        const float ml = s_c[glo][0], rl = s_c[glo][1], mh = s_c[ghi][0], rh = s_c[ghi][1];
+        if (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const bool lo = j < split;
+            const float z = fmaf((xf[j] - (lo ? ml : mh)) * (lo ? rl : rh), gm[j], bt[j]);
+            o[j] = silu ? silu_f(z) : z;
+          }
+        } else {
+          float df[8];
+          unpack8(dr[i], df);
+          const float S1l = s_c[glo][2], S2l = s_c[glo][3], S1h = s_c[ghi][2], S2h = s_c[ghi][3];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const bool lo = j < split;
+            const float rs = lo ? rl : rh;
+            const float xh = (xf[j] - (lo ? ml : mh)) * rs;
+            float dz = df[j];
+            if (silu) dz *= dsilu_f(fmaf(xh, gm[j], bt[j]));
+            o[j] = rs * (dz * gm[j] - (lo ? S1l : S1h) - xh * (lo ? S2l : S2h));
+          }
+          if (add1) {
+            float a[8];
+            unpack8(ld16(add1 + ((long long)b * hw + p0 + ppx) * ld1 + c0 + ch), a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += a[j];
+          }
+          if (add2) {
+            float a[8];
+            unpack8(ld16(add2 + ((long long)b * hw + p0 + ppx) * ld2 + c0 + ch), a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += a[j];
+          }
+        }
+        *reinterpret_cast<uint4*>(yb + (long long)ppx * ldy + ch) = pack8(o);
+      }
+      ppx += dpx; vv += dv;
+      if (vv >= Wv) { vv -= Wv; ++ppx; }
+    }
+  }
+  gn_cluster_wait();                               // no CTA leaves while a peer may still read its s_part
+}
+
 struct GNCluster {
   int G2, CS, T, NI;
+  int vec16;                 // 1: gn_cluster16_kernel (uint4 items), 0: gn_cluster_kernel (4-byte items)
 };
 static int g_gn_cluster = -1;
 // Shapes the cluster kernel covers: even channels per group, at most two groups per cluster, the CTA's slab in <= 32 words
@@ -1124,6 +1326,24 @@ bool gn_cluster_geom(int nb, int hw, int C, int groups, GNCluster* g) {
   const int cpg = C / groups;
   if (cpg < 2 || (cpg & 1)) return false;
   g->CS = hw >= 512 ? 8 : hw >= 128 ? 4 : hw >= 32 ? 2 : 1;
+  g->vec16 = 0;
+  if (cpg >= 8 && g_gn_cluster != 4) {            // VN_GN_CLUSTER=4: 4-byte items only (A/B switch)
+    // 16-byte items: the smallest G2 in {1, 2, 4} that makes the cluster's channel run whole vectors
+    for (int g2 = 1; g2 <= 4; g2 *= 2) {
+      if ((g2 * cpg) % 8 != 0 || groups % g2 != 0) continue;
+      const int Wv = g2 * cpg / 8;
+      const int items = vn_cdiv(hw, g->CS) * Wv;
+      static const int lim16 = getenv("VN_GN_CLUSTER_ITEMS") ? atoi(getenv("VN_GN_CLUSTER_ITEMS")) : 512;
+      if (items > (g_gn_cluster >= 2 ? 512 * 8 : lim16)) break;      // same 2048-word slab limit as below (VN_GN_CLUSTER=2 lifts it)
+      g->G2 = g2;
+      g->T = items > 1024 ? 512 : 256;
+      if (Wv > g->T) break;
+      const int per = vn_cdiv(items, g->T);
+      g->NI = per <= 4 ? 4 : (per <= 5 && g->T == 512) ? 5 : 8;
+      g->vec16 = 1;
+      return true;
+    }
+  }
   // two groups per cluster when the slab still fits (longer contiguous runs per pixel, fewer clusters); a CTA keeps at most
   // 32 words per thread at 256 threads, 16 at 512 (register budget of the backward: x and dy words both stay live)
   for (int g2 = (cpg <= 20 && groups % 2 == 0) ? 2 : 1; g2 >= 1; --g2) {
@@ -1145,7 +1365,7 @@ bool gn_cluster_geom(int nb, int hw, int C, int groups, GNCluster* g) {
   return false;
 }
 
-template <int MODE, int NI, int T>
+template <int MODE, int NI, int T, bool VEC16 = false>
 int gn_cluster_launch(const GNCluster& g, const bf16* x, long long ldx, const bf16* dy, long long lddy, const double* stats_in,
                       const float* gamma, const float* beta, float eps, int silu, double* stats_out, const bf16* add1,
                       long long ld1, const bf16* add2, long long ld2, bf16* y, long long ldy, int nb, int hw, int C,
@@ -1166,8 +1386,13 @@ int gn_cluster_launch(const GNCluster& g, const bf16* x, long long ldx, const bf
   attr[na].val.clusterDim.x = (unsigned)g.CS; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
   ++na;
   cfg.attrs = attr; cfg.numAttrs = na;
-  VN_CUDA(cudaLaunchKernelEx(&cfg, gn_cluster_kernel<MODE, NI, T>, x, ldx, dy, lddy, stats_in, gamma, beta, eps, silu, stats_out,
-                             add1, ld1, add2, ld2, y, ldy, hw, C, groups, g.G2, g.CS));
+  if constexpr (VEC16) {
+    VN_CUDA(cudaLaunchKernelEx(&cfg, gn_cluster16_kernel<MODE, NI, T>, x, ldx, dy, lddy, stats_in, gamma, beta, eps, silu,
+                               stats_out, add1, ld1, add2, ld2, y, ldy, hw, C, groups, g.G2, g.CS));
+  } else {
+    VN_CUDA(cudaLaunchKernelEx(&cfg, gn_cluster_kernel<MODE, NI, T>, x, ldx, dy, lddy, stats_in, gamma, beta, eps, silu, stats_out,
+                               add1, ld1, add2, ld2, y, ldy, hw, C, groups, g.G2, g.CS));
+  }
   vn_count_launch();
   return 0;
 }
@@ -1180,6 +1405,15 @@ int gn_cluster_dispatch(const GNCluster& g, const bf16* x, long long ldx, const 
 #define VN_GNC(NI_, T_)                                                                                                  \
   return gn_cluster_launch<MODE, NI_, T_>(g, x, ldx, dy, lddy, stats_in, gamma, beta, eps, silu, stats_out, add1, ld1, add2, \
                                           ld2, y, ldy, nb, hw, C, groups, st)
+#define VN_GNC16(NI_, T_)                                                                                                \
+  return gn_cluster_launch<MODE, NI_, T_, true>(g, x, ldx, dy, lddy, stats_in, gamma, beta, eps, silu, stats_out, add1, ld1, \
+                                                add2, ld2, y, ldy, nb, hw, C, groups, st)
+  if (g.vec16) {
+    if (g.T == 256) { if (g.NI == 4) VN_GNC16(4, 256); VN_GNC16(8, 256); }
+    if (g.NI == 4) VN_GNC16(4, 512);
+    if (g.NI == 5) VN_GNC16(5, 512);
+    VN_GNC16(8, 512);
+  }
   if (g.T == 256) {
     if (g.NI == 8) VN_GNC(8, 256);
     if (g.NI == 16) VN_GNC(16, 256);
@@ -1188,6 +1422,7 @@ int gn_cluster_dispatch(const GNCluster& g, const bf16* x, long long ldx, const 
   if (g.NI == 8) VN_GNC(8, 512);
   VN_GNC(16, 512);
 #undef VN_GNC
+#undef VN_GNC16
 }
 
 int gn_check(int C, int groups, long long ldx) {
