@@ -219,6 +219,36 @@ __device__ __forceinline__ void store8(const GemmParams& p, float (&o)[8], long 
   }
 }
 
+// store8 for the split-K finishing pass: bias (and a conv's per-image row-bias) and a bf16 residual were already added
+// from shared memory / registers by the caller
+__device__ __forceinline__ void store8_rest(const GemmParams& p, float (&o)[8], long long gm, int bidx, int n,
+                                            bool rowbias_done, bool r_done) {
+  if (p.rowbias && !rowbias_done) {
+    const float* rb = p.rowbias + (long long)bidx * p.ld_rowbias + n;
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(rb + 4));
+    o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+    o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+  }
+  if (p.R && !r_done) {                            // fp32 residual stream (the CLIP text encoder)
+    const float* rf = reinterpret_cast<const float*>(p.R) + gm * p.ldr + n;
+    const float4 r0 = *reinterpret_cast<const float4*>(rf);
+    const float4 r1 = *reinterpret_cast<const float4*>(rf + 4);
+    o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w;
+    o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
+  }
+  if (p.out_fp32) {
+    float* dst = reinterpret_cast<float*>(p.D) + gm * p.ldd + n;
+    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  } else {
+    uint4 w;
+    w.x = pack_bf162(o[0], o[1]); w.y = pack_bf162(o[2], o[3]);
+    w.z = pack_bf162(o[4], o[5]); w.w = pack_bf162(o[6], o[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.D) + gm * p.ldd + n) = w;
+  }
+}
+
 struct TileCoord {
   int m0, n0, img, h0, w0;
 };
@@ -659,7 +689,36 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     // conflict-free for the same reason.
     float* exch = reinterpret_cast<float*>(smem);
     const TileCoord c = c_first;
+    // Operands of the finishing pass that do not depend on the partials - bias (+ the per-image row-bias of a conv) of the
+    // tile and this thread's residual values - are requested NOW, while the main loop still runs: read after the second
+    // cluster barrier they cost one exposed L2 round trip per 8-column group (4 x 0.57 us on a 128-wide tile split 4
+    // ways, profiles/r1_kernel_timeline_v4.txt: "cluster sync 2" -> "epilogue done" 2.3 us).
+    constexpr int PRE = 4;                        // residual groups kept in registers per chunk
+    const int te = (int)threadIdx.x - 64;         // 0..127 in the epilogue warps
+    const int rl = te % rpo, cg = te / rpo;
+    const int ngrp = cpt / 8;
+    const bool smem_rowbias = p.rowbias && p.mode == 1;
+    const bool r16 = p.R && !p.r_fp32;
+    long long gm = 0;
+    int bidx = 0;
+    bool row_ok = false;
+    uint4 rpre[PRE];
     if (warp >= 2 && warp < 6) {
+      for (int col = te; col < BN; col += 128) {
+        float b = 0.f;
+        if (c.n0 + col < p.N) {
+          if (p.bias) b = __ldg(p.bias + c.n0 + col);
+          if (smem_rowbias) b += __ldg(p.rowbias + (long long)min(c.img, p.nbimg - 1) * p.ld_rowbias + c.n0 + col);
+        }
+        sbias[col] = b;                           // visible to the finishing threads through the two cluster barriers below
+      }
+      row_ok = tile_row(p, c, (int)crank * rpo + rl, &gm, &bidx);
+#pragma unroll
+      for (int g = 0; g < PRE; ++g) {
+        rpre[g] = make_uint4(0u, 0u, 0u, 0u);
+        const int n = c.n0 + cg * cpt + g * 8;
+        if (r16 && row_ok && g < ngrp && n < p.N) rpre[g] = *reinterpret_cast<const uint4*>(p.R + gm * p.ldr + n);
+      }
       mbar_wait(&tfull_bar[0], 0);                // my accumulator is complete => my stages are no longer read
       tc_fence_after();
       if (threadIdx.x == 64) VN_STAMP(8);
@@ -691,27 +750,39 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     cluster_sync_all();                           // all partials have landed (release / acquire at cluster scope)
     if (threadIdx.x == 64) VN_STAMP(13);
     if (warp >= 2 && warp < 6) {
-      const int te = threadIdx.x - 64;            // 0..127
-      const int rl = te % rpo;
-      const int cg = te / rpo;
-      long long gm;
-      int bidx;
-      const bool row_ok = tile_row(p, c, (int)crank * rpo + rl, &gm, &bidx);
       if (row_ok) {
-        for (int g = 0; g < cpt / 8; ++g) {
-          const int col = cg * cpt + g * 8;
-          const int n = c.n0 + col;
-          if (n >= p.N) break;
-          float o[8];
+        for (int g0 = 0; g0 < ngrp; g0 += PRE) {
+          if (g0 > 0) {                           // later chunks (wide tiles split 2 ways): their residuals together
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = 0.f;
-          for (int src = 0; src < S; ++src) {
-            const float4* e = reinterpret_cast<const float4*>(exch) + ((long long)src * (BN / 4) + (col >> 2)) * rpo + rl;
-            const float4 v0 = e[0], v1 = e[rpo];
-            o[0] += v0.x; o[1] += v0.y; o[2] += v0.z; o[3] += v0.w;
-            o[4] += v1.x; o[5] += v1.y; o[6] += v1.z; o[7] += v1.w;
+            for (int g = 0; g < PRE; ++g) {
+              const int n = c.n0 + cg * cpt + (g0 + g) * 8;
+              if (r16 && g0 + g < ngrp && n < p.N) rpre[g] = *reinterpret_cast<const uint4*>(p.R + gm * p.ldr + n);
+            }
           }
-          store8(p, o, gm, bidx, n);
+#pragma unroll
+          for (int g = 0; g < PRE; ++g) {
+            const int col = cg * cpt + (g0 + g) * 8;
+            const int n = c.n0 + col;
+            if (g0 + g < ngrp && n < p.N) {
+              const float4 b0 = *reinterpret_cast<const float4*>(sbias + col);
+              const float4 b1 = *reinterpret_cast<const float4*>(sbias + col + 4);
+              float o[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              for (int src = 0; src < S; ++src) {
+                const float4* e = reinterpret_cast<const float4*>(exch) + ((long long)src * (BN / 4) + (col >> 2)) * rpo + rl;
+                const float4 v0 = e[0], v1 = e[rpo];
+                o[0] += v0.x; o[1] += v0.y; o[2] += v0.z; o[3] += v0.w;
+                o[4] += v1.x; o[5] += v1.y; o[6] += v1.z; o[7] += v1.w;
+              }
+              if (r16) {
+                float2 f;
+                f = unpack_bf162(rpre[g].x); o[0] += f.x; o[1] += f.y;
+                f = unpack_bf162(rpre[g].y); o[2] += f.x; o[3] += f.y;
+                f = unpack_bf162(rpre[g].z); o[4] += f.x; o[5] += f.y;
+                f = unpack_bf162(rpre[g].w); o[6] += f.x; o[7] += f.y;
+              }
+              store8_rest(p, o, gm, bidx, n, smem_rowbias, r16);
+            }
+          }
         }
       }
       if (threadIdx.x == 64) VN_STAMP(9);
