@@ -60,7 +60,8 @@ void        vn_set_pdl(int enabled);
 typedef struct vn_gemm_desc {
   int32_t mode;
   int32_t M, N, K;
-  int32_t nb, H, W, C;              /* mode 1 only */
+  int32_t nb, H, W, C;              /* conv modes only: INPUT dims (mode 1: 3x3 s1 p1; 2: s2 p1, Downsample2D; 3: s2, zero beyond
+                                       the far edge only - the VAE encoder's pad (0,1,0,1); M = nb*Ho*Wo) */
   const void* A;  int64_t lda;
   const void* B;  int64_t ldb;
   void*       D;  int64_t ldd;

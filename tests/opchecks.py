@@ -299,6 +299,19 @@ def check_resample(nb, H, W, Cc):
     xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
     ref = F.conv2d(xr, w.float(), None, stride=2, padding=1)
     out.append((f"downsample {H}x{W}x{Cc} fwd", rel(D.reshape(nb, Ho, Wo, N), ref.permute(0, 2, 3, 1)), 6e-3))
+    # the same convolution with its taps read straight from the NHWC tensor map (TMA element strides 2, vn_gemm mode 2)
+    bv = rnd(N, seed=34)
+    D2 = torch.full((nb, Ho, Wo, N), 7.0, dtype=BF, device=DEV)
+    ops.conv3x3(x, conv_weight_to_k(w), D2, bias=bv, ws=ws(), stride=2, pad=1)
+    out.append((f"downsample {H}x{W}x{Cc} fwd (strided tensor map)",
+                rel(D2, ref.detach().permute(0, 2, 3, 1) + bv), 6e-3))
+    # and the VAE encoder's form: F.pad(x, (0, 1, 0, 1)) then stride 2 without padding (vn_gemm mode 3)
+    if H >= 2 and W >= 2:
+        Hp, Wp = (H - 2) // 2 + 1, (W - 2) // 2 + 1
+        D3 = torch.full((nb, Hp, Wp, N), 7.0, dtype=BF, device=DEV)
+        ops.conv3x3(x, conv_weight_to_k(w), D3, bias=bv, ws=ws(), stride=2, pad=0)
+        ref3 = F.conv2d(F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1)), w.float(), bv, stride=2)
+        out.append((f"downsample {H}x{W}x{Cc} fwd (strided tensor map, pad (0,1,0,1))", rel(D3, ref3.permute(0, 2, 3, 1)), 6e-3))
     dyo = rnd(nb, Ho, Wo, N, seed=32).to(BF)
     ref.backward(dyo.float().permute(0, 3, 1, 2))
     Wt = w.permute(2, 3, 1, 0).reshape(9 * Cc, N).contiguous()        # [9C, N]: dcol = dy @ Wk  (B = Wk^T)

@@ -60,13 +60,17 @@ def groupnorm_fwd(x, gamma, beta, eps, silu, y, nb, hw, groups, stats, partials)
     _mark(y)
 
 
-def conv3x3(x, Wk, D, *, bias=None, rowbias=None, R=None, ws=None, force_bn=0, force_split=0):
+def conv3x3(x, Wk, D, *, bias=None, rowbias=None, R=None, ws=None, force_bn=0, force_split=0, stride=1, pad=1):
     nb, H, W, C = x.shape
     N = Wk.shape[0]
-    assert Wk.shape == (N, 9 * C) and D.shape == (nb, H, W, N) and rowbias is None and C % 64 == 0 and N % 8 == 0
+    assert Wk.shape == (N, 9 * C) and rowbias is None and C % 64 == 0 and N % 8 == 0
     _no_alias(D, x, R)
     w = Wk.float().view(N, 3, 3, C).permute(0, 3, 1, 2)
-    o = F.conv2d(x.float().permute(0, 3, 1, 2), w, bias, padding=1).permute(0, 2, 3, 1)
+    xi = x.float().permute(0, 3, 1, 2)
+    if stride == 2 and pad == 0:
+        xi, pad = F.pad(xi, (0, 1, 0, 1)), 0
+    o = F.conv2d(xi, w, bias, stride=stride, padding=pad).permute(0, 2, 3, 1)
+    assert D.shape == o.shape
     D.copy_(o + R.float() if R is not None else o)
     _mark(D)
 

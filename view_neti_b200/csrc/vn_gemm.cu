@@ -56,7 +56,8 @@ struct GemmParams {
   int kb_total, kb_per_split, splits;
   int mode;
   int m_tiles, n_tiles;
-  int H, W, cblocks, tw, th, tiles_w, tiles_h, rows_a;
+  int H, W, cblocks, tw, th, tiles_w, tiles_h, rows_a;   // conv: H, W = OUTPUT grid
+  int cs, cpad;         // conv stride (1 | 2) and leading zero padding (1 | 0): tap (dx,dy) of output (w,h) reads input (w*cs + dx - cpad, ...)
   void* D; long long ldd;
   const float* bias;
   const float* rowbias; long long ld_rowbias; int rows_per_batch;
@@ -251,12 +252,13 @@ __device__ __forceinline__ void store8_rest(const GemmParams& p, float (&o)[8], 
 
 struct TileCoord {
   int m0, n0, img, h0, w0;
+  int ah0, aw0;         // conv: input coordinates of tap (0,0) of the tile's first output pixel
 };
 __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int tile, int bn) {
   TileCoord c;
   const int mt = tile % p.m_tiles;
   c.n0 = (tile / p.m_tiles) * bn;
-  c.m0 = 0; c.img = 0; c.h0 = 0; c.w0 = 0;
+  c.m0 = 0; c.img = 0; c.h0 = 0; c.w0 = 0; c.ah0 = 0; c.aw0 = 0;
   if (p.mode == 0) {
     c.m0 = mt * BM;
   } else {
@@ -265,6 +267,8 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int tile, i
     const int r = mt - c.img * tpi;
     c.h0 = (r / p.tiles_w) * p.th;
     c.w0 = (r % p.tiles_w) * p.tw;
+    c.ah0 = c.h0 * p.cs - p.cpad;
+    c.aw0 = c.w0 * p.cs - p.cpad;
   }
   return c;
 }
@@ -431,13 +435,13 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
             if (p.mode == 0) {
               tma_load_2d_cg2(sa, &tmA, fb, kx, c.m0);
             } else {
-              tma_load_4d_cg2(sa, &tmA, fb, cb * BK, c.w0 + dx - 1, c.h0 + dy - 1, c.img);
+              tma_load_4d_cg2(sa, &tmA, fb, cb * BK, c.aw0 + dx, c.ah0 + dy, c.img);
               if (++cb == p.cblocks) { cb = 0; if (++dx == 3) { dx = 0; ++dy; } }
             }
           } else if (p.mode == 0) {
             tma_load_2d(sa, &tmA, &full_bar[s], kx, c.m0);
           } else {
-            tma_load_4d(sa, &tmA, &full_bar[s], cb * BK, c.w0 + dx - 1, c.h0 + dy - 1, c.img);
+            tma_load_4d(sa, &tmA, &full_bar[s], cb * BK, c.aw0 + dx, c.ah0 + dy, c.img);
             if (++cb == p.cblocks) { cb = 0; if (++dx == 3) { dx = 0; ++dy; } }
           }
           if (MC == 1) {
@@ -939,7 +943,7 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
   GemmParams p{};
   p.M = d->M; p.N = d->N;
   p.kb_total = d->K / BK;
-  p.mode = d->mode;
+  p.mode = d->mode ? 1 : 0;                       // the kernel knows linear (0) and conv (1); stride / pad are parameters
   p.D = d->D; p.ldd = d->ldd;
   p.bias = d->bias;
   p.rowbias = d->rowbias; p.ld_rowbias = d->ld_rowbias; p.rows_per_batch = d->rows_per_batch;
@@ -953,6 +957,7 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
   memset(&td, 0, sizeof(td));
   memset(&tr, 0, sizeof(tr));
   cuuint32_t box_a[4];
+  int out_h = 0, out_w = 0;                       // conv: output grid (== input dims at stride 1)
   if (d->mode == 0) {
     VN_CHECK(d->lda >= d->K, "vn_gemm: lda < K");
     cuuint64_t dims[2] = {(cuuint64_t)d->K, (cuuint64_t)d->M};
@@ -961,23 +966,34 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
     if (make_map(&ta, d->A, 2, dims, str, box_a)) return -1;
     p.m_tiles = vn_cdiv(d->M, BM);
     p.rows_a = BM;
-  } else if (d->mode == 1) {
+  } else if (d->mode >= 1 && d->mode <= 3) {
+    // mode 1: 3x3 / stride 1 / pad 1.  mode 2: stride 2 / pad 1 (diffusers Downsample2D).  mode 3: stride 2, no leading pad,
+    // zero beyond the far edge (the VAE encoder's F.pad(x, (0,1,0,1)) + pad-0 conv).  H, W of the descriptor are the INPUT
+    // dims; the tile geometry runs over the output grid and the A map traverses the input with element strides
+    // (experiments/tma_stride2_probe.cu: box dims count source elements, the tw*th loaded pixels are compacted).
+    const int cs = d->mode == 1 ? 1 : 2, cpad = d->mode == 3 ? 0 : 1;
+    const int Ho = cs == 1 ? d->H : (cpad ? (d->H - 1) / 2 + 1 : (d->H - 2) / 2 + 1);
+    const int Wo = cs == 1 ? d->W : (cpad ? (d->W - 1) / 2 + 1 : (d->W - 2) / 2 + 1);
     VN_CHECK(d->C % BK == 0 && d->K == 9 * d->C, "vn_gemm conv: need C %% 64 == 0 and K == 9*C (C=%d K=%d)", d->C, d->K);
-    VN_CHECK(d->M == d->nb * d->H * d->W, "vn_gemm conv: M != nb*H*W");
+    VN_CHECK(Ho >= 1 && Wo >= 1 && d->M == d->nb * Ho * Wo, "vn_gemm conv: M != nb*Ho*Wo (M=%d Ho=%d Wo=%d)", d->M, Ho, Wo);
     VN_CHECK(d->lda >= d->C, "vn_gemm conv: pixel stride < C");
     int tw = 1;
-    while (tw < 64 && d->W % (tw * 2) == 0) tw *= 2;
+    while (tw < 64 && Wo % (tw * 2) == 0) tw *= 2;
     int th = BM / tw;
-    while (th > 1 && th / 2 >= d->H) th /= 2;     // do not fetch far more rows than the image has
+    while (th > 1 && th / 2 >= Ho) th /= 2;       // do not fetch far more rows than the image has
+    VN_CHECK(cs * tw <= 256 && cs * th <= 256, "vn_gemm conv: tile %d x %d too large for a stride-%d box", tw, th, cs);
     p.tw = tw; p.th = th;
-    p.tiles_w = vn_cdiv(d->W, tw);
-    p.tiles_h = vn_cdiv(d->H, th);
+    p.tiles_w = vn_cdiv(Wo, tw);
+    p.tiles_h = vn_cdiv(Ho, th);
     p.rows_a = tw * th;
-    p.H = d->H; p.W = d->W; p.cblocks = d->C / BK;
+    p.H = Ho; p.W = Wo; p.cblocks = d->C / BK;
+    p.cs = cs; p.cpad = cpad;
+    out_h = Ho; out_w = Wo;
     cuuint64_t dims[4] = {(cuuint64_t)d->C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->nb};
     cuuint64_t str[3] = {(cuuint64_t)d->lda * 2, (cuuint64_t)d->lda * 2 * d->W, (cuuint64_t)d->lda * 2 * d->W * d->H};
-    box_a[0] = BK; box_a[1] = (cuuint32_t)tw; box_a[2] = (cuuint32_t)th; box_a[3] = 1;
-    if (make_map(&ta, d->A, 4, dims, str, box_a)) return -1;
+    cuuint32_t es[4] = {1, (cuuint32_t)cs, (cuuint32_t)cs, 1};
+    box_a[0] = BK; box_a[1] = (cuuint32_t)(cs * tw); box_a[2] = (cuuint32_t)(cs * th); box_a[3] = 1;
+    if (vn_make_map(&ta, d->A, 4, dims, str, box_a, es)) return -1;
     p.m_tiles = d->nb * p.tiles_w * p.tiles_h;
   } else {
     VN_CHECK(false, "vn_gemm: unknown mode %d", d->mode);
@@ -1002,7 +1018,7 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
   p.kb_per_split = vn_cdiv(p.kb_total, splits);
   p.splits = splits;
   p.n_tiles = vn_cdiv(d->N, bn);
-  p.nbimg = d->mode == 1 ? d->nb : 1;
+  p.nbimg = d->mode != 0 ? d->nb : 1;
   p.dbg = vn_debug_buffer();
   {
     // weight look-ahead: few m-tiles stream a big weight matrix (>= 4 MB) - keep ~256 KB per CTA requested ahead
@@ -1053,9 +1069,9 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
         cuuint32_t box[2] = {64, BM};
         if (make_map(m, base, 2, dims, str, box)) return -1;
       } else {
-        cuuint64_t dims[4] = {(cuuint64_t)d->N, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->nb};
-        cuuint64_t str[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * d->W, (cuuint64_t)ld * 2 * d->W * d->H};
-        cuuint32_t box[4] = {64, box_a[1], box_a[2], 1};
+        cuuint64_t dims[4] = {(cuuint64_t)d->N, (cuuint64_t)out_w, (cuuint64_t)out_h, (cuuint64_t)d->nb};
+        cuuint64_t str[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * out_w, (cuuint64_t)ld * 2 * out_w * out_h};
+        cuuint32_t box[4] = {64, (cuuint32_t)p.tw, (cuuint32_t)p.th, 1};
         if (make_map(m, base, 4, dims, str, box)) return -1;
       }
     }

@@ -21,12 +21,12 @@ inline VnEncodeTiledFn vn_get_encode_fn() {
 
 // dims / box in elements (innermost first), strides in bytes for dims 1..rank-1.  Out-of-bounds elements read as zero.
 inline int vn_make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                       const cuuint32_t* box) {
+                       const cuuint32_t* box, const cuuint32_t* elem_strides = nullptr) {
   VnEncodeTiledFn fn = vn_get_encode_fn();
   VN_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not found (no CUDA driver?)");
   cuuint32_t ones[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
-                  box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  box, elem_strides ? elem_strides : ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)",
            (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);

@@ -15,6 +15,7 @@ buffer (torch.cat never runs); norm / bias / time-embedding parameters fp32.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Tuple
 
 import torch
@@ -24,6 +25,7 @@ from .sd21 import SD21, UNetConfig, up_block_resnet_channels
 
 BF = torch.bfloat16
 F32 = torch.float32
+_S2_TMA = os.environ.get("VN_CONV_S2_TMA", "1") != "0"      # forward stride-2 convs without im2col (0: im2col + GEMM cross-check)
 
 
 def _lin(w: torch.Tensor, dev) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -518,10 +520,13 @@ class _Plan:
             if i < nlev - 1:
                 wf, _, bias = eng.down[f"down_blocks.{i}.downsamplers.0"]
                 Ho, Wo = H // 2, W // 2
-                col = self.buf(f"down.{i}.col", (nb * Ho * Wo, 9 * ch[i]))
-                ops.im2col_s2(x.unflatten(1, (H, W)), col)
                 out = skip_home(k); k += 1
-                ops.gemm(col, wf, out, bias=bias, ws=self.ws)
+                if _S2_TMA:      # taps straight from the NHWC tensor map (element strides 2): no im2col buffer
+                    ops.conv3x3(x.unflatten(1, (H, W)), wf, out.unflatten(1, (Ho, Wo)), bias=bias, ws=self.ws, stride=2)
+                else:
+                    col = self.buf(f"down.{i}.col", (nb * Ho * Wo, 9 * ch[i]))
+                    ops.im2col_s2(x.unflatten(1, (H, W)), col)
+                    ops.gemm(col, wf, out, bias=bias, ws=self.ws)
                 x = out
                 H, W = Ho, Wo
         c = ch[-1]

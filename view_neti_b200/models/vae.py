@@ -177,6 +177,8 @@ class VAEEngine:
     # with K padded to 64, conv_out as the implicit 3x3 GEMM with N padded to 8.  False: the CUDA-core thin-conv
     # kernels of the UNet (fp32 weights; 683 us for the decoder's 128 -> 3 at 512 x 512 against ~50 us on tensor cores)
     THIN_ON_GEMM = os.environ.get("VN_VAE_THIN_GEMM", "1") != "0"
+    # the three stride-2 encoder convolutions without im2col (TMA element strides; 0: im2col + GEMM cross-check)
+    S2_TMA = os.environ.get("VN_CONV_S2_TMA", "1") != "0"
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: VAEConfig = SD21_VAE, device="cuda"):
         self.cfg = cfg
@@ -394,11 +396,15 @@ class VAEEngine:
             if i < len(ch) - 1:
                 wf, bias = self.samplers[f"encoder.down_blocks.{i}.downsamplers.0"]
                 Ho, Wo = H // 2, W // 2
-                col = self._buf("col", (nb * Ho * Wo, 9 * ch[i]))
-                ops.im2col_s2_pad0(x.view(nb, H, W, ch[i]), col)
-                x = self._buf(f"x{flip}", (nb, Ho * Wo, ch[i]))
+                y = self._buf(f"x{flip}", (nb, Ho * Wo, ch[i]))
                 flip ^= 1
-                ops.gemm(col, wf, x.view(nb * Ho * Wo, ch[i]), bias=bias, ws=self.ws)
+                if self.S2_TMA:
+                    ops.conv3x3(x.view(nb, H, W, ch[i]), wf, y.view(nb, Ho, Wo, ch[i]), bias=bias, ws=self.ws, stride=2, pad=0)
+                else:
+                    col = self._buf("col", (nb * Ho * Wo, 9 * ch[i]))
+                    ops.im2col_s2_pad0(x.view(nb, H, W, ch[i]), col)
+                    ops.gemm(col, wf, y.view(nb * Ho * Wo, ch[i]), bias=bias, ws=self.ws)
+                x = y
                 H, W = Ho, Wo
         x = self._mid("encoder.mid_block", x, H, W)
         a = self._gn(x, self.enc_norm, True)

@@ -114,15 +114,19 @@ def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, bias=None, rowbia
 
 
 def conv3x3(x: torch.Tensor, Wk: torch.Tensor, D: torch.Tensor, *, bias=None, rowbias=None, R=None,
-            ws: Optional[Workspace] = None, force_bn: int = 0, force_split: int = 0) -> torch.Tensor:
-    """Implicit-GEMM 3x3 / stride 1 / pad 1 conv.  x [nb,H,W,C] NHWC view, Wk [N, 9*C] (k = tap*C + c), D [nb,H,W,N]."""
+            ws: Optional[Workspace] = None, force_bn: int = 0, force_split: int = 0, stride: int = 1,
+            pad: int = 1) -> torch.Tensor:
+    """Implicit-GEMM 3x3 conv.  x [nb,H,W,C] NHWC view, Wk [N, 9*C] (k = tap*C + c), D [nb,Ho,Wo,N].
+    stride 1 / pad 1; stride 2 / pad 1 (Downsample2D); stride 2 / pad 0 = zero beyond the far edge only (VAE encoder)."""
     lib = _abi.load()
     nb, H, W, Cc = x.shape
     N = Wk.shape[0]
-    assert Wk.shape[1] == 9 * Cc
+    assert Wk.shape[1] == 9 * Cc and (stride, pad) in ((1, 1), (2, 1), (2, 0))
+    Ho, Wo = (H, W) if stride == 1 else (((H - 1) // 2 + 1, (W - 1) // 2 + 1) if pad else ((H - 2) // 2 + 1, (W - 2) // 2 + 1))
+    assert tuple(D.shape) == (nb, Ho, Wo, N), (tuple(D.shape), (nb, Ho, Wo, N))
     d = GemmDesc()
-    d.mode = 1
-    d.M, d.N, d.K = nb * H * W, N, 9 * Cc
+    d.mode = 1 if stride == 1 else (2 if pad else 3)
+    d.M, d.N, d.K = nb * Ho * Wo, N, 9 * Cc
     d.nb, d.H, d.W, d.C = nb, H, W, Cc
     d.A, d.lda = ptr(x), _pix_ld(x)
     d.B, d.ldb = ptr(Wk), Wk.stride(0)
@@ -130,13 +134,13 @@ def conv3x3(x: torch.Tensor, Wk: torch.Tensor, D: torch.Tensor, *, bias=None, ro
     d.out_fp32 = 1 if D.dtype == torch.float32 else 0
     d.bias = ptr(bias)
     if rowbias is not None:
-        d.rowbias, d.ld_rowbias, d.rows_per_batch = ptr(rowbias), rowbias.stride(0), H * W
+        d.rowbias, d.ld_rowbias, d.rows_per_batch = ptr(rowbias), rowbias.stride(0), Ho * Wo
     if R is not None:
         d.R, d.ldr = ptr(R), _pix_ld(R)
     if ws is not None:
         d.workspace, d.workspace_bytes = ptr(ws.buf), ws.bytes
     if not force_bn and not force_split:
-        force_bn, force_split = TUNING.get(tuning_key(1, nb * H * W, N, 9 * Cc, H, W), (0, 0))
+        force_bn, force_split = TUNING.get(tuning_key(d.mode, nb * Ho * Wo, N, 9 * Cc, H, W), (0, 0))
     d.force_bn, d.force_split = force_bn, force_split
     check(lib.vn_gemm(C.byref(d), stream()), "vn_gemm(conv)")
     return D
