@@ -27,7 +27,24 @@ namespace {
 constexpr int D = 64;
 constexpr int T = 128;                            // tile edge (queries and keys)
 constexpr int TILE_BYTES = T * 128;               // [128 rows x 64 bf16], 128B-swizzled
-constexpr int kThreads = 320;                     // producer warp, MMA warp, 8 compute warps
+// Compute warps per TMEM lane quarter.  P / dS are elementwise in the backward (row constants lse / delta are known), so
+// the 64 columns of a half tile split freely over warps: with 4 per quarter (16 compute warps, 16 columns per thread and
+// half) each scheduler has 4 warps to hide the tcgen05.ld -> ex2 -> pack -> st.shared -> fence -> arrive chain behind,
+// instead of 2 (ncu: issue utilisation 0.35 per scheduler, tensor pipe 27 % of active cycles).
+#ifndef VN_ATTN_BWD_CW
+#define VN_ATTN_BWD_CW 4
+#endif
+constexpr int kCW = VN_ATTN_BWD_CW;                // 2 or 4
+constexpr int kComputeThreads = 128 * kCW;
+constexpr int CWCOLS = 64 / kCW;                   // columns per thread and half tile
+constexpr int kThreads = 64 + kComputeThreads;     // producer warp, MMA warp, compute warps
+static_assert(kCW == 2 || kCW == 4, "compute warps per lane quarter");
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[N]) {
+  if constexpr (N == 32) tmem_ld32(taddr, v);
+  else tmem_ld16(taddr, v);
+}
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory"); }
 constexpr int TMEM_COLS = 512;
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -92,6 +109,8 @@ __device__ __forceinline__ void ld64(uint32_t taddr, uint32_t (&v)[64]) {
   tmem_ld32(taddr, c0);
   tmem_ld32(taddr + 32, c1);
 }
+__device__ __forceinline__ void ld_acc(uint32_t taddr, uint32_t (&v)[64]) { ld64(taddr, v); }
+__device__ __forceinline__ void ld_acc(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
 __device__ __forceinline__ void store_row8(uint8_t* row, int chunk, int r, const float (&e)[8]) {
   uint4 w;
   w.x = pack_bf162(e[0], e[1]); w.y = pack_bf162(e[2], e[3]);
@@ -139,7 +158,7 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 256);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kComputeThreads);
     }
     mbar_init(acc_full, 1);
     mbar_fence_init();
@@ -203,41 +222,41 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
     }
     __syncwarp();
   } else {
-    const int qd = warp & 3, hf = (warp - 2) >> 2;     // hf: which 32 of the 64 queries of a half (and dV / dK at the end)
+    const int qd = warp & 3, cs = (warp - 2) >> 2;     // cs: which CWCOLS of the 64 queries of a half (and dV / dK columns at the end)
     const int r = qd * 32 + lane;                      // key row of the tile
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     const float sl2 = p.scale * kLog2e;
     // per-query lse (pre-scaled by log2 e) and delta of a query tile live in the stage's [2][128] fp32 vector; the 256
     // compute threads fetch the NEXT tile's values into a register while they work on the current one
-    const int te = threadIdx.x - 64;                   // 0..255: [0,128) -> lse, [128,256) -> delta
+    const int te = threadIdx.x - 64;                   // [0,128) -> lse, [128,256) -> delta (threads beyond 256 fetch nothing)
     auto fetch = [&](int i) -> float {
       const int q = (qt_begin + i) * T + (te & 127);
-      if (i >= nt || q >= p.nq) return 0.f;
+      if (i >= nt || q >= p.nq || te >= 256) return 0.f;
       return te < 128 ? -p.lse[sidx + q] * kLog2e : -p.delta[sidx + q] * p.scale;     // pre-negated / pre-scaled
     };
-    reinterpret_cast<float*>(sStage + 2 * TILE_BYTES)[te] = fetch(0);
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (te < 256) reinterpret_cast<float*>(sStage + 2 * TILE_BYTES)[te] = fetch(0);
+    bar_compute();
     for (int i = 0; i < nt; ++i) {
       const int s = i & 1;
       const int q0 = (qt_begin + i) * T;
       const float next_val = fetch(i + 1);
 #pragma unroll 1
       for (int hh = 0; hh < 2; ++hh) {
-        const int cbase = hh * 64 + hf * 32;           // first query column of this thread in the tile
+        const int cbase = hh * 64 + cs * CWCOLS;       // first query column of this thread in the tile
         const float* lse = reinterpret_cast<const float*>(sStage + s * DKV_STAGE_BYTES + 2 * TILE_BYTES) + cbase;
         const float* dl = lse + T;
         mbar_wait(&s_full[hh], i & 1);
         tc_fence_after();
-        uint32_t sv[32], dp[32];
-        tmem_ld32(tST + lane_addr + cbase, sv);
-        tmem_ld32(tdPT + lane_addr + cbase, dp);
+        uint32_t sv[CWCOLS], dp[CWCOLS];
+        tmem_ld_cols(tST + lane_addr + cbase, sv);
+        tmem_ld_cols(tdPT + lane_addr + cbase, dp);
         tmem_ld_wait();
         const int qvalid = p.nq - q0 - cbase;          // queries of this slice that exist
         uint8_t* prow = sP + hh * TILE_BYTES + r * 128;
         uint8_t* drow = sdS + hh * TILE_BYTES + r * 128;
         const float2 sl2v = make_float2(sl2, sl2), scv = make_float2(p.scale, p.scale);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < CWCOLS / 8; ++g) {
           // nl = -lse * log2(e), nd = -delta * scale for 8 consecutive queries (packed f32x2 arithmetic, sm_100)
           const float4 l0 = *reinterpret_cast<const float4*>(lse + g * 8), l1 = *reinterpret_cast<const float4*>(lse + g * 8 + 4);
           const float4 d0 = *reinterpret_cast<const float4*>(dl + g * 8), d1 = *reinterpret_cast<const float4*>(dl + g * 8 + 4);
@@ -253,7 +272,7 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
             pe[2 * c] = pp.x; pe[2 * c + 1] = pp.y;
             de[2 * c] = dd.x; de[2 * c + 1] = dd.y;
           }
-          if (qvalid < 32) {                           // ragged last query tile: padded queries contribute nothing
+          if (qvalid < CWCOLS) {                       // ragged last query tile: padded queries contribute nothing
 #pragma unroll
             for (int c = 0; c < 8; ++c)
               if (g * 8 + c >= qvalid) { pe[c] = 0.f; de[c] = 0.f; }
@@ -264,41 +283,43 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
             for (int c = 0; c < 8; ++c)
               if (c < qfirst) { pe[c] = 0.f; de[c] = 0.f; }
           }
-          store_row8(prow, hf * 4 + g, r, pe);
-          store_row8(drow, hf * 4 + g, r, de);
+          store_row8(prow, cs * (CWCOLS / 8) + g, r, pe);
+          store_row8(drow, cs * (CWCOLS / 8) + g, r, de);
         }
         tc_fence_before();
         fence_async_smem();
         mbar_arrive(&p_full[hh]);
       }
-      reinterpret_cast<float*>(sStage + ((i + 1) & 1) * DKV_STAGE_BYTES + 2 * TILE_BYTES)[te] = next_val;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (te < 256) reinterpret_cast<float*>(sStage + ((i + 1) & 1) * DKV_STAGE_BYTES + 2 * TILE_BYTES)[te] = next_val;
+      bar_compute();
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    // half 0 finishes dV, half 1 finishes dK
-    uint32_t acc[64];
-    ld64((hf == 0 ? tdV : tdK) + lane_addr, acc);
+    // dV | dK sit side by side in TMEM columns [256, 384): compute warp group cs finishes 128 / kCW of those columns
+    constexpr int EW = 128 / kCW;                      // 64 (one whole accumulator) or 32 (half of one)
+    const int sel = (cs * EW) / 64, col0 = (cs * EW) % 64;            // sel 0: dV, 1: dK
+    uint32_t acc[EW];
+    ld_acc(tdV + lane_addr + cs * EW, acc);
     tmem_ld_wait();
     tc_fence_before();
     const int krow = k0 + r;
     if (slot >= 0) {
-      float* dst = p.part + (((long long)slot * 2 + (hf == 0 ? 0 : 1)) * T + r) * D;
+      float* dst = p.part + (((long long)slot * 2 + sel) * T + r) * D + col0;
 #pragma unroll
-      for (int c = 0; c < 64; c += 4)
+      for (int c = 0; c < EW; c += 4)
         *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(acc[c]), __uint_as_float(acc[c + 1]),
                                                           __uint_as_float(acc[c + 2]), __uint_as_float(acc[c + 3]));
     } else if (krow < p.nk) {
       if (ATOMIC) {
         const long long C = (long long)p.heads * D;
-        double* dst = p.dkv_acc + (hf == 0 ? (long long)p.nb * p.nk * C : 0) + ((long long)b * p.nk + krow) * C + h * D;
+        double* dst = p.dkv_acc + (sel == 0 ? (long long)p.nb * p.nk * C : 0) + ((long long)b * p.nk + krow) * C + h * D + col0;
 #pragma unroll
-        for (int c = 0; c < 64; ++c) atomicAdd(dst + c, (double)__uint_as_float(acc[c]));
+        for (int c = 0; c < EW; ++c) atomicAdd(dst + c, (double)__uint_as_float(acc[c]));
       } else {
-        bf16* dst = hf == 0 ? p.dv + (long long)b * p.bsdv + (long long)krow * p.lddv + h * D
-                            : p.dk + (long long)b * p.bsdk + (long long)krow * p.lddk + h * D;
+        bf16* dst = (sel == 0 ? p.dv + (long long)b * p.bsdv + (long long)krow * p.lddv
+                              : p.dk + (long long)b * p.bsdk + (long long)krow * p.lddk) + h * D + col0;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
+        for (int g = 0; g < EW / 8; ++g) {
           uint4 w;
           w.x = pack_bf162(__uint_as_float(acc[g * 8 + 0]), __uint_as_float(acc[g * 8 + 1]));
           w.y = pack_bf162(__uint_as_float(acc[g * 8 + 2]), __uint_as_float(acc[g * 8 + 3]));
@@ -350,7 +371,7 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 256);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kComputeThreads);
     }
     mbar_init(acc_full, 1);
     mbar_fence_init();
@@ -408,7 +429,7 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
     }
     __syncwarp();
   } else {
-    const int qd = warp & 3, hf = (warp - 2) >> 2;
+    const int qd = warp & 3, cs = (warp - 2) >> 2;
     const int r = qd * 32 + lane;                      // query row of the tile
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     const float sl2 = p.scale * kLog2e;
@@ -419,19 +440,19 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
     for (int j = 0; j < nt; ++j) {
 #pragma unroll 1
       for (int hh = 0; hh < 2; ++hh) {
-        const int cbase = hh * 64 + hf * 32;           // first key column of this thread in the tile
+        const int cbase = hh * 64 + cs * CWCOLS;       // first key column of this thread in the tile
         mbar_wait(&s_full[hh], j & 1);
         tc_fence_after();
-        uint32_t sv[32], dp[32];
-        tmem_ld32(tS + lane_addr + cbase, sv);
-        tmem_ld32(tdP + lane_addr + cbase, dp);
+        uint32_t sv[CWCOLS], dp[CWCOLS];
+        tmem_ld_cols(tS + lane_addr + cbase, sv);
+        tmem_ld_cols(tdP + lane_addr + cbase, dp);
         tmem_ld_wait();
         const int kvalid = p.nk - (kt0 + j) * T - cbase;
         uint8_t* drow = sdS + hh * TILE_BYTES + r * 128;
         const float2 sl2v = make_float2(sl2, sl2), scv = make_float2(p.scale, p.scale);
         const float2 nlv = make_float2(nlse2, nlse2), ndv = make_float2(ndl, ndl);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < CWCOLS / 8; ++g) {
           float de[8];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -441,7 +462,7 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
             const float2 dd = __fmul2_rn(pp, tt);
             de[2 * c] = dd.x; de[2 * c + 1] = dd.y;
           }
-          if (kvalid < 32) {                           // ragged last key tile
+          if (kvalid < CWCOLS) {                       // ragged last key tile
 #pragma unroll
             for (int c = 0; c < 8; ++c)
               if (g * 8 + c >= kvalid) de[c] = 0.f;
@@ -452,7 +473,7 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
             for (int c = 0; c < 8; ++c)
               if (c > klast) de[c] = 0.f;
           }
-          store_row8(drow, hf * 4 + g, r, de);
+          store_row8(drow, cs * (CWCOLS / 8) + g, r, de);
         }
         tc_fence_before();
         fence_async_smem();
@@ -461,20 +482,21 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    uint32_t acc[32];
-    tmem_ld32(tdQ + lane_addr + hf * 32, acc);
+    constexpr int QW = 64 / kCW;                       // dQ columns finished per thread
+    uint32_t acc[QW];
+    tmem_ld_cols(tdQ + lane_addr + cs * QW, acc);
     tmem_ld_wait();
     tc_fence_before();
     if (slot >= 0) {
-      float* dst = p.part + (((long long)slot * 2) * T + r) * D + hf * 32;
+      float* dst = p.part + (((long long)slot * 2) * T + r) * D + cs * QW;
 #pragma unroll
-      for (int c = 0; c < 32; c += 4)
+      for (int c = 0; c < QW; c += 4)
         *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(acc[c]), __uint_as_float(acc[c + 1]),
                                                           __uint_as_float(acc[c + 2]), __uint_as_float(acc[c + 3]));
     } else if (row < p.nq) {
-      bf16* dst = p.dq + (long long)b * p.bsdq + (long long)row * p.lddq + h * D + hf * 32;
+      bf16* dst = p.dq + (long long)b * p.bsdq + (long long)row * p.lddq + h * D + cs * QW;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+      for (int g = 0; g < QW / 8; ++g) {
         uint4 w;
         w.x = pack_bf162(__uint_as_float(acc[g * 8 + 0]), __uint_as_float(acc[g * 8 + 1]));
         w.y = pack_bf162(__uint_as_float(acc[g * 8 + 2]), __uint_as_float(acc[g * 8 + 3]));
