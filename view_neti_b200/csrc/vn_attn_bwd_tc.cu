@@ -44,6 +44,27 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[N]) {
   if constexpr (N == 32) tmem_ld32(taddr, v);
   else tmem_ld16(taddr, v);
 }
+// P^T / dS^T (dK/dV body) and dS (dQ body) go back into TENSOR memory as packed bf16 pairs and feed the second product as
+// its A operand from there: with A in shared memory a 128 x 64 x 16 MMA reads 4 KB (A) + 2 KB (B) per 32 tensor cycles -
+// 192 B/clk against the 128 B/clk shared-memory port - and the compute warps pay 64 KB of swizzled stores + a proxy fence
+// per tile pair.  VN_ATTN_BWD_TS=0 keeps the shared-memory operand (cross-check).
+#ifndef VN_ATTN_BWD_TS
+#define VN_ATTN_BWD_TS 1
+#endif
+constexpr bool kTS = VN_ATTN_BWD_TS != 0;
+constexpr int T_PT = 384, T_DST = 448;             // TMEM columns of the packed operands: 2 halves x 32 columns each
+template <int N>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&v)[N]) {
+  if constexpr (N == 16) tmem_st16(taddr, v);
+  else tmem_st8(taddr, v);
+}
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr);
+// D[128 x 64] (+)= A[tensor memory: 128 lanes x 64 k as 32 packed columns] * B[k-rows h*64.. of the MN-major tile]
+__device__ __forceinline__ void mma_tmn_half(uint32_t tacc, uint32_t ta, uint32_t b, int h, uint32_t id, bool accumulate) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_bf16_ts(tacc, ta + (uint32_t)(k * 8), desc_mn_sw128(b + (h * 4 + k) * 2048), id, (accumulate || k) ? 1u : 0u);
+}
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory"); }
 constexpr int TMEM_COLS = 512;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -102,6 +123,20 @@ __device__ __forceinline__ void mma_kmn_half(uint32_t tacc, uint32_t a, uint32_t
   for (int k = 0; k < 4; ++k)
     umma_bf16(tacc, umma_desc_k_sw128(a + h * TILE_BYTES) + (uint64_t)(k * 2), desc_mn_sw128(b + (h * 4 + k) * 2048), id,
               (accumulate || k) ? 1u : 0u);
+}
+// The same products from PRECOMPUTED tile descriptors.  All operand tiles are 1024-byte aligned and below 256 KB, so the
+// descriptor of (tile + off) is the tile's descriptor plus (off >> 4) in the 14-bit start-address field: one 64-bit add per
+// MMA in the single issuing thread instead of rebuilding the descriptor (shift, two masks, merge) in front of every
+// tcgen05.mma - the issue thread is on the critical path between the compute warps' arrive and the next S / dP.
+__device__ __forceinline__ void mma_kk_half_d(uint32_t tacc, uint64_t da, uint64_t db, int h, uint32_t id64) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_bf16(tacc + (uint32_t)(h * 64), da + (uint64_t)(k * 2), db + (uint64_t)(h * 512 + k * 2), id64, k ? 1u : 0u);
+}
+__device__ __forceinline__ void mma_tmn_half_d(uint32_t tacc, uint32_t ta, uint64_t dbmn, int h, uint32_t id, bool accumulate) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_bf16_ts(tacc, ta + (uint32_t)(k * 8), dbmn + (uint64_t)((h * 4 + k) * 128), id, (accumulate || k) ? 1u : 0u);
 }
 __device__ __forceinline__ void ld64(uint32_t taddr, uint32_t (&v)[64]) {
   uint32_t(&c0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
@@ -187,17 +222,25 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                                  // warp-uniform control flow; one elected lane issues
+      const bool leader = elect_one();
       constexpr uint32_t id_s = idesc(T, 64, 0);       // 128 keys x 64 queries, both K-major
       constexpr uint32_t id_acc = idesc(T, D, 1);      // 128 x 64, B MN-major
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), adS = smem_u32(sdS);
       // Software pipeline over 64-query halves: while the compute warps turn S^T/dP^T of one half into P^T/dS^T, the
       // tensor pipe accumulates dV/dK of the other half and produces the next S^T/dP^T.
+      const uint64_t dKk = umma_desc_k_sw128(aK), dVk = umma_desc_k_sw128(aV);
+      const uint32_t aSt0 = smem_u32(sStage), aSt1 = aSt0 + DKV_STAGE_BYTES;
+      const uint64_t dQk[2] = {umma_desc_k_sw128(aSt0), umma_desc_k_sw128(aSt1)};
+      const uint64_t ddOk[2] = {umma_desc_k_sw128(aSt0 + TILE_BYTES), umma_desc_k_sw128(aSt1 + TILE_BYTES)};
+      const uint64_t dQmn[2] = {desc_mn_sw128(aSt0), desc_mn_sw128(aSt1)};
+      const uint64_t ddOmn[2] = {desc_mn_sw128(aSt0 + TILE_BYTES), desc_mn_sw128(aSt1 + TILE_BYTES)};
       auto issue_sdp = [&](int i, int hh) {            // S^T_h = K Q_h^T, dP^T_h = V dO_h^T of query tile i
-        const uint32_t aQ = smem_u32(sStage + (i & 1) * DKV_STAGE_BYTES), adO = aQ + TILE_BYTES;
-        mma_kk_half(tST, aK, aQ, hh, id_s);
-        mma_kk_half(tdPT, aV, adO, hh, id_s);
-        umma_commit(&s_full[hh]);                      // in-order retirement: also covers dV/dK(i-1, h) -> sP/sdS block h free
+        if (leader) {
+          mma_kk_half_d(tST, dKk, dQk[i & 1], hh, id_s);
+          mma_kk_half_d(tdPT, dVk, ddOk[i & 1], hh, id_s);
+          umma_commit(&s_full[hh]);                    // in-order retirement: also covers dV/dK(i-1, h) -> operand block h free
+        }
       };
       mbar_wait(kv_full, 0);
       mbar_wait(&st_full[0], 0);
@@ -209,16 +252,23 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
         for (int hh = 0; hh < 2; ++hh) {
           mbar_wait(&p_full[hh], i & 1);               // P^T_h / dS^T_h in smem; TMEM half h has been read
           tc_fence_after();
-          mma_kmn_half(tdV, aP, adO, hh, id_acc, i > 0 || hh > 0);     // dV += P^T_h dO_h
-          mma_kmn_half(tdK, adS, aQ, hh, id_acc, i > 0 || hh > 0);     // dK += dS^T_h Q_h
-          if (hh == 1) umma_commit(&st_empty[i & 1]);
+          if (leader) {
+            if (kTS) {
+              mma_tmn_half_d(tdV, tmem_base + T_PT + hh * 32, ddOmn[i & 1], hh, id_acc, i > 0 || hh > 0);   // dV += P^T_h dO_h
+              mma_tmn_half_d(tdK, tmem_base + T_DST + hh * 32, dQmn[i & 1], hh, id_acc, i > 0 || hh > 0);   // dK += dS^T_h Q_h
+            } else {
+              mma_kmn_half(tdV, aP, adO, hh, id_acc, i > 0 || hh > 0);
+              mma_kmn_half(tdK, adS, aQ, hh, id_acc, i > 0 || hh > 0);
+            }
+            if (hh == 1) umma_commit(&st_empty[i & 1]);
+          }
           if (i + 1 < nt) {
             if (hh == 0) { mbar_wait(&st_full[(i + 1) & 1], ((i + 1) >> 1) & 1); tc_fence_after(); }
             issue_sdp(i + 1, hh);
           }
         }
       }
-      umma_commit(acc_full);
+      if (leader) umma_commit(acc_full);
     }
     __syncwarp();
   } else {
@@ -254,6 +304,7 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
         const int qvalid = p.nq - q0 - cbase;          // queries of this slice that exist
         uint8_t* prow = sP + hh * TILE_BYTES + r * 128;
         uint8_t* drow = sdS + hh * TILE_BYTES + r * 128;
+        uint32_t pw[CWCOLS / 2], dw[CWCOLS / 2];      // packed bf16 pairs for the tensor-memory operand
         const float2 sl2v = make_float2(sl2, sl2), scv = make_float2(p.scale, p.scale);
 #pragma unroll
         for (int g = 0; g < CWCOLS / 8; ++g) {
@@ -283,11 +334,26 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
             for (int c = 0; c < 8; ++c)
               if (c < qfirst) { pe[c] = 0.f; de[c] = 0.f; }
           }
-          store_row8(prow, cs * (CWCOLS / 8) + g, r, pe);
-          store_row8(drow, cs * (CWCOLS / 8) + g, r, de);
+          if (kTS) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              pw[g * 4 + c] = pack_bf162(pe[2 * c], pe[2 * c + 1]);
+              dw[g * 4 + c] = pack_bf162(de[2 * c], de[2 * c + 1]);
+            }
+          } else {
+            store_row8(prow, cs * (CWCOLS / 8) + g, r, pe);
+            store_row8(drow, cs * (CWCOLS / 8) + g, r, de);
+          }
         }
-        tc_fence_before();
-        fence_async_smem();
+        if (kTS) {
+          tmem_st_cols(tmem_base + lane_addr + T_PT + (uint32_t)(cbase >> 1), pw);
+          tmem_st_cols(tmem_base + lane_addr + T_DST + (uint32_t)(cbase >> 1), dw);
+          tmem_st_wait();
+          tc_fence_before();
+        } else {
+          tc_fence_before();
+          fence_async_smem();
+        }
         mbar_arrive(&p_full[hh]);
       }
       if (te < 256) reinterpret_cast<float*>(sStage + ((i + 1) & 1) * DKV_STAGE_BYTES + 2 * TILE_BYTES)[te] = next_val;
@@ -397,15 +463,22 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                                  // warp-uniform control flow; one elected lane issues
+      const bool leader = elect_one();
       constexpr uint32_t id_s = idesc(T, 64, 0);       // 128 queries x 64 keys
       constexpr uint32_t id_acc = idesc(T, D, 1);
       const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), adS = smem_u32(sdS);
+      const uint64_t dQk = umma_desc_k_sw128(aQ), ddOk = umma_desc_k_sw128(adO);
+      const uint32_t aKV0 = smem_u32(sKV), aKV1 = aKV0 + 2 * TILE_BYTES;
+      const uint64_t dKk[2] = {umma_desc_k_sw128(aKV0), umma_desc_k_sw128(aKV1)};
+      const uint64_t dVk[2] = {umma_desc_k_sw128(aKV0 + TILE_BYTES), umma_desc_k_sw128(aKV1 + TILE_BYTES)};
+      const uint64_t dKmn[2] = {desc_mn_sw128(aKV0), desc_mn_sw128(aKV1)};
       auto issue_sdp = [&](int j, int hh) {            // S_h = Q K_h^T, dP_h = dO V_h^T of key tile j
-        const uint32_t aK = smem_u32(sKV + (j & 1) * 2 * TILE_BYTES), aV = aK + TILE_BYTES;
-        mma_kk_half(tS, aQ, aK, hh, id_s);
-        mma_kk_half(tdP, adO, aV, hh, id_s);
-        umma_commit(&s_full[hh]);
+        if (leader) {
+          mma_kk_half_d(tS, dQk, dKk[j & 1], hh, id_s);
+          mma_kk_half_d(tdP, ddOk, dVk[j & 1], hh, id_s);
+          umma_commit(&s_full[hh]);
+        }
       };
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
@@ -417,15 +490,18 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
         for (int hh = 0; hh < 2; ++hh) {
           mbar_wait(&p_full[hh], j & 1);
           tc_fence_after();
-          mma_kmn_half(tdQ, adS, aK, hh, id_acc, j > 0 || hh > 0);     // dQ += dS_h K_h
-          if (hh == 1) umma_commit(&kv_empty[j & 1]);
+          if (leader) {
+            if (kTS) mma_tmn_half_d(tdQ, tmem_base + T_PT + hh * 32, dKmn[j & 1], hh, id_acc, j > 0 || hh > 0);     // dQ += dS_h K_h
+            else mma_kmn_half(tdQ, adS, aK, hh, id_acc, j > 0 || hh > 0);
+            if (hh == 1) umma_commit(&kv_empty[j & 1]);
+          }
           if (j + 1 < nt) {
             if (hh == 0) { mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1); tc_fence_after(); }
             issue_sdp(j + 1, hh);
           }
         }
       }
-      umma_commit(acc_full);
+      if (leader) umma_commit(acc_full);
     }
     __syncwarp();
   } else {
@@ -449,6 +525,7 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
         tmem_ld_wait();
         const int kvalid = p.nk - (kt0 + j) * T - cbase;
         uint8_t* drow = sdS + hh * TILE_BYTES + r * 128;
+        uint32_t dw[CWCOLS / 2];
         const float2 sl2v = make_float2(sl2, sl2), scv = make_float2(p.scale, p.scale);
         const float2 nlv = make_float2(nlse2, nlse2), ndv = make_float2(ndl, ndl);
 #pragma unroll
@@ -473,10 +550,21 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
             for (int c = 0; c < 8; ++c)
               if (c > klast) de[c] = 0.f;
           }
-          store_row8(drow, cs * (CWCOLS / 8) + g, r, de);
+          if (kTS) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dw[g * 4 + c] = pack_bf162(de[2 * c], de[2 * c + 1]);
+          } else {
+            store_row8(drow, cs * (CWCOLS / 8) + g, r, de);
+          }
         }
-        tc_fence_before();
-        fence_async_smem();
+        if (kTS) {
+          tmem_st_cols(tmem_base + lane_addr + T_PT + (uint32_t)(cbase >> 1), dw);
+          tmem_st_wait();
+          tc_fence_before();
+        } else {
+          tc_fence_before();
+          fence_async_smem();
+        }
         mbar_arrive(&p_full[hh]);
       }
     }
