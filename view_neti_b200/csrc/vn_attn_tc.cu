@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                              // warp-uniform control flow, one elected lane issues (vn_common.cuh: elect_one)
+      const bool leader = elect_one();
       constexpr uint32_t idesc_s = idesc_bf16(BQ, BKV, 0);
       constexpr uint32_t idesc_pv = idesc_bf16(BQ, D, 1);
       const uint32_t aQ = smem_u32(sQ);
@@ -166,12 +167,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
         tc_fence_after();
         const uint32_t aK = smem_u32(sKV + s * 2 * TILE_BYTES);
         const uint32_t tS = tmem_base + (uint32_t)((j & 1) * BKV);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k)
-          umma_bf16(tS, umma_desc_k_sw128(aQ) + (uint64_t)(k * 2), umma_desc_k_sw128(aK) + (uint64_t)(k * 2), idesc_s,
-                    k ? 1u : 0u);
-        umma_commit(&s_full[j & 1]);
-        if (last_of_segment) umma_commit(q_empty);
+          for (int k = 0; k < D / 16; ++k)
+            umma_bf16(tS, umma_desc_k_sw128(aQ) + (uint64_t)(k * 2), umma_desc_k_sw128(aK) + (uint64_t)(k * 2), idesc_s,
+                      k ? 1u : 0u);
+          umma_commit(&s_full[j & 1]);
+          if (last_of_segment) umma_commit(q_empty);
+        }
       };
       int it0 = 0;
       for (int seg = 0; seg < nseg; ++seg) {
@@ -189,15 +192,17 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
         const uint32_t aP = smem_u32(sP + (j & 1) * 2 * TILE_BYTES);
         const uint32_t aV = smem_u32(sKV + s * 2 * TILE_BYTES + TILE_BYTES);
         const uint32_t tPV = tmem_base + 2 * BKV + (uint32_t)((j & 1) * 2 * D);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          // keys [0,64) accumulate into PV[j&1][0], keys [64,128) into PV[j&1][1]
-          const uint64_t adesc = umma_desc_k_sw128(aP + (k >> 2) * TILE_BYTES) + (uint64_t)((k & 3) * 2);
-          const uint64_t bdesc = umma_desc_mn_sw128(aV + k * 2048);
-          umma_bf16(tPV + (uint32_t)((k >> 2) * D), adesc, bdesc, idesc_pv, (k & 3) ? 1u : 0u);
+          for (int k = 0; k < BKV / 16; ++k) {
+            // keys [0,64) accumulate into PV[j&1][0], keys [64,128) into PV[j&1][1]
+            const uint64_t adesc = umma_desc_k_sw128(aP + (k >> 2) * TILE_BYTES) + (uint64_t)((k & 3) * 2);
+            const uint64_t bdesc = umma_desc_mn_sw128(aV + k * 2048);
+            umma_bf16(tPV + (uint32_t)((k >> 2) * D), adesc, bdesc, idesc_pv, (k & 3) ? 1u : 0u);
+          }
+          umma_commit(&kv_empty[s]);         // K(j) (read by S(j), issued earlier) and V(j) are no longer needed
+          umma_commit(&pv_full[j & 1]);
         }
-        umma_commit(&kv_empty[s]);           // K(j) (read by S(j), issued earlier) and V(j) are no longer needed
-        umma_commit(&pv_full[j & 1]);
       }
       it0 += n;
       }

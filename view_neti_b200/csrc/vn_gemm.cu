@@ -502,7 +502,11 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     __syncwarp();
   } else if (warp == 1) {
     // ================= MMA issuer (CG == 2: the leader CTA issues for the pair) =================
-    if (lane == 0 && (CG == 1 || crank == 0)) {
+    // The whole warp runs the loop (warp-uniform control flow) and ONE elected lane issues: descriptors and tensor-memory
+    // addresses then live in uniform registers and the tcgen05.mma of a k-block go out back to back; under a divergent
+    // `if (lane == 0)` each one was wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~9 instructions per MMA).
+    if (CG == 1 || crank == 0) {
+      const bool leader = elect_one();
       int s = 0, t = 0;
       uint32_t ph = 0;                             // parity to wait for on full_bar[s]
       const uint64_t desc0 = umma_desc_k_sw128(smem_u32(smem));          // stage 0, A operand
@@ -522,23 +526,27 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
         for (int i = 0; i < nkb; ++i) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          if (i == 0 && t == 0) VN_STAMP(6);
+          if (i == 0 && t == 0 && leader) VN_STAMP(6);
           const uint64_t adesc = desc0 + (uint64_t)s * kStageStep;
           const uint64_t bdesc = adesc + kBOffset;
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            if (CG == 2) umma_bf16_cg2(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) ? 1u : 0u);
-            else umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+              if (CG == 2) umma_bf16_cg2(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) ? 1u : 0u);
+              else umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) ? 1u : 0u);
+            }
+            if (CG == 2) umma_commit_cg2(&empty_bar[s], 3);   // the stage is free in BOTH CTAs of the pair
+            else if (MC == 1) umma_commit(&empty_bar[s]);   // frees this smem stage when the MMAs above have read it
+            else umma_commit_mc(&empty_bar[s], (uint16_t)((1u << MC) - 1));
           }
-          if (CG == 2) umma_commit_cg2(&empty_bar[s], 3);   // the stage is free in BOTH CTAs of the pair
-          else if (MC == 1) umma_commit(&empty_bar[s]);   // frees this smem stage when the MMAs above have read it
-          else umma_commit_mc(&empty_bar[s], (uint16_t)((1u << MC) - 1));
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        if (CG == 2) umma_commit_cg2(&tfull_bar[as], 3);   // both halves of the pair's accumulator are complete
-        else umma_commit(&tfull_bar[as]);             // accumulator complete
-        if (t == 0) VN_STAMP(7);
+        if (leader) {
+          if (CG == 2) umma_commit_cg2(&tfull_bar[as], 3);   // both halves of the pair's accumulator are complete
+          else umma_commit(&tfull_bar[as]);             // accumulator complete
+        }
+        if (t == 0 && leader) VN_STAMP(7);
       }
     }
     __syncwarp();
