@@ -411,8 +411,11 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     // ================= TMA producer =================
     // One thread issues every load; its per-k-block instruction chain is on the critical path of the whole main loop
     // (a stage is re-armed only after this thread has seen it drained), so the loop carries no division or modulo:
-    // stage index / phase and the conv (tap, channel-block) coordinates advance incrementally.
-    if (lane == 0) {
+    // stage index / phase and the conv (tap, channel-block) coordinates advance incrementally.  The warp's control flow is
+    // uniform and one ELECTED lane issues (elect_one): coordinates, barrier addresses and the tensor-map pointer stay in
+    // uniform registers instead of being broadcast lane by lane in front of every cp.async.bulk.tensor.
+    {
+      const bool leader = elect_one();
       const uint32_t tx_bytes = (uint32_t)(CG * (p.rows_a * BK * 2 + B_BYTES));      // both CTAs of a pair
       const uint32_t lead_full = CG == 2 ? mapa_shared(smem_u32(full_bar), 0) : 0;  // leader's full_bar[0]
       int s = 0, t = 0;
@@ -428,21 +431,20 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
         }
         for (int i = 0; i < nkb; ++i) {
           mbar_wait(&empty_bar[s], ph);
-          if (CG == 1 || crank == 0) mbar_expect_tx(&full_bar[s], tx_bytes);
           uint8_t* sa = smem + s * STAGE_BYTES;
+          if (leader) {
+          if (CG == 1 || crank == 0) mbar_expect_tx(&full_bar[s], tx_bytes);
           if (CG == 2) {
             const uint32_t fb = lead_full + (uint32_t)(s * 8);
             if (p.mode == 0) {
               tma_load_2d_cg2(sa, &tmA, fb, kx, c.m0);
             } else {
               tma_load_4d_cg2(sa, &tmA, fb, cb * BK, c.aw0 + dx, c.ah0 + dy, c.img);
-              if (++cb == p.cblocks) { cb = 0; if (++dx == 3) { dx = 0; ++dy; } }
             }
           } else if (p.mode == 0) {
             tma_load_2d(sa, &tmA, &full_bar[s], kx, c.m0);
           } else {
             tma_load_4d(sa, &tmA, &full_bar[s], cb * BK, c.aw0 + dx, c.ah0 + dy, c.img);
-            if (++cb == p.cblocks) { cb = 0; if (++dx == 3) { dx = 0; ++dy; } }
           }
           if (MC == 1) {
             if (kProducers == 1) tma_load_2d(sa + A_BYTES, &tmB, &full_bar[s], kx, c.n0);
@@ -452,19 +454,23 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
             tma_load_2d_mc(sa + A_BYTES + (int)crank * SLICE * 128, &tmB, &full_bar[s], kx, c.n0 + (int)crank * SLICE,
                            (uint16_t)((1u << MC) - 1));
           }
+          }                                        // leader
+          if (p.mode != 0 && ++cb == p.cblocks) { cb = 0; if (++dx == 3) { dx = 0; ++dy; } }
           kx += BK;
           if (++s == STAGES) { s = 0; ph ^= 1u; }
-          if (i == 0 && t == 0) VN_STAMP(4);
+          if (i == 0 && t == 0 && leader) VN_STAMP(4);
         }
-        if (t == 0) VN_STAMP(5);
+        if (t == 0 && leader) VN_STAMP(5);
         if (tma_epi && p.R) {
           // residual tile -> staging, once the previous tile's store has finished reading it
           mbar_wait(sfree_bar, (t & 1) ^ 1);
           const int nblk = min(BN / 64, (p.N - c.n0 + 63) / 64);
-          mbar_expect_tx(rfull_bar, (uint32_t)(nblk * p.rows_a * 128));
-          for (int j = 0; j < nblk; ++j) {
-            if (p.mode == 0) tma_load_2d(staging + j * (BM * 128), &tmR, rfull_bar, c.n0 + j * 64, c.m0);
-            else tma_load_4d(staging + j * (BM * 128), &tmR, rfull_bar, c.n0 + j * 64, c.w0, c.h0, c.img);
+          if (leader) {
+            mbar_expect_tx(rfull_bar, (uint32_t)(nblk * p.rows_a * 128));
+            for (int j = 0; j < nblk; ++j) {
+              if (p.mode == 0) tma_load_2d(staging + j * (BM * 128), &tmR, rfull_bar, c.n0 + j * 64, c.m0);
+              else tma_load_4d(staging + j * (BM * 128), &tmR, rfull_bar, c.n0 + j * 64, c.w0, c.h0, c.img);
+            }
           }
         }
       }
@@ -475,7 +481,9 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     // Issue latency of the single producer thread bounds the main loop; the B loads of a stage need nothing from the
     // A producer but the drained stage (same empty barrier) - their complete_tx may land before its expect_tx, the
     // phase cannot complete until that arrival.
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
+      const int b_pre_w = __shfl_sync(0xffffffffu, b_pre, 0);        // lane 0 put the first b_pre weight tiles in flight above
       int s = 0;
       uint32_t ph = 1;
       const uint32_t lead_full = CG == 2 ? mapa_shared(smem_u32(full_bar), 0) : 0;
@@ -488,11 +496,13 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
         }
         int kx = kb_begin * BK;
         for (int i = 0; i < nkb; ++i) {
-          if (p.pf_dist > 0 && i + p.pf_dist < nkb) tma_prefetch_l2_2d(&tmB, kx + p.pf_dist * BK, n0);
-          if (w != tile_begin || i >= b_pre) {             // (the first b_pre tiles of the first tile are already in flight)
+          if (leader && p.pf_dist > 0 && i + p.pf_dist < nkb) tma_prefetch_l2_2d(&tmB, kx + p.pf_dist * BK, n0);
+          if (w != tile_begin || i >= b_pre_w) {           // (the first b_pre tiles of the first tile are already in flight)
             mbar_wait(&empty_bar[s], ph);
-            if (CG == 2) tma_load_2d_cg2(smem + s * STAGE_BYTES + A_BYTES, &tmB, lead_full + (uint32_t)(s * 8), kx, n0);
-            else tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &tmB, &full_bar[s], kx, n0);
+            if (leader) {
+              if (CG == 2) tma_load_2d_cg2(smem + s * STAGE_BYTES + A_BYTES, &tmB, lead_full + (uint32_t)(s * 8), kx, n0);
+              else tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &tmB, &full_bar[s], kx, n0);
+            }
           }
           kx += BK;
           if (++s == STAGES) { s = 0; ph ^= 1u; }
