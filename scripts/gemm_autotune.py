@@ -30,6 +30,8 @@ def rec_gemm(A, B, D, **kw):
 
 def rec_conv(x, Wk, D, **kw):
     nb, H, W, C = x.shape
+    if kw.get("stride", 1) != 1:                    # strided tensor-map convs (3 per forward) keep the cost model's choice
+        return orig_conv(x, Wk, D, **kw)
     key = ops.tuning_key(1, nb * H * W, Wk.shape[0], 9 * C, H, W)
     seen.setdefault(key, ("conv", nb * H * W, Wk.shape[0], C, (nb, H, W), kw.get("bias") is not None, kw.get("R") is not None, False))
     return orig_conv(x, Wk, D, **kw)
@@ -71,6 +73,8 @@ for key, (kind, M, N, K, geom, has_bias, has_r, f32) in seen.items():
     cands = [(b, s + 512) for b in (64, 128, 192, 256) for s in (1, 2, 4, 8)] + [(160, 2 + 512), (160, 4 + 512)]
     cands += [(b, 1 + 256) for b in (128, 192, 256)]
     for bn, sp in [(0, 0)] + cands:
+        if os.environ.get("VN_TUNE_VERBOSE"):
+            print(f"  {key} bn{bn} sp{sp}", flush=True)
         try:
             call(bn, sp)
             torch.cuda.synchronize()
@@ -99,4 +103,6 @@ path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
 os.makedirs(os.path.dirname(path), exist_ok=True)
 with open(path, "w") as f:
     json.dump(out, f, indent=0, sort_keys=True)
+with open(path.replace(".json", "_seen.json"), "w") as f:      # every key timed in this run (winner or not): lets a merge drop stale entries
+    json.dump(sorted(seen), f)
 print("wrote", path, len(out), "entries")

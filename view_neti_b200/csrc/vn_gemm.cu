@@ -1030,9 +1030,11 @@ extern "C" int vn_gemm(const vn_gemm_desc* d, vn_stream_t stream) {
   // schedule only (the staged epilogue needs 64-column blocks); every finishing thread owns a multiple of 8 columns
   if (bn == 160 && splits == 1) splits = 2;
   while (splits > 1 && (bn / splits) % 8 != 0) splits /= 2;
-  VN_CHECK(!(bn == 160 && splits == 1), "vn_gemm: BN 160 needs a split-K cluster of 2 or 4");
   while (splits > 1 && (vn_cdiv(p.kb_total, splits) < 1 || p.kb_total <= (splits - 1) * vn_cdiv(p.kb_total, splits)))
     splits /= 2;
+  // (checked AFTER the clamp to the number of k-blocks: a forced BN 160 on a one-k-block product used to reach the split
+  //  kernel with a cluster of 1 and hang on a barrier nobody arms)
+  VN_CHECK(!(bn == 160 && splits == 1), "vn_gemm: BN 160 needs a split-K cluster of 2 or 4 (and at least 2 k-blocks)");
   p.kb_per_split = vn_cdiv(p.kb_total, splits);
   p.splits = splits;
   p.n_tiles = vn_cdiv(d->N, bn);
