@@ -403,8 +403,11 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
   // predecessor kernel's tail, instead of at the head of every role's loop behind griddepcontrol.wait
   const int tile_first = VN_TILE_OF(tile_begin);
   const TileCoord c_first = tile_coord(p, tile_first, BN);
-  pdl_wait();          // everything above overlapped the previous kernel; activations are touched only from here on
-  if (threadIdx.x == 0) VN_STAMP(3);
+  // griddepcontrol.wait is executed PER ROLE, as late as each role allows (it is a per-thread instruction): the A producer
+  // right in front of its first activation load - its ~150 instructions of loop set-up used to sit behind the wait, 0.45 us
+  // of every launch (profiles/r1_kernel_timeline_v4.txt: "pdl_wait passed" -> "first A load issued") -, the epilogue /
+  // finishing warps before their first global access (residual, row-bias, D), the weight producer and the MMA warp never:
+  // frozen weights and shared / tensor memory do not depend on the previous kernel.
   const bool tma_epi = !SPLIT && p.use_tma_epilogue;
 
   if (warp == 0) {
@@ -432,6 +435,10 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
         for (int i = 0; i < nkb; ++i) {
           mbar_wait(&empty_bar[s], ph);
           uint8_t* sa = smem + s * STAGE_BYTES;
+          if (i == 0 && t == 0) {
+            pdl_wait();                            // activations (A, the residual tile) are read from here on
+            if (leader) VN_STAMP(3);
+          }
           if (leader) {
           if (CG == 1 || crank == 0) mbar_expect_tx(&full_bar[s], tx_bytes);
           if (CG == 2) {
@@ -565,6 +572,7 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     // Two warps per TMEM lane quarter: warps 2..5 finish the left half of the tile's columns, warps 6..9 the right half
     // (a lone warp per scheduler cannot hide its own instruction latency, and most launches of a batch-1 step are
     // single-tile, so the epilogue is on the critical path).  TMEM loads are software-pipelined one chunk ahead.
+    pdl_wait();                                  // row-bias / residual reads and the D stores depend on the previous kernel
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                 // tile row == TMEM lane
     const int half = (warp - 2) >> 2;            // column half of the tile (0 when kEpiHalves == 1)
@@ -726,6 +734,7 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     bool row_ok = false;
     uint4 rpre[PRE];
     if (warp >= 2 && warp < 6) {
+      pdl_wait();                                 // row-bias / residual reads and the D stores depend on the previous kernel
       for (int col = te; col < BN; col += 128) {
         float b = 0.f;
         if (c.n0 + col < p.N) {
