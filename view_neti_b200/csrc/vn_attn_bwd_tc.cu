@@ -206,18 +206,23 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(kv_full, 2 * TILE_BYTES);
-      tma_load_3d(sK, &tmK, kv_full, h * D, k0, b);
-      tma_load_3d(sV, &tmV, kv_full, h * D, k0, b);
+    {                                                  // warp-uniform control flow, one elected lane issues
+      const bool leader = elect_one();
+      if (leader) {
+        mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+        tma_load_3d(sK, &tmK, kv_full, h * D, k0, b);
+        tma_load_3d(sV, &tmV, kv_full, h * D, k0, b);
+      }
       for (int i = 0; i < nt; ++i) {
         const int s = i & 1;
         const int q0 = (qt_begin + i) * T;
         uint8_t* st = sStage + s * DKV_STAGE_BYTES;
         mbar_wait(&st_empty[s], ((i >> 1) & 1) ^ 1);
-        mbar_expect_tx(&st_full[s], 2 * TILE_BYTES);
-        tma_load_3d(st, &tmQ, &st_full[s], h * D, q0, b);
-        tma_load_3d(st + TILE_BYTES, &tmdO, &st_full[s], h * D, q0, b);
+        if (leader) {
+          mbar_expect_tx(&st_full[s], 2 * TILE_BYTES);
+          tma_load_3d(st, &tmQ, &st_full[s], h * D, q0, b);
+          tma_load_3d(st + TILE_BYTES, &tmdO, &st_full[s], h * D, q0, b);
+        }
       }
     }
     __syncwarp();
@@ -449,16 +454,21 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, 2 * TILE_BYTES);
-      tma_load_3d(sQ, &tmQ, q_full, h * D, q0, b);
-      tma_load_3d(sdO, &tmdO, q_full, h * D, q0, b);
+    {                                                  // warp-uniform control flow, one elected lane issues
+      const bool leader = elect_one();
+      if (leader) {
+        mbar_expect_tx(q_full, 2 * TILE_BYTES);
+        tma_load_3d(sQ, &tmQ, q_full, h * D, q0, b);
+        tma_load_3d(sdO, &tmdO, q_full, h * D, q0, b);
+      }
       for (int j = 0; j < nt; ++j) {
         const int s = j & 1;
         mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-        tma_load_3d(sKV + s * 2 * TILE_BYTES, &tmK, &kv_full[s], h * D, (kt0 + j) * T, b);
-        tma_load_3d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &tmV, &kv_full[s], h * D, (kt0 + j) * T, b);
+        if (leader) {
+          mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+          tma_load_3d(sKV + s * 2 * TILE_BYTES, &tmK, &kv_full[s], h * D, (kt0 + j) * T, b);
+          tma_load_3d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &tmV, &kv_full[s], h * D, (kt0 + j) * T, b);
+        }
       }
     }
     __syncwarp();

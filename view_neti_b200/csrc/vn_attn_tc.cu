@@ -28,6 +28,14 @@
 #include <stdlib.h>
 
 namespace {
+// P goes back into TENSOR memory (packed bf16 pairs over the first half of the S columns it was computed from) and feeds
+// P V as the A operand from there: no swizzled shared-memory stores / proxy fence in the softmax threads, and only the V tile
+// crosses the shared-memory port during the product.  VN_ATTN_FWD_TS=0 keeps the shared-memory operand (cross-check).
+#ifndef VN_ATTN_FWD_TS
+#define VN_ATTN_FWD_TS 1
+#endif
+constexpr bool kFwdTS = VN_ATTN_FWD_TS != 0;
+
 
 constexpr int D = 64;
 constexpr int BQ = 128;           // queries per CTA
@@ -137,19 +145,24 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
+    {                                              // warp-uniform control flow, one elected lane issues
+      const bool leader = elect_one();
       int it = 0;                                  // iterations issued so far, over all segments (barrier phases run on)
       for (int seg = 0; seg < nseg; ++seg) {
         const Segment g = segment(p, seg, nt);
         if (seg > 0) mbar_wait(q_empty, (seg - 1) & 1);      // the previous segment's S products are done with sQ
-        mbar_expect_tx(q_full, TILE_BYTES);
-        tma_load_3d(sQ, &tmQ, q_full, g.h * D, g.q0, g.b);
+        if (leader) {
+          mbar_expect_tx(q_full, TILE_BYTES);
+          tma_load_3d(sQ, &tmQ, q_full, g.h * D, g.q0, g.b);
+        }
         for (int kb = g.kb0; kb < g.kb1; ++kb, ++it) {
           const int s = it % KV_STAGES;
           mbar_wait(&kv_empty[s], ((it / KV_STAGES) & 1) ^ 1);
-          mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-          tma_load_3d(sKV + s * 2 * TILE_BYTES, &tmK, &kv_full[s], g.h * D, kb * BKV, g.b);
-          tma_load_3d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &tmV, &kv_full[s], g.h * D, kb * BKV, g.b);
+          if (leader) {
+            mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+            tma_load_3d(sKV + s * 2 * TILE_BYTES, &tmK, &kv_full[s], g.h * D, kb * BKV, g.b);
+            tma_load_3d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &tmV, &kv_full[s], g.h * D, kb * BKV, g.b);
+          }
         }
       }
     }
@@ -196,9 +209,15 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k) {
             // keys [0,64) accumulate into PV[j&1][0], keys [64,128) into PV[j&1][1]
-            const uint64_t adesc = umma_desc_k_sw128(aP + (k >> 2) * TILE_BYTES) + (uint64_t)((k & 3) * 2);
             const uint64_t bdesc = umma_desc_mn_sw128(aV + k * 2048);
-            umma_bf16(tPV + (uint32_t)((k >> 2) * D), adesc, bdesc, idesc_pv, (k & 3) ? 1u : 0u);
+            if (kFwdTS) {
+              // P of key block (k >> 2): 32 packed columns at the start of that block's 64 S columns, 8 columns per k-step
+              const uint32_t tP = tmem_base + (uint32_t)((j & 1) * BKV + (k >> 2) * 64 + (k & 3) * 8);
+              umma_bf16_ts(tPV + (uint32_t)((k >> 2) * D), tP, bdesc, idesc_pv, (k & 3) ? 1u : 0u);
+            } else {
+              const uint64_t adesc = umma_desc_k_sw128(aP + (k >> 2) * TILE_BYTES) + (uint64_t)((k & 3) * 2);
+              umma_bf16(tPV + (uint32_t)((k >> 2) * D), adesc, bdesc, idesc_pv, (k & 3) ? 1u : 0u);
+            }
           }
           umma_commit(&kv_empty[s]);         // K(j) (read by S(j), issued earlier) and V(j) are no longer needed
           umma_commit(&pv_full[j & 1]);
@@ -276,6 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
       float2 rsa = make_float2(0.f, 0.f), rsb = make_float2(0.f, 0.f);
       const float2 sl2v = make_float2(sl2, sl2), nm = make_float2(-mref, -mref);
       uint8_t* prow = sP + ((j & 1) * 2 + hf) * TILE_BYTES + r * 128;
+      uint32_t pw[32];                   // packed bf16 pairs of my 64 probabilities (tensor-memory operand)
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         float e[8];
@@ -286,14 +306,25 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
         }
         rsa = __fadd2_rn(rsa, __fadd2_rn(make_float2(e[0], e[1]), make_float2(e[2], e[3])));
         rsb = __fadd2_rn(rsb, __fadd2_rn(make_float2(e[4], e[5]), make_float2(e[6], e[7])));
-        uint4 w;
-        w.x = pack_bf162(e[0], e[1]); w.y = pack_bf162(e[2], e[3]);
-        w.z = pack_bf162(e[4], e[5]); w.w = pack_bf162(e[6], e[7]);
-        *reinterpret_cast<uint4*>(prow + ((g ^ (r & 7)) << 4)) = w;
+        if (kFwdTS) {
+          pw[g * 4 + 0] = pack_bf162(e[0], e[1]); pw[g * 4 + 1] = pack_bf162(e[2], e[3]);
+          pw[g * 4 + 2] = pack_bf162(e[4], e[5]); pw[g * 4 + 3] = pack_bf162(e[6], e[7]);
+        } else {
+          uint4 w;
+          w.x = pack_bf162(e[0], e[1]); w.y = pack_bf162(e[2], e[3]);
+          w.z = pack_bf162(e[4], e[5]); w.w = pack_bf162(e[6], e[7]);
+          *reinterpret_cast<uint4*>(prow + ((g ^ (r & 7)) << 4)) = w;
+        }
       }
       l_run = l_run * alpha + ((rsa.x + rsa.y) + (rsb.x + rsb.y));
-      tc_fence_before();                 // my TMEM reads of S(j) are done
-      fence_async_smem();                // my P writes are visible to the tensor core (async proxy)
+      if (kFwdTS) {
+        tmem_st32(tS, pw);               // over the first 32 of my own 64 S columns (all of them are in registers by now)
+        tmem_st_wait();
+        tc_fence_before();
+      } else {
+        tc_fence_before();               // my TMEM reads of S(j) are done
+        fence_async_smem();              // my P writes are visible to the tensor core (async proxy)
+      }
       mbar_arrive(&p_full[j & 1]);
       if (jj > 0) accumulate_pv(j - 1, alpha_prev);    // overlaps PV(j) / S(j+1) on the tensor pipe
       alpha_prev = alpha;
