@@ -32,6 +32,8 @@
 // scripts/kernel_timeline.py (-DVN_TIMELINE build) shows where the microseconds of one launch go.
 #include "vn_tma.cuh"
 
+#include <type_traits>
+
 #include <stdlib.h>
 #include <string.h>
 
@@ -248,6 +250,12 @@ __device__ __forceinline__ void store8_rest(const GemmParams& p, float (&o)[8], 
     w.z = pack_bf162(o[4], o[5]); w.w = pack_bf162(o[6], o[7]);
     *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.D) + gm * p.ldd + n) = w;
   }
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
 }
 
 struct TileCoord {
@@ -782,39 +790,68 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     if (threadIdx.x == 64) VN_STAMP(13);
     if (warp >= 2 && warp < 6) {
       if (row_ok) {
-        for (int g0 = 0; g0 < ngrp; g0 += PRE) {
-          if (g0 > 0) {                           // later chunks (wide tiles split 2 ways): their residuals together
+        // Finishing pass with the split count as a COMPILE-TIME constant (2, 4 or 8): the partials of up to four 8-column
+        // groups (<= 16 LDS.128, explicit shared-space loads) are all requested before the first add.  The generic-pointer
+        // version issued one dependent load -> add -> store chain per group, and the compiler could not move a group's
+        // loads above the previous group's global store: 600 cycles per group, 3.4 us for the ten groups of a BN-160 tile
+        // split two ways (in-kernel timeline, "cluster sync 2" -> "epilogue done").
+        const uint32_t ex_s = smem_u32(exch), sb_s = smem_u32(sbias);
+        auto finish = [&](auto sc) {
+          constexpr int SS = decltype(sc)::value;
+          constexpr int NG = BN / (8 * SS);        // 8-column groups per finishing thread
+          constexpr int RPO = BM / SS;
+          constexpr int G = (8 / SS) < 1 ? 1 : ((8 / SS) < NG ? (8 / SS) : NG);     // groups per chunk
 #pragma unroll
-            for (int g = 0; g < PRE; ++g) {
-              const int n = c.n0 + cg * cpt + (g0 + g) * 8;
-              if (r16 && g0 + g < ngrp && n < p.N) rpre[g] = *reinterpret_cast<const uint4*>(p.R + gm * p.ldr + n);
+          for (int g0 = 0; g0 < NG; g0 += G) {
+            float4 v[G][SS][2], bb[G][2];
+            uint4 rr[G];
+#pragma unroll
+            for (int gi = 0; gi < G; ++gi) {
+              const int g = g0 + gi;
+              if (g < NG) {
+                const int col = cg * (BN / SS) + g * 8;
+                bb[gi][0] = lds128(sb_s + (uint32_t)(col * 4));
+                bb[gi][1] = lds128(sb_s + (uint32_t)(col * 4 + 16));
+#pragma unroll
+                for (int src = 0; src < SS; ++src) {
+                  const uint32_t a = ex_s + (uint32_t)(((src * (BN / 4) + (col >> 2)) * RPO + rl) * 16);
+                  v[gi][src][0] = lds128(a);
+                  v[gi][src][1] = lds128(a + RPO * 16);
+                }
+                rr[gi] = make_uint4(0u, 0u, 0u, 0u);
+                if (g < PRE) rr[gi] = rpre[g];
+                else if (r16 && c.n0 + col < p.N) rr[gi] = *reinterpret_cast<const uint4*>(p.R + gm * p.ldr + c.n0 + col);
+              }
+            }
+#pragma unroll
+            for (int gi = 0; gi < G; ++gi) {
+              const int g = g0 + gi;
+              if (g < NG) {
+                const int col = cg * (BN / SS) + g * 8;
+                const int n = c.n0 + col;
+                if (n < p.N) {
+                  float o[8] = {bb[gi][0].x, bb[gi][0].y, bb[gi][0].z, bb[gi][0].w, bb[gi][1].x, bb[gi][1].y, bb[gi][1].z, bb[gi][1].w};
+#pragma unroll
+                  for (int src = 0; src < SS; ++src) {        // fixed order: deterministic
+                    o[0] += v[gi][src][0].x; o[1] += v[gi][src][0].y; o[2] += v[gi][src][0].z; o[3] += v[gi][src][0].w;
+                    o[4] += v[gi][src][1].x; o[5] += v[gi][src][1].y; o[6] += v[gi][src][1].z; o[7] += v[gi][src][1].w;
+                  }
+                  if (r16) {
+                    float2 f;
+                    f = unpack_bf162(rr[gi].x); o[0] += f.x; o[1] += f.y;
+                    f = unpack_bf162(rr[gi].y); o[2] += f.x; o[3] += f.y;
+                    f = unpack_bf162(rr[gi].z); o[4] += f.x; o[5] += f.y;
+                    f = unpack_bf162(rr[gi].w); o[6] += f.x; o[7] += f.y;
+                  }
+                  store8_rest(p, o, gm, bidx, n, smem_rowbias, r16);
+                }
+              }
             }
           }
-#pragma unroll
-          for (int g = 0; g < PRE; ++g) {
-            const int col = cg * cpt + (g0 + g) * 8;
-            const int n = c.n0 + col;
-            if (g0 + g < ngrp && n < p.N) {
-              const float4 b0 = *reinterpret_cast<const float4*>(sbias + col);
-              const float4 b1 = *reinterpret_cast<const float4*>(sbias + col + 4);
-              float o[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-              for (int src = 0; src < S; ++src) {
-                const float4* e = reinterpret_cast<const float4*>(exch) + ((long long)src * (BN / 4) + (col >> 2)) * rpo + rl;
-                const float4 v0 = e[0], v1 = e[rpo];
-                o[0] += v0.x; o[1] += v0.y; o[2] += v0.z; o[3] += v0.w;
-                o[4] += v1.x; o[5] += v1.y; o[6] += v1.z; o[7] += v1.w;
-              }
-              if (r16) {
-                float2 f;
-                f = unpack_bf162(rpre[g].x); o[0] += f.x; o[1] += f.y;
-                f = unpack_bf162(rpre[g].y); o[2] += f.x; o[3] += f.y;
-                f = unpack_bf162(rpre[g].z); o[4] += f.x; o[5] += f.y;
-                f = unpack_bf162(rpre[g].w); o[6] += f.x; o[7] += f.y;
-              }
-              store8_rest(p, o, gm, bidx, n, smem_rowbias, r16);
-            }
-          }
-        }
+        };
+        if (S == 2) finish(std::integral_constant<int, 2>{});
+        else if (S == 4) finish(std::integral_constant<int, 4>{});
+        else finish(std::integral_constant<int, 8>{});
       }
       if (threadIdx.x == 64) VN_STAMP(9);
     }
