@@ -771,18 +771,30 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
       const uint32_t owner = (uint32_t)(r / rpo);
       const uint32_t remote = mapa_shared(smem_u32(exch), owner) + (uint32_t)((((int)crank * (BN / 4)) * rpo + (r % rpo)) * 16);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        if (c.n0 + cc * 32 >= p.N) break;
-        uint32_t raw[32];
-        tmem_ld32(taddr + cc * 32, raw);
-        tmem_ld_wait();
+      // tensor-memory loads run one 32-column chunk ahead of the remote stores.  Rows of the tile that do not exist (M = 64
+      // launches fill half a tile) are not sent: the SM-to-SM network moves ~20 B/clk per SM, the exchange is bound by it,
+      // and their owners never read them.
+      constexpr int NCC = BN / 32;
+      long long gm_x;
+      int b_x;
+      const bool send = tile_row(p, c, r, &gm_x, &b_x);
+      const bool wsend = __any_sync(0xffffffffu, send);        // tcgen05.ld is warp-collective: loads stay warp-uniform
+      uint32_t raw[2][32];
+      if (wsend) tmem_ld32(taddr, raw[0]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(remote + (uint32_t)((cc * 8 + j) * rpo * 16)),
-                       "r"(raw[4 * j]), "r"(raw[4 * j + 1]), "r"(raw[4 * j + 2]), "r"(raw[4 * j + 3])
-                       : "memory");
+      for (int cc = 0; cc < NCC; ++cc) {
+        if (wsend && c.n0 + cc * 32 < p.N) {
+          tmem_ld_wait();
+          if (cc + 1 < NCC && c.n0 + (cc + 1) * 32 < p.N) tmem_ld32(taddr + (cc + 1) * 32, raw[(cc + 1) & 1]);
+          if (send)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(remote + (uint32_t)((cc * 8 + j) * rpo * 16)),
+                         "r"(raw[cc & 1][4 * j]), "r"(raw[cc & 1][4 * j + 1]), "r"(raw[cc & 1][4 * j + 2]), "r"(raw[cc & 1][4 * j + 3])
+                         : "memory");
+        }
       }
+      tmem_ld_wait();
     }
     tc_fence_before();
     __syncwarp();
