@@ -15,6 +15,7 @@ shapes = [(1, 5, 4096, 4096), (1, 10, 1024, 1024), (1, 20, 256, 256), (1, 20, 64
           (2, 5, 4096, 4096)]
 only = os.environ.get("ONLY_IDX")
 acc = torch.zeros(2 * 2 * 80 * 1280, dtype=torch.float64, device=dev)
+ws = torch.empty(64 << 20, dtype=torch.uint8, device=dev)      # scratch for the split leftover items (persistent schedule)
 for idx, (nb, h, nq, nk) in enumerate(shapes):
     if only is not None and idx != int(only):
         continue
@@ -28,9 +29,9 @@ for idx, (nb, h, nq, nk) in enumerate(shapes):
     delta = torch.empty(nb, h, nq, device=dev)
     dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
     fl = 4.0 * nb * h * nq * nk * 64
-    for name, f, mult in (("fwd", lambda: ops.attention_fwd(q, k, v, o, lse, h), 1.0),
+    for name, f, mult in (("fwd", lambda: ops.attention_fwd(q, k, v, o, lse, h, ws=ws), 1.0),
                           ("bwd", lambda: ops.attention_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, h,
-                                                            dkv_acc=acc if nk < 256 else None), 2.5)):
+                                                            dkv_acc=acc if nk < 256 else None, ws=ws), 2.5)):
         if name not in which:
             continue
         for _ in range(3):

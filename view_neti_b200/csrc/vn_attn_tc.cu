@@ -249,9 +249,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
       tc_fence_after();
       const uint32_t tPV = tmem_base + 2 * BKV + (uint32_t)(((jj & 1) * 2 + hf) * D) + lane_addr;
       uint32_t r0[32], r1[32];
+#ifdef VN_ABL_NOPV
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { r0[i] = 0u; r1[i] = 0u; }                  // timing ablation: no PV read-back
+#else
       tmem_ld32(tPV, r0);
       tmem_ld32(tPV + 32, r1);
       tmem_ld_wait();
+#endif
       const float2 av = make_float2(alpha, alpha);
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {                  // packed f32x2 arithmetic (sm_100)
@@ -287,7 +292,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
         mx0 = fmaxf(mx0, __uint_as_float(s[i])); mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
         mx2 = fmaxf(mx2, __uint_as_float(s[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
       }
+#ifdef VN_ABL_NOMAX
+      float mx = fmaxf(m_run, __uint_as_float(s[0]) * sl2);                     // timing ablation: no row maximum
+#else
       float mx = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2);   // scale > 0
+#endif
       // a half that has not seen a valid key yet keeps m = -inf; use 0 as the reference so that ex2(-inf - 0) = 0
       const float mref = (mx == -INFINITY) ? 0.f : mx;
       const float alpha = ex2_approx(m_run - mref);    // first tile: ex2(-inf) = 0
@@ -302,7 +311,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
           const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[g * 8 + i]), __uint_as_float(s[g * 8 + i + 1])), sl2v, nm);
+#ifdef VN_ABL_NOEXP
+          e[i] = fmaf(x.x, 0.01f, 1.f); e[i + 1] = fmaf(x.y, 0.01f, 1.f);      // timing ablation: no MUFU
+#else
           e[i] = ex2_approx(x.x); e[i + 1] = ex2_approx(x.y);
+#endif
         }
         rsa = __fadd2_rn(rsa, __fadd2_rn(make_float2(e[0], e[1]), make_float2(e[2], e[3])));
         rsb = __fadd2_rn(rsb, __fadd2_rn(make_float2(e[4], e[5]), make_float2(e[6], e[7])));
