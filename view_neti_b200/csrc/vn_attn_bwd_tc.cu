@@ -193,7 +193,7 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kComputeThreads);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kComputeThreads / 32);     // one arrival per compute WARP
     }
     mbar_init(acc_full, 1);
     mbar_fence_init();
@@ -359,7 +359,9 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
           tc_fence_before();
           fence_async_smem();
         }
-        mbar_arrive(&p_full[hh]);
+        __syncwarp();                              // every lane's stores are complete and fenced
+        if (lane == 0) mbar_arrive(&p_full[hh]);   // one arrival per warp (512 arrivals on one shared-memory word serialise)
+        __syncwarp();                              // reconverge: the next tcgen05.ld is .sync.aligned
       }
       if (te < 256) reinterpret_cast<float*>(sStage + ((i + 1) & 1) * DKV_STAGE_BYTES + 2 * TILE_BYTES)[te] = next_val;
       bar_compute();
@@ -442,7 +444,7 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kComputeThreads);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kComputeThreads / 32);     // one arrival per compute WARP
     }
     mbar_init(acc_full, 1);
     mbar_fence_init();
@@ -575,7 +577,9 @@ __device__ __forceinline__ void dq_body(const CUtensorMap& tmQ, const CUtensorMa
           tc_fence_before();
           fence_async_smem();
         }
-        mbar_arrive(&p_full[hh]);
+        __syncwarp();                              // every lane's stores are complete and fenced
+        if (lane == 0) mbar_arrive(&p_full[hh]);   // one arrival per warp (512 arrivals on one shared-memory word serialise)
+        __syncwarp();                              // reconverge: the next tcgen05.ld is .sync.aligned
       }
     }
     mbar_wait(acc_full, 0);

@@ -35,12 +35,26 @@ namespace {
 #define VN_ATTN_FWD_TS 1
 #endif
 constexpr bool kFwdTS = VN_ATTN_FWD_TS != 0;
+// OPTIONAL schedule (VN_ATTN_FWD_HALVES=1, off by default): the two 64-key halves of a tile as independent chains
+// (S_h -> softmax_h -> P_h V) with their own S / P / PV barriers and S issued as two N = 64 products, so that the softmax warps of
+// the two halves may drift apart.  Built to test the hypothesis that the two warps of a scheduler lose time by running the same
+// phase at the same time; measured NEUTRAL on B200 (64x64: 70.8 vs 70.2 us eager), as were 4 K/V stages and one barrier arrival
+// per warp instead of per thread.  Timing ablations (profiles/r2_ncu_attn_summary.txt): with the softmax threads doing nothing
+// but passing the barriers on, the kernel still takes 31 of its 49 us - the barrier round trips between the roles, not the
+// arithmetic, bound it.
+#ifndef VN_ATTN_FWD_HALVES
+#define VN_ATTN_FWD_HALVES 0
+#endif
+constexpr bool kHalves = (VN_ATTN_FWD_HALVES != 0) && kFwdTS;
 
 
 constexpr int D = 64;
 constexpr int BQ = 128;           // queries per CTA
 constexpr int BKV = 128;          // keys per iteration
-constexpr int KV_STAGES = 3;
+#ifndef VN_ATTN_KV_STAGES
+#define VN_ATTN_KV_STAGES 3
+#endif
+constexpr int KV_STAGES = VN_ATTN_KV_STAGES;
 constexpr int TILE_BYTES = 128 * 128;             // [128 rows x 64 bf16]
 constexpr int kThreads = 320;             // producer warp, MMA warp, 8 softmax warps
 constexpr int TMEM_COLS = 512;                    // S[2]: 2 x 128 fp32 columns, PV[2][half]: 4 x 64
@@ -119,10 +133,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;                            // [KV_STAGES]
   uint64_t* kv_empty = kv_full + KV_STAGES;                // [KV_STAGES]
-  uint64_t* s_full = kv_empty + KV_STAGES;                 // [2]
-  uint64_t* p_full = s_full + 2;                           // [2]
-  uint64_t* pv_full = p_full + 2;                          // [2]
-  uint64_t* q_empty = pv_full + 2;                         // every S product of a segment has read the Q tile
+  uint64_t* s_full = kv_empty + KV_STAGES;                 // [2] (kHalves: [half][2], index h * 2 + buffer)
+  uint64_t* p_full = s_full + 4;                           // [2] / [half][2]
+  uint64_t* pv_full = p_full + 4;                          // [2] / [half][2]
+  uint64_t* q_empty = pv_full + 4;                         // every S product of a segment has read the Q tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -134,7 +148,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 256); mbar_init(&pv_full[s], 1); }
+    for (int s = 0; s < (kHalves ? 4 : 2); ++s) {
+      mbar_init(&s_full[s], 1); mbar_init(&pv_full[s], 1);
+      mbar_init(&p_full[s], kHalves ? 4 : 8);      // one arrival per softmax WARP
+    }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -189,6 +206,68 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
           if (last_of_segment) umma_commit(q_empty);
         }
       };
+      if constexpr (kHalves) {
+        // two independent chains per tile (key halves h = 0 / 1), served in the fixed order h0(j), h1(j), h0(j+1), ...
+        constexpr uint32_t idesc_s64 = idesc_bf16(BQ, 64, 0);
+        auto wait_kv = [&](int j) {
+          mbar_wait(&kv_full[j % KV_STAGES], (j / KV_STAGES) & 1);
+          tc_fence_after();
+        };
+        auto issue_s_half = [&](int j, int h) {      // S_h(j) = Q K_h(j)^T -> S[j & 1] columns [64 h, 64 h + 64)
+          const uint32_t aK = smem_u32(sKV + (j % KV_STAGES) * 2 * TILE_BYTES) + (uint32_t)(h * 64 * 128);
+          const uint32_t tS = tmem_base + (uint32_t)((j & 1) * BKV + h * 64);
+          if (leader) {
+#ifndef VN_ABL_NOSMMA
+#pragma unroll
+            for (int k = 0; k < D / 16; ++k)
+              umma_bf16(tS, umma_desc_k_sw128(aQ) + (uint64_t)(k * 2), umma_desc_k_sw128(aK) + (uint64_t)(k * 2), idesc_s64,
+                        k ? 1u : 0u);
+#endif
+            umma_commit(&s_full[h * 2 + (j & 1)]);
+          }
+        };
+        int it0 = 0;
+        for (int seg = 0; seg < nseg; ++seg) {
+          const Segment g = segment(p, seg, nt);
+          const int n = g.kb1 - g.kb0;
+          mbar_wait(q_full, seg & 1);
+          wait_kv(it0);
+          issue_s_half(it0, 0); issue_s_half(it0, 1);
+          if (n > 1) {
+            wait_kv(it0 + 1);
+            issue_s_half(it0 + 1, 0); issue_s_half(it0 + 1, 1);
+          }
+          if (n <= 2 && leader) umma_commit(q_empty);          // every S product of the segment has been issued
+          for (int jj = 0; jj < n; ++jj) {
+            const int j = it0 + jj;
+            const int s = j % KV_STAGES;
+            const uint32_t aV = smem_u32(sKV + s * 2 * TILE_BYTES + TILE_BYTES);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              mbar_wait(&p_full[h * 2 + (j & 1)], (j >> 1) & 1);
+              tc_fence_after();
+              if (leader) {
+#ifndef VN_ABL_NOPVMMA
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  const uint64_t bdesc = umma_desc_mn_sw128(aV + (h * 4 + kk) * 2048);
+                  const uint32_t tP = tmem_base + (uint32_t)((j & 1) * BKV + h * 64 + kk * 8);
+                  umma_bf16_ts(tmem_base + 2 * BKV + (uint32_t)(((j & 1) * 2 + h) * D), tP, bdesc, idesc_pv, kk ? 1u : 0u);
+                }
+#endif
+                umma_commit(&pv_full[h * 2 + (j & 1)]);
+                if (h == 1) umma_commit(&kv_empty[s]);         // K(j) and V(j) are no longer needed
+              }
+              if (jj + 2 < n) {                                // S_h(j+2) takes over the columns P_h(j) has just been read from
+                if (h == 0) wait_kv(j + 2);
+                issue_s_half(j + 2, h);
+                if (h == 1 && jj + 3 == n && leader) umma_commit(q_empty);
+              }
+            }
+          }
+          it0 += n;
+        }
+      } else {
       int it0 = 0;
       for (int seg = 0; seg < nseg; ++seg) {
       const Segment g = segment(p, seg, nt);
@@ -225,6 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
       }
       it0 += n;
       }
+      }
     }
     __syncwarp();
   } else {
@@ -245,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
     for (int i = 0; i < D; ++i) o[i] = 0.f;
 
     auto accumulate_pv = [&](int jj, float alpha) {   // O = alpha * O + PV(jj)[hf]
-      mbar_wait(&pv_full[jj & 1], (jj >> 1) & 1);
+      mbar_wait(&pv_full[(kHalves ? hf * 2 : 0) + (jj & 1)], (jj >> 1) & 1);
       tc_fence_after();
       const uint32_t tPV = tmem_base + 2 * BKV + (uint32_t)(((jj & 1) * 2 + hf) * D) + lane_addr;
       uint32_t r0[32], r1[32];
@@ -269,9 +349,19 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
     for (int jj = 0; jj < nloc; ++jj) {
       const int j = it0 + jj;                      // iteration index over all segments (buffer parities, phases)
       const int kb = g.kb0 + jj;                   // key block
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&s_full[(kHalves ? hf * 2 : 0) + (j & 1)], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t tS = tmem_base + (uint32_t)((j & 1) * BKV + hf * 64) + lane_addr;
+#ifdef VN_ABL_NOSOFTMAX
+      tc_fence_before();                           // timing ablation: the softmax threads only pass the barriers on
+      __syncwarp();                      // every lane's tensor-memory stores are complete and fenced
+      if (lane == 0) mbar_arrive(&p_full[(kHalves ? hf * 2 : 0) + (j & 1)]);      // one arrival per warp: 256 arrivals on one
+                                                                                  // shared-memory word serialise
+      __syncwarp();                      // reconverge: the next tcgen05.ld is .sync.aligned
+      if (jj > 0) { mbar_wait(&pv_full[(kHalves ? hf * 2 : 0) + ((j - 1) & 1)], ((j - 1) >> 1) & 1); tc_fence_after(); }
+      alpha_prev = 1.f;
+      continue;
+#endif
       uint32_t s[64];
       {
         uint32_t(&c0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
@@ -338,7 +428,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
         tc_fence_before();               // my TMEM reads of S(j) are done
         fence_async_smem();              // my P writes are visible to the tensor core (async proxy)
       }
-      mbar_arrive(&p_full[j & 1]);
+      __syncwarp();                      // every lane's tensor-memory stores are complete and fenced
+      if (lane == 0) mbar_arrive(&p_full[(kHalves ? hf * 2 : 0) + (j & 1)]);      // one arrival per warp: 256 arrivals on one
+                                                                                  // shared-memory word serialise
+      __syncwarp();                      // reconverge: the next tcgen05.ld is .sync.aligned
       if (jj > 0) accumulate_pv(j - 1, alpha_prev);    // overlaps PV(j) / S(j+1) on the tensor pipe
       alpha_prev = alpha;
     }
