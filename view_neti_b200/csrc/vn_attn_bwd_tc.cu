@@ -58,13 +58,6 @@ __device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&v)
   if constexpr (N == 16) tmem_st16(taddr, v);
   else tmem_st8(taddr, v);
 }
-__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr);
-// D[128 x 64] (+)= A[tensor memory: 128 lanes x 64 k as 32 packed columns] * B[k-rows h*64.. of the MN-major tile]
-__device__ __forceinline__ void mma_tmn_half(uint32_t tacc, uint32_t ta, uint32_t b, int h, uint32_t id, bool accumulate) {
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    umma_bf16_ts(tacc, ta + (uint32_t)(k * 8), desc_mn_sw128(b + (h * 4 + k) * 2048), id, (accumulate || k) ? 1u : 0u);
-}
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory"); }
 constexpr int TMEM_COLS = 512;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -109,14 +102,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// half-tile variants (64 of the 128 columns / k-rows), used to pipeline the tensor pipe against the compute warps:
-// D[128 x 64] = A[128 x 64 k] * B[rows h*64.. of a 128-row K-major tile]^T
-__device__ __forceinline__ void mma_kk_half(uint32_t tacc, uint32_t a, uint32_t b, int h, uint32_t id64) {
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    umma_bf16(tacc + (uint32_t)(h * 64), umma_desc_k_sw128(a) + (uint64_t)(k * 2),
-              umma_desc_k_sw128(b + h * 64 * 128) + (uint64_t)(k * 2), id64, k ? 1u : 0u);
-}
+// half-tile variants (64 of the 128 columns / k-rows), used to pipeline the tensor pipe against the compute warps
 // D[128 x 64] (+)= A[block h: 128 x 64 k, K-major] * B[k-rows h*64.. of the MN-major tile]
 __device__ __forceinline__ void mma_kmn_half(uint32_t tacc, uint32_t a, uint32_t b, int h, uint32_t id, bool accumulate) {
 #pragma unroll
@@ -144,7 +130,7 @@ __device__ __forceinline__ void ld64(uint32_t taddr, uint32_t (&v)[64]) {
   tmem_ld32(taddr, c0);
   tmem_ld32(taddr + 32, c1);
 }
-__device__ __forceinline__ void ld_acc(uint32_t taddr, uint32_t (&v)[64]) { ld64(taddr, v); }
+[[maybe_unused]] __device__ __forceinline__ void ld_acc(uint32_t taddr, uint32_t (&v)[64]) { ld64(taddr, v); }   // kCW == 2
 __device__ __forceinline__ void ld_acc(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
 __device__ __forceinline__ void store_row8(uint8_t* row, int chunk, int r, const float (&e)[8]) {
   uint4 w;
