@@ -71,7 +71,8 @@ for key, (kind, M, N, K, geom, has_bias, has_r, f32) in seen.items():
     res = {}
     # force_split code: low 4 bits split-K cluster size, +256 = CTA pairs (cta_group::2) on, +512 = pairs off
     cands = [(b, s + 512) for b in (64, 128, 192, 256) for s in (1, 2, 4, 8)] + [(160, 2 + 512), (160, 4 + 512)]
-    cands += [(b, 1 + 256) for b in (128, 192, 256)]
+    if ((M + 127) // 128) % 2 == 0:              # CTA pairs need an even number of m-tiles (vn_gemm ignores the request otherwise)
+        cands += [(b, 1 + 256) for b in (128, 192, 256)]
     for bn, sp in [(0, 0)] + cands:
         if os.environ.get("VN_TUNE_VERBOSE"):
             print(f"  {key} bn{bn} sp{sp}", flush=True)

@@ -25,7 +25,8 @@ for spec in sys.argv[1:]:
     R = torch.randn(M, N, device="cuda").to(BF) if has_r else None
     bias = torch.randn(N, device="cuda") if has_bias else None
     cands = [(b, s + 512) for b in (64, 128, 192, 256) for s in (1, 2, 4, 8)] + [(160, 2 + 512), (160, 4 + 512)]
-    cands += [(b, 1 + 256) for b in (128, 192, 256)]
+    if ((M + 127) // 128) % 2 == 0:              # CTA pairs need an even number of m-tiles (vn_gemm ignores the request otherwise)
+        cands += [(b, 1 + 256) for b in (128, 192, 256)]
     res = {}
     for bn, sp in [(0, 0)] + cands:
         try:
