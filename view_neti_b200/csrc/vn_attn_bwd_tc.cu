@@ -77,8 +77,20 @@ struct BwdParams {
   int persistent, items, rounds, n_left, parts;
   int left_dkv;                     // how many of the n_left split items are dK/dV items (the rest are dQ items)
   float* part;                      // [n_left * parts][2][128][64] fp32 partial tiles (dQ: [0]; dK/dV: [0] = dV, [1] = dK)
+  long long* dbg;                   // -DVN_TIMELINE builds: clock stamps of CTA 0 (scripts/attn_timeline.py), else unused
 };
 
+// In-kernel timeline (instrumented builds): CTA 0, first body (a dK/dV item), query tiles [8, 16): dbg[1024 + (i - 8) * 16 + e];
+//   e = 0/1 S^T,dP^T(i, half 0/1) issued, 2/3 dV,dK(i, half 0/1) issued (p_full seen), 4/5 s_full(half 0/1) seen by compute
+//   thread 64, 6/7 its arrive on p_full(half 0/1)
+#ifdef VN_TIMELINE
+#define VN_BSTAMP(i, e)                                                                                              \
+  do {                                                                                                               \
+    if (p.dbg && blockIdx.x == 0 && seg == 0 && (i) >= 8 && (i) < 16) p.dbg[1024 + ((i) - 8) * 16 + (e)] = clock64(); \
+  } while (0)
+#else
+#define VN_BSTAMP(i, e) do { } while (0)
+#endif
 __device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fffu);
@@ -231,6 +243,7 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
           mma_kk_half_d(tST, dKk, dQk[i & 1], hh, id_s);
           mma_kk_half_d(tdPT, dVk, ddOk[i & 1], hh, id_s);
           umma_commit(&s_full[hh]);                    // in-order retirement: also covers dV/dK(i-1, h) -> operand block h free
+          VN_BSTAMP(i, hh);
         }
       };
       mbar_wait(kv_full, 0);
@@ -252,6 +265,7 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
               mma_kmn_half(tdK, adS, aQ, hh, id_acc, i > 0 || hh > 0);
             }
             if (hh == 1) umma_commit(&st_empty[i & 1]);
+            VN_BSTAMP(i, 2 + hh);
           }
           if (i + 1 < nt) {
             if (hh == 0) { mbar_wait(&st_full[(i + 1) & 1], ((i + 1) >> 1) & 1); tc_fence_after(); }
@@ -288,6 +302,7 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
         const float* dl = lse + T;
         mbar_wait(&s_full[hh], i & 1);
         tc_fence_after();
+        if (threadIdx.x == 64) VN_BSTAMP(i, 4 + hh);
         uint32_t sv[CWCOLS], dp[CWCOLS];
         tmem_ld_cols(tST + lane_addr + cbase, sv);
         tmem_ld_cols(tdPT + lane_addr + cbase, dp);
@@ -348,6 +363,7 @@ __device__ __forceinline__ void dkv_body(const CUtensorMap& tmQ, const CUtensorM
         __syncwarp();                              // every lane's stores are complete and fenced
         if (lane == 0) mbar_arrive(&p_full[hh]);   // one arrival per warp (512 arrivals on one shared-memory word serialise)
         __syncwarp();                              // reconverge: the next tcgen05.ld is .sync.aligned
+        if (threadIdx.x == 64) VN_BSTAMP(i, 6 + hh);
       }
       if (te < 256) reinterpret_cast<float*>(sStage + ((i + 1) & 1) * DKV_STAGE_BYTES + 2 * TILE_BYTES)[te] = next_val;
       bar_compute();
@@ -830,6 +846,7 @@ extern "C" int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s) {
   if (qkv_map(&tv, d->v, width, d->nk, d->nb, d->ldv, d->bsv)) return -1;
   if (qkv_map(&tdo, d->d_o, width, d->nq, d->nb, d->lddo, d->bsdo)) return -1;
   BwdParams p{};
+  p.dbg = vn_debug_buffer();
   p.nb = d->nb; p.heads = d->heads; p.nq = d->nq; p.nk = d->nk; p.scale = d->scale;
   p.lse = d->lse; p.delta = d->delta;
   p.dq = (bf16*)d->dq; p.lddq = d->lddq; p.bsdq = d->bsdq;

@@ -72,7 +72,21 @@ struct FwdParams {
   int nqt, items, rounds, n_left, parts;
   float* part_o;        // [n_left * parts][128][64] unnormalised partial outputs
   float* part_ml;       // [n_left * parts][128][2]  (running max in the log2 domain, running sum)
+  long long* dbg;       // -DVN_TIMELINE builds: clock stamps of CTA 0 (scripts/attn_timeline.py), else unused
 };
+
+// In-kernel timeline (instrumented builds only): CTA 0 stamps clock64 for iterations [8, 16) of its first segment.
+//   slot layout: dbg[(j - 8) * 16 + e]; e = 0 S(j) issued, 1 P V(j) issued (p_full(j) seen), 2 s_full(j) seen by a softmax
+//   thread, 3 that thread's arrive on p_full(j), 4 pv_full(j-1) seen by it, 5 K/V stage of tile j free (producer), 6 its TMA issued,
+//   7 kv_full(j) seen by the MMA warp
+#ifdef VN_TIMELINE
+#define VN_ASTAMP(j, e)                                                                                  \
+  do {                                                                                                   \
+    if (p.dbg && blockIdx.x == 0 && (j) >= 8 && (j) < 16) p.dbg[((j) - 8) * 16 + (e)] = clock64();       \
+  } while (0)
+#else
+#define VN_ASTAMP(j, e) do { } while (0)
+#endif
 
 struct Segment {
   int q0, h, b;         // query-tile origin, head, image
@@ -176,9 +190,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
           const int s = it % KV_STAGES;
           mbar_wait(&kv_empty[s], ((it / KV_STAGES) & 1) ^ 1);
           if (leader) {
+            VN_ASTAMP(it, 5);
             mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
             tma_load_3d(sKV + s * 2 * TILE_BYTES, &tmK, &kv_full[s], g.h * D, kb * BKV, g.b);
             tma_load_3d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &tmV, &kv_full[s], g.h * D, kb * BKV, g.b);
+            VN_ASTAMP(it, 6);
           }
         }
       }
@@ -198,11 +214,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
         const uint32_t aK = smem_u32(sKV + s * 2 * TILE_BYTES);
         const uint32_t tS = tmem_base + (uint32_t)((j & 1) * BKV);
         if (leader) {
+          VN_ASTAMP(j, 7);
 #pragma unroll
           for (int k = 0; k < D / 16; ++k)
             umma_bf16(tS, umma_desc_k_sw128(aQ) + (uint64_t)(k * 2), umma_desc_k_sw128(aK) + (uint64_t)(k * 2), idesc_s,
                       k ? 1u : 0u);
           umma_commit(&s_full[j & 1]);
+          VN_ASTAMP(j, 0);
           if (last_of_segment) umma_commit(q_empty);
         }
       };
@@ -300,6 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
           }
           umma_commit(&kv_empty[s]);         // K(j) (read by S(j), issued earlier) and V(j) are no longer needed
           umma_commit(&pv_full[j & 1]);
+          VN_ASTAMP(j, 1);
         }
       }
       it0 += n;
@@ -351,6 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
       const int kb = g.kb0 + jj;                   // key block
       mbar_wait(&s_full[(kHalves ? hf * 2 : 0) + (j & 1)], (j >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 64) VN_ASTAMP(j, 2);
       const uint32_t tS = tmem_base + (uint32_t)((j & 1) * BKV + hf * 64) + lane_addr;
 #ifdef VN_ABL_NOSOFTMAX
       tc_fence_before();                           // timing ablation: the softmax threads only pass the barriers on
@@ -432,7 +452,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
       if (lane == 0) mbar_arrive(&p_full[(kHalves ? hf * 2 : 0) + (j & 1)]);      // one arrival per warp: 256 arrivals on one
                                                                                   // shared-memory word serialise
       __syncwarp();                      // reconverge: the next tcgen05.ld is .sync.aligned
+      if (threadIdx.x == 64) VN_ASTAMP(j, 3);
       if (jj > 0) accumulate_pv(j - 1, alpha_prev);    // overlaps PV(j) / S(j+1) on the tensor pipe
+      if (threadIdx.x == 64) VN_ASTAMP(j, 4);
       alpha_prev = alpha;
     }
     accumulate_pv(it0 + nloc - 1, alpha_prev);
@@ -611,6 +633,7 @@ extern "C" int vn_attention_fwd(const vn_attn_desc* d, vn_stream_t s) {
     p.part_o = reinterpret_cast<float*>(d->ws);
     p.part_ml = p.part_o + (size_t)n_left * parts * BQ * D;
   }
+  p.dbg = vn_debug_buffer();
   VN_LAUNCH(attn_fwd_tc_kernel, grid, kThreads, SMEM_BYTES, (cudaStream_t)s, tq, tk, tv, p);
   if (p.n_left > 0) VN_LAUNCH(attn_fwd_fixup_kernel, p.n_left * 8, 128, 0, (cudaStream_t)s, p);
   return 0;
