@@ -39,9 +39,9 @@ constexpr bool kFwdTS = VN_ATTN_FWD_TS != 0;
 // (S_h -> softmax_h -> P_h V) with their own S / P / PV barriers and S issued as two N = 64 products, so that the softmax warps of
 // the two halves may drift apart.  Built to test the hypothesis that the two warps of a scheduler lose time by running the same
 // phase at the same time; measured NEUTRAL on B200 (64x64: 70.8 vs 70.2 us eager), as were 4 K/V stages and one barrier arrival
-// per warp instead of per thread.  Timing ablations (profiles/r2_ncu_attn_summary.txt): with the softmax threads doing nothing
-// but passing the barriers on, the kernel still takes 31 of its 49 us - the barrier round trips between the roles, not the
-// arithmetic, bound it.
+// per warp instead of per thread.  Timing ablations (profiles/r2_ncu_attn_summary.txt) and the in-kernel timeline
+// (profiles/r2_attn_timeline.txt): the two softmax warps of a scheduler need ~2 080 cycles per tile (1 024 of them MUFU) and are
+// the bottleneck; with them idle the barrier round trips between the roles still take 31 of the 49 us.
 #ifndef VN_ATTN_FWD_HALVES
 #define VN_ATTN_FWD_HALVES 0
 #endif
