@@ -514,6 +514,300 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
   }
 }
 
+// =================================================================================================
+// Forward with SIXTEEN softmax warps (four per scheduler).  The in-kernel timeline of the kernel above shows its two softmax
+// warps per scheduler as the bottleneck (profiles/r2_attn_timeline.txt: 2 080 cycles per 128-key tile, 1 024 of them MUFU time,
+// the rest latencies two warps cannot overlap).  Here a thread owns (query row, 32-key QUARTER of every tile):
+//   * O is accumulated by the tensor core itself: four accumulators O_c [128 x 64] in tensor memory, one per key quarter
+//     (2 x 128 columns of S + 4 x 64 = all 512), P_c V_c issued with accumulate; no per-tile read-back, no 64 accumulator registers;
+//   * every quarter keeps its OWN running maximum, and only moves it when a row maximum grows by more than 2^8 (probabilities then
+//     stay below 256, exact in bf16's range; sums are fp32): the rescale of O_c - tcgen05.ld, multiply, tcgen05.st, warp-voted
+//     because the tensor-memory accesses are warp-collective - is rare after the first tiles;
+//   * the four quarters of a row are merged once at the end, like the two halves above.
+// Same work decomposition (persistent CTAs, key parts of leftover items, attn_fwd_fixup_kernel) and the same results up to the
+// rounding of P against a different reference maximum.
+// =================================================================================================
+constexpr int kThreads16 = 64 + 512;
+constexpr int XCH16_FLOATS = 3 * BQ * 67;                         // quarters 1..3 park (O, m, l) per row, odd stride
+constexpr int SMEM16_BYTES = TILE_BYTES + KV_STAGES * 2 * TILE_BYTES + XCH16_FLOATS * 4 + 256 + 1024;
+static_assert(SMEM16_BYTES <= 232448, "shared memory budget");
+constexpr float kRescaleThreshold = 8.f;                          // log2 domain
+
+__global__ void __launch_bounds__(kThreads16, 1) attn_fwd16_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                       const __grid_constant__ CUtensorMap tmK,
+                                                                       const __grid_constant__ CUtensorMap tmV,
+                                                                       const FwdParams p) {
+  pdl_trigger();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + TILE_BYTES;                          // stage s: K at s*2*TILE, V right after
+  float* xch = reinterpret_cast<float*>(sKV + KV_STAGES * 2 * TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + XCH16_FLOATS);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;                            // [KV_STAGES]
+  uint64_t* kv_empty = kv_full + KV_STAGES;                // [KV_STAGES]
+  uint64_t* s_full = kv_empty + KV_STAGES;                 // [2]
+  uint64_t* p_full = s_full + 2;                           // [2], one arrival per softmax warp
+  uint64_t* pv_full = p_full + 2;                          // [2], alternating per tile
+  uint64_t* q_empty = pv_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = (p.nk + BKV - 1) / BKV;
+  const int nseg = num_segments(p);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 16); mbar_init(&pv_full[s], 1); }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    const bool leader = elect_one();
+    int it = 0;
+    for (int seg = 0; seg < nseg; ++seg) {
+      const Segment g = segment(p, seg, nt);
+      if (seg > 0) mbar_wait(q_empty, (seg - 1) & 1);
+      if (leader) {
+        mbar_expect_tx(q_full, TILE_BYTES);
+        tma_load_3d(sQ, &tmQ, q_full, g.h * D, g.q0, g.b);
+      }
+      for (int kb = g.kb0; kb < g.kb1; ++kb, ++it) {
+        const int s = it % KV_STAGES;
+        mbar_wait(&kv_empty[s], ((it / KV_STAGES) & 1) ^ 1);
+        if (leader) {
+          mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+          tma_load_3d(sKV + s * 2 * TILE_BYTES, &tmK, &kv_full[s], g.h * D, kb * BKV, g.b);
+          tma_load_3d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &tmV, &kv_full[s], g.h * D, kb * BKV, g.b);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = idesc_bf16(BQ, BKV, 0);
+    constexpr uint32_t idesc_pv = idesc_bf16(BQ, D, 1);
+    const uint32_t aQ = smem_u32(sQ);
+    auto issue_s = [&](int j, bool last_of_segment) {
+      const int s = j % KV_STAGES;
+      mbar_wait(&kv_full[s], (j / KV_STAGES) & 1);
+      tc_fence_after();
+      const uint32_t aK = smem_u32(sKV + s * 2 * TILE_BYTES);
+      const uint32_t tS = tmem_base + (uint32_t)((j & 1) * BKV);
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          umma_bf16(tS, umma_desc_k_sw128(aQ) + (uint64_t)(k * 2), umma_desc_k_sw128(aK) + (uint64_t)(k * 2), idesc_s,
+                    k ? 1u : 0u);
+        umma_commit(&s_full[j & 1]);
+        if (last_of_segment) umma_commit(q_empty);
+      }
+    };
+    int it0 = 0;
+    for (int seg = 0; seg < nseg; ++seg) {
+      const Segment g = segment(p, seg, nt);
+      const int n = g.kb1 - g.kb0;
+      mbar_wait(q_full, seg & 1);
+      issue_s(it0, n == 1);
+      for (int jj = 0; jj < n; ++jj) {
+        const int j = it0 + jj;
+        if (jj + 1 < n) issue_s(j + 1, jj + 2 == n);
+        const int s = j % KV_STAGES;
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);       // P(j) in tensor memory, O rescaled where a maximum moved
+        tc_fence_after();
+        const uint32_t aV = smem_u32(sKV + s * 2 * TILE_BYTES + TILE_BYTES);
+        if (leader) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              // O_c (+)= P_c[128 x 16 keys] V[16 keys x 64]: P_c = 16 packed columns at the start of quarter c's 32 S columns
+              const uint64_t bdesc = umma_desc_mn_sw128(aV + (c * 2 + kk) * 2048);
+              const uint32_t tP = tmem_base + (uint32_t)((j & 1) * BKV + c * 32 + kk * 8);
+              umma_bf16_ts(tmem_base + 2 * BKV + (uint32_t)(c * D), tP, bdesc, idesc_pv, (jj > 0 || kk > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&kv_empty[s]);
+          umma_commit(&pv_full[j & 1]);
+        }
+      }
+      it0 += n;
+    }
+    __syncwarp();
+  } else {
+    // ---- softmax: thread = (query row, 32-key quarter) ----
+    const int qd = warp & 3;                   // TMEM lane quarter this warp may access
+    const int cs = (warp - 2) >> 2;            // key quarter of every tile
+    const int r = qd * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const uint32_t tO = tmem_base + 2 * BKV + (uint32_t)(cs * D) + lane_addr;
+    const float sl2 = p.scale * kLog2e;
+    int it0 = 0;
+    for (int seg = 0; seg < nseg; ++seg) {
+      const Segment g = segment(p, seg, nt);
+      const int q0 = g.q0, h = g.h, b = g.b;
+      const int nloc = g.kb1 - g.kb0;
+      float m_used = -INFINITY, l_run = 0.f;
+      for (int jj = 0; jj < nloc; ++jj) {
+        const int j = it0 + jj;
+        const int kb = g.kb0 + jj;
+        mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tS = tmem_base + (uint32_t)((j & 1) * BKV + cs * 32) + lane_addr;
+        uint32_t s[32];
+        int kvalid = p.nk - kb * BKV - cs * 32;
+        if (p.causal) kvalid = min(kvalid, q0 + r + 1 - kb * BKV - cs * 32);
+        auto load_s = [&]() {
+          tmem_ld32(tS, s);
+          tmem_ld_wait();
+          if (kvalid < 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i >= kvalid) s[i] = 0xff800000u;   // -inf
+          }
+        };
+        load_s();
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[i])); mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(s[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+        }
+        const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2);      // scale > 0
+        const bool fresh = m_used == -INFINITY;                 // nothing accumulated against a finite reference yet
+        const bool need = !fresh && m_new > m_used + kRescaleThreshold;
+        if (fresh) m_used = m_new;
+        if (__any_sync(0xffffffffu, need)) {                    // warp-voted: tcgen05.ld / st are warp-collective
+          // (need implies jj > 0: the reference is finite only after a tile of this segment has been accumulated)
+          mbar_wait(&pv_full[(j - 1) & 1], ((j - 1) >> 1) & 1);   // P V(j-1) has been added to O_c
+          tc_fence_after();
+          const float alpha = need ? ex2_approx(m_used - m_new) : 1.f;
+          const float2 av = make_float2(alpha, alpha);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t oc[32];
+            tmem_ld32(tO + half * 32, oc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float2 t = __fmul2_rn(make_float2(__uint_as_float(oc[i]), __uint_as_float(oc[i + 1])), av);
+              oc[i] = __float_as_uint(t.x); oc[i + 1] = __float_as_uint(t.y);
+            }
+            tmem_st32(tO + half * 32, oc);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+          if (need) m_used = m_new;
+          load_s();          // the scores are read again instead of being kept across this (rare) block: with both s[32] and the
+                             // O chunk live the 96-register budget spilled s on EVERY tile
+        }
+        const float mref = (m_used == -INFINITY) ? 0.f : m_used;
+        float2 rsa = make_float2(0.f, 0.f), rsb = make_float2(0.f, 0.f);
+        const float2 sl2v = make_float2(sl2, sl2), nm = make_float2(-mref, -mref);
+        uint32_t pw[16];
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[gq * 8 + i]), __uint_as_float(s[gq * 8 + i + 1])), sl2v, nm);
+            e[i] = ex2_approx(x.x); e[i + 1] = ex2_approx(x.y);
+          }
+          rsa = __fadd2_rn(rsa, __fadd2_rn(make_float2(e[0], e[1]), make_float2(e[2], e[3])));
+          rsb = __fadd2_rn(rsb, __fadd2_rn(make_float2(e[4], e[5]), make_float2(e[6], e[7])));
+          pw[gq * 4 + 0] = pack_bf162(e[0], e[1]); pw[gq * 4 + 1] = pack_bf162(e[2], e[3]);
+          pw[gq * 4 + 2] = pack_bf162(e[4], e[5]); pw[gq * 4 + 3] = pack_bf162(e[6], e[7]);
+        }
+        l_run += (rsa.x + rsa.y) + (rsb.x + rsb.y);
+        tmem_st16(tS, pw);                   // over the first 16 of my own 32 S columns (all of them are in registers)
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[j & 1]);
+        __syncwarp();
+      }
+      // ---- the segment's O_c: read back once, merge the four key quarters of each row ----
+      const int jl = it0 + nloc - 1;
+      mbar_wait(&pv_full[jl & 1], (jl >> 1) & 1);
+      tc_fence_after();
+      float o[D];
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tO, r0);
+        tmem_ld32(tO + 32, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { o[i] = __uint_as_float(r0[i]); o[32 + i] = __uint_as_float(r1[i]); }
+      }
+      tc_fence_before();
+      if (cs > 0) {
+        float* x = xch + ((cs - 1) * BQ + r) * 67;
+#pragma unroll
+        for (int i = 0; i < D; ++i) x[i] = o[i];
+        x[64] = m_used;
+        x[65] = l_run;
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      const int row = q0 + r;
+      if (cs == 0) {
+        float m = m_used;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) m = fmaxf(m, xch[(c * BQ + r) * 67 + 64]);
+        const float a0 = (m_used == -INFINITY) ? 0.f : ex2_approx(m_used - m);
+        float l = l_run * a0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) o[i] *= a0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float* x = xch + (c * BQ + r) * 67;
+          const float mc = x[64];
+          const float ac = (mc == -INFINITY) ? 0.f : ex2_approx(mc - m);
+          l += x[65] * ac;
+#pragma unroll
+          for (int i = 0; i < D; ++i) o[i] = fmaf(x[i], ac, o[i]);
+        }
+        if (g.slot >= 0) {
+          // key part of a leftover item: merged, UNNORMALISED (O, m, l) of this row; attn_fwd_fixup_kernel finishes
+          float* po = p.part_o + ((long long)g.slot * BQ + r) * D;
+#pragma unroll
+          for (int i = 0; i < D; i += 4) *reinterpret_cast<float4*>(po + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+          *reinterpret_cast<float2*>(p.part_ml + ((long long)g.slot * BQ + r) * 2) = make_float2(m, l);
+        } else if (row < p.nq) {
+          const float inv = 1.f / l;
+          bf16* dst = p.o + (long long)b * p.bso + (long long)row * p.ldo + h * D;
+#pragma unroll
+          for (int gq = 0; gq < 8; ++gq) {
+            uint4 w;
+            w.x = pack_bf162(o[gq * 8 + 0] * inv, o[gq * 8 + 1] * inv); w.y = pack_bf162(o[gq * 8 + 2] * inv, o[gq * 8 + 3] * inv);
+            w.z = pack_bf162(o[gq * 8 + 4] * inv, o[gq * 8 + 5] * inv); w.w = pack_bf162(o[gq * 8 + 6] * inv, o[gq * 8 + 7] * inv);
+            *reinterpret_cast<uint4*>(dst + gq * 8) = w;
+          }
+          if (p.lse) p.lse[((long long)b * p.heads + h) * p.nq + row] = (m + log2f(l)) / kLog2e;
+        }
+      }
+      it0 += nloc;
+      if (seg + 1 < nseg) asm volatile("bar.sync 1, 512;" ::: "memory");   // xch is written again by the next segment
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
 // Merge the key parts of every leftover item: thread = (query row, 8 output columns), 16 rows per CTA (8 CTAs per item so
 // that the launch spreads over the SMs); all loads of a thread are independent and issued up front - the kernel is pure
 // latency otherwise (12 dependent round trips to L2 measured 15 us for what is 5 MB of traffic).
@@ -634,6 +928,14 @@ extern "C" int vn_attention_fwd(const vn_attn_desc* d, vn_stream_t s) {
     p.part_ml = p.part_o + (size_t)n_left * parts * BQ * D;
   }
   p.dbg = vn_debug_buffer();
+  static int w16 = -1;
+  if (w16 < 0) {
+    const char* e = getenv("VN_ATTN_FWD_W16");
+    w16 = e ? atoi(e) : 0;
+    if (w16) VN_CUDA(cudaFuncSetAttribute(attn_fwd16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM16_BYTES));
+  }
+  if (w16) VN_LAUNCH(attn_fwd16_tc_kernel, grid, kThreads16, SMEM16_BYTES, (cudaStream_t)s, tq, tk, tv, p);
+  else
   VN_LAUNCH(attn_fwd_tc_kernel, grid, kThreads, SMEM_BYTES, (cudaStream_t)s, tq, tk, tv, p);
   if (p.n_left > 0) VN_LAUNCH(attn_fwd_fixup_kernel, p.n_left * 8, 128, 0, (cudaStream_t)s, p);
   return 0;
