@@ -928,12 +928,15 @@ extern "C" int vn_attention_fwd(const vn_attn_desc* d, vn_stream_t s) {
     p.part_ml = p.part_o + (size_t)n_left * parts * BQ * D;
   }
   p.dbg = vn_debug_buffer();
-  static int w16 = -1;
-  if (w16 < 0) {
+  // VN_ATTN_FWD_W16: 0 = never, 1 = always, 2 (default) = long key ranges only (nk >= 2048: the 64 x 64 self-attention, where it
+  // measures 4-8 % faster; it loses on items of a few tiles)
+  static int w16_mode = -1;
+  if (w16_mode < 0) {
     const char* e = getenv("VN_ATTN_FWD_W16");
-    w16 = e ? atoi(e) : 0;
-    if (w16) VN_CUDA(cudaFuncSetAttribute(attn_fwd16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM16_BYTES));
+    w16_mode = e ? atoi(e) : 2;
+    if (w16_mode) VN_CUDA(cudaFuncSetAttribute(attn_fwd16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM16_BYTES));
   }
+  const bool w16 = w16_mode == 1 || (w16_mode == 2 && d->nk >= 2048);
   if (w16) VN_LAUNCH(attn_fwd16_tc_kernel, grid, kThreads16, SMEM16_BYTES, (cudaStream_t)s, tq, tk, tv, p);
   else
   VN_LAUNCH(attn_fwd_tc_kernel, grid, kThreads, SMEM_BYTES, (cudaStream_t)s, tq, tk, tv, p);
