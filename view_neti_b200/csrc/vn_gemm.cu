@@ -294,6 +294,11 @@ __device__ __forceinline__ bool tile_row(const GemmParams& p, const TileCoord& c
   return (r < p.rows_a) && (h < p.H) && (w < p.W);
 }
 
+// split-K: does a dedicated exchange buffer (128 x BN fp32) fit behind the pipeline stages?  (227 KB of dynamic shared memory)
+template <int BN, int STAGES>
+constexpr bool split_exch_own() {
+  return STAGES * (BM * BK * 2 + BN * BK * 2) + BM * BN * 4 + BN * 4 + (2 * STAGES + 6) * 8 + 16 + 1024 <= 232448;
+}
 template <int BN, int STAGES, bool SPLIT, int MC, int CG>
 __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
@@ -307,7 +312,11 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
   constexpr int A_BYTES = BM * BK * 2;            // 16 KB
   constexpr int B_BYTES = (BN / CG) * BK * 2;     // CG == 2: each CTA of the pair holds half of the B tile
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int STAGING_BYTES = SPLIT ? 0 : BM * BN * 2;     // BN/64 blocks of [128 rows x 128 B], 128B-swizzled
+  // split-K: where it fits (BN 64 / 128 with 6 / 5 stages; BN 160 would have to drop to 4 stages, measured slower: 6.32 -> 6.36 ms) the
+  // exchange buffer gets its OWN shared memory behind the
+  // pipeline stages; wider tiles alias it with the stages and need a cluster barrier between the main loop and the exchange
+  constexpr bool kExchOwn = SPLIT && split_exch_own<BN, STAGES>();
+  constexpr int STAGING_BYTES = SPLIT ? (kExchOwn ? BM * BN * 4 : 0) : BM * BN * 2;     // BN/64 blocks of [128 rows x 128 B], 128B-swizzled
   constexpr int ACC_STAGES = SPLIT ? 1 : 2;
   constexpr int TMEM_COLS = (ACC_STAGES * BN) <= 32 ? 32 : (ACC_STAGES * BN) <= 64 ? 64 : (ACC_STAGES * BN) <= 128 ? 128
                           : (ACC_STAGES * BN) <= 256 ? 256 : 512;
@@ -361,6 +370,9 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // (own exchange buffer: the only thing the first cluster barrier still has to guarantee is that every CTA of the cluster has
+  //  started before a peer writes into its shared memory - arrive here, wait in front of the exchange, nobody ever blocks)
+  if (kExchOwn) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   if (threadIdx.x == 0) VN_STAMP(2);
 
   // ---- work assignment ----
@@ -725,7 +737,7 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
     // network with a quarter of the instructions of scalar stores (a row-major float4 layout, 32 scattered 16-byte
     // pieces per instruction, measured 1.7x slower on B200); the finishing threads read it back with LDS.128,
     // conflict-free for the same reason.
-    float* exch = reinterpret_cast<float*>(smem);
+    float* exch = reinterpret_cast<float*>(kExchOwn ? staging : smem);
     const TileCoord c = c_first;
     // Operands of the finishing pass that do not depend on the partials - bias (+ the per-image row-bias of a conv) of the
     // tile and this thread's residual values - are requested NOW, while the main loop still runs: read after the second
@@ -763,7 +775,8 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsPers, 1) vn_ge
       if (threadIdx.x == 64) VN_STAMP(8);
     }
     __syncwarp();
-    cluster_sync_all();                           // every CTA of the cluster is done with its pipeline stages
+    if (kExchOwn) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // completes the arrive made at set-up
+    else cluster_sync_all();                      // every CTA of the cluster is done with its pipeline stages
     if (threadIdx.x == 64) VN_STAMP(12);
     if (warp >= 2 && warp < 6) {
       const int q = warp & 3;
@@ -904,7 +917,8 @@ int num_sms() {
 
 template <int BN, int STAGES, bool SPLIT, int CG = 1>
 constexpr int smem_bytes() {
-  return STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + (SPLIT ? 0 : BM * BN * 2) + BN * 4 + (2 * STAGES + 6) * 8 + 16 + 1024;
+  return STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + (SPLIT ? (split_exch_own<BN, STAGES>() ? BM * BN * 4 : 0) : BM * BN * 2) + BN * 4 +
+         (2 * STAGES + 6) * 8 + 16 + 1024;
 }
 
 template <int BN, int STAGES, bool SPLIT, int MC = 1, int CG = 1>
