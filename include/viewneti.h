@@ -171,6 +171,8 @@ typedef struct vn_attn_desc {
   double* dkv_acc;                        /* NULL or zeroed scratch, see above */
   int32_t causal;                         /* 1: key j is visible to query i only if j <= i (CLIP text encoder) */
   void*   ws; int64_t ws_bytes;           /* fwd: scratch of vn_attention_fwd_workspace_bytes() bytes, or NULL (see below) */
+  int32_t defer_dkv_finish;               /* bwd with dkv_acc: 1 = leave dK / dV in the fp64 accumulator; the caller runs
+                                             vn_attention_dkv_finish later, e.g. on another stream (see below) */
 } vn_attn_desc;
 /* Forward work balancing: when the (query tile, head, image) items do not fill whole waves of SMs (64x64 latents at B = 1:
  * 160 items on 148 SMs), the leftover items are split along the keys over all SMs and merged by a second small launch;
@@ -183,6 +185,12 @@ size_t vn_attention_fwd_workspace_bytes(int nb, int heads, int nq, int nk);
 size_t vn_attention_bwd_workspace_bytes(int nb, int heads, int nq, int nk, int has_dq);
 int vn_attention_fwd(const vn_attn_desc* d, vn_stream_t s);
 int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s);
+/* Second half of a backward launched with defer_dkv_finish = 1 (same descriptor): fp64 accumulator -> bf16 dK / dV, accumulator
+ * zeroed again.  Nothing downstream of the cross-attention's dQ needs dK / dV (they only feed the context gradients,
+ * reference xti_attention_processor.py:38-42 under coach.py:214), so the UNet plan runs this on its side stream instead of on
+ * the chain of the backward; a later backward that uses the SAME accumulator must be ordered after it.  A no-op when the
+ * backward wrote dK / dV directly (no query split). */
+int vn_attention_dkv_finish(const vn_attn_desc* d, vn_stream_t s);
 
 /* ------------------------------------------------------------------------------------------------
  * Resampling / small convolutions / glue

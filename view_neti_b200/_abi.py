@@ -57,6 +57,7 @@ class AttnDesc(C.Structure):
         ("dkv_acc", C.c_void_p),
         ("causal", C.c_int32),
         ("ws", C.c_void_p), ("ws_bytes", C.c_int64),
+        ("defer_dkv_finish", C.c_int32),
     ]
 
 
@@ -97,6 +98,7 @@ SIGNATURES = {
     "vn_seq_attention_bwd": (C.c_int, [C.POINTER(AttnDesc), _I, _P]),
     "vn_attention_fwd": (C.c_int, [C.POINTER(AttnDesc), _P]),
     "vn_attention_bwd": (C.c_int, [C.POINTER(AttnDesc), _P]),
+    "vn_attention_dkv_finish": (C.c_int, [C.POINTER(AttnDesc), _P]),
     "vn_upsample2x_fwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _I, _I, _P]),
     "vn_upsample2x_bwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _I, _I, _P]),
     "vn_im2col_s2": (C.c_int, [_P, _L, _P, _I, _I, _I, _I, _P]),

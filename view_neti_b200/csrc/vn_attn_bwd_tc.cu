@@ -902,10 +902,12 @@ extern "C" int vn_attention_bwd(const vn_attn_desc* d, vn_stream_t s) {
     VN_LAUNCH(attn_bwd_fixup_kernel, p.n_left * 8, 128, 0, st, p);
   } else if (splits > 1) {
     VN_LAUNCH(attn_bwd_tc_kernel<true>, grid, kThreads, SMEM, st, tq, tk, tv, tdo, p);
-    const long long pairs = (long long)d->nb * d->nk * d->heads * D / 2;
-    int blocks = (int)vn_cdiv64(pairs, 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    VN_LAUNCH(attn_dkv_finish_kernel, blocks, 256, 0, st, p);
+    if (!d->defer_dkv_finish) {
+      const long long pairs = (long long)d->nb * d->nk * d->heads * D / 2;
+      int blocks = (int)vn_cdiv64(pairs, 256);
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      VN_LAUNCH(attn_dkv_finish_kernel, blocks, 256, 0, st, p);
+    }
   } else {
     VN_LAUNCH(attn_bwd_tc_kernel<false>, grid, kThreads, SMEM, st, tq, tk, tv, tdo, p);
   }
@@ -916,4 +918,29 @@ extern "C" size_t vn_attention_bwd_workspace_bytes(int nb, int heads, int nq, in
   int n_left = 0, parts = 0;
   bwd_split(nb, heads, nq, nk, has_dq, &n_left, &parts);
   return (size_t)n_left * parts * 2 * T * D * sizeof(float);
+}
+
+extern "C" int vn_attention_dkv_finish(const vn_attn_desc* d, vn_stream_t s) {
+  VN_CHECK(d != nullptr, "attention dkv finish: null descriptor");
+  VN_CHECK(d->dkv_acc != nullptr && d->dk != nullptr && d->dv != nullptr, "attention dkv finish: dkv_acc, dk and dv are required");
+  cudaStream_t st = (cudaStream_t)s;
+  // the same query-split decision as vn_attention_bwd: without a split dK / dV were written directly
+  const int ktiles = vn_cdiv(d->nk, T), qtiles = vn_cdiv(d->nq, T);
+  const long long base_ctas = (long long)ktiles * d->heads * d->nb;
+  if (base_ctas >= 148) return 0;
+  int splits = (int)((148 + base_ctas - 1) / base_ctas);
+  if (splits > qtiles) splits = qtiles;
+  if (splits < 1) splits = 1;
+  splits = vn_cdiv(qtiles, vn_cdiv(qtiles, splits));
+  if (splits <= 1) return 0;
+  BwdParams p{};
+  p.nb = d->nb; p.heads = d->heads; p.nq = d->nq; p.nk = d->nk;
+  p.dk = (bf16*)d->dk; p.lddk = d->lddk; p.bsdk = d->bsdk;
+  p.dv = (bf16*)d->dv; p.lddv = d->lddv; p.bsdv = d->bsdv;
+  p.dkv_acc = d->dkv_acc;
+  const long long pairs = (long long)d->nb * d->nk * d->heads * D / 2;
+  int blocks = (int)vn_cdiv64(pairs, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  VN_LAUNCH(attn_dkv_finish_kernel, blocks, 256, 0, st, p);
+  return 0;
 }

@@ -237,6 +237,8 @@ class _Plan:
         self.ev_temb = torch.cuda.Event()
         self.ev_kv = [torch.cuda.Event() for _ in range(self.n_layers)]
         self.ev_dkv = [torch.cuda.Event() for _ in range(self.n_layers)]
+        self.ev_fin = [torch.cuda.Event() for _ in range(self.n_layers)]   # dK / dV finished on the side stream (accumulator free)
+        self._fin_ev = None
         self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self.launches: Dict[str, int] = {}
         self._saved = False
@@ -415,13 +417,20 @@ class _Plan:
         dkv2 = self.buf(name + ".dkv2", (2 * nb * L, c))              # [dK ; dV] rows: one operand for both context gradients
         dk2, dv2 = dkv2[:nb * L].view(nb, L, c), dkv2[nb * L:].view(nb, L, c)
         _, k2, v2 = self._kv2(name, c)
-        ops.attention_bwd(B[name + ".q2"], k2, v2, B[name + ".o2"], B[name + ".lse2"], do2,
-                          self.buf(name + ".delta", (nb, heads, hw), F32), dq2, dk2, dv2, heads, dkv_acc=self.ws.dkv)
-        # d CONTEXT_TENSOR_l / d CONTEXT_TENSOR_BYPASS_l (fp32 out) leave the chain: side stream, joined in backward()
+        if self._fin_ev is not None:                                     # the shared fp64 accumulator is free (zero) again
+            torch.cuda.current_stream().wait_event(self._fin_ev)
+        desc = ops.attention_bwd(B[name + ".q2"], k2, v2, B[name + ".o2"], B[name + ".lse2"], do2,
+                                 self.buf(name + ".delta", (nb, heads, hw), F32), dq2, dk2, dv2, heads, dkv_acc=self.ws.dkv,
+                                 defer_finish=True)
+        # dK / dV -> bf16 and d CONTEXT_TENSOR_l / d CONTEXT_TENSOR_BYPASS_l (fp32 out) leave the chain: side stream, joined in
+        # backward(); only dQ continues on the main chain
         self.ev_dkv[layer].record(torch.cuda.current_stream())
         self.side.wait_event(self.ev_dkv[layer])
         with torch.cuda.stream(self.side):
+            ops.attention_dkv_finish(desc)
+            self.ev_fin[layer].record(self.side)
             ops.gemm(dkv2, t.kv2b, self.d_ctx_store[layer], ws=self.ws)
+        self._fin_ev = self.ev_fin[layer]
         if first:
             return                                                       # nothing upstream depends on the contexts
         dn2 = dn3
@@ -584,6 +593,7 @@ class _Plan:
     def backward(self) -> torch.Tensor:
         """d_ctx[k|v][layer] = d<eps, d_eps>/d ctx for the activations of the last forward (coach.py:214, dgrad only)."""
         assert self._saved, "backward() needs a forward() on this plan first"
+        self._fin_ev = None                      # no deferred dK / dV conversion pending on the side stream yet
         eng, cfg = self.eng, self.eng.cfg
         nb, h, w = self.nb, self.h, self.w
         ch = cfg.block_out_channels

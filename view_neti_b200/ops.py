@@ -266,7 +266,9 @@ def attention_bwd_workspace_bytes(nb: int, heads: int, nq: int, nk: int, has_dq:
 
 
 def attention_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, heads, scale=0.125, dkv_acc=None, causal=False,
-                  ws: Optional[torch.Tensor] = None):
+                  ws: Optional[torch.Tensor] = None, defer_finish: bool = False):
+    """defer_finish (with dkv_acc): dK / dV stay in the fp64 accumulator; pass the returned descriptor to
+    attention_dkv_finish - on any stream ordered after this call - to convert them and zero the accumulator again."""
     d = _attn_desc(q, k, v, o, lse, heads, scale)
     d.causal = int(causal)
     if ws is not None:
@@ -278,7 +280,14 @@ def attention_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, heads, scale=0.125, d
     d.dk, d.lddk, d.bsdk = ptr(dk), dk.stride(1), dk.stride(0)
     d.dv, d.lddv, d.bsdv = ptr(dv), dv.stride(1), dv.stride(0)
     d.dkv_acc = ptr(dkv_acc)
+    d.defer_dkv_finish = 1 if (defer_finish and dkv_acc is not None) else 0
     check(_abi.load().vn_attention_bwd(C.byref(d), stream()), "attention_bwd")
+    return d
+
+
+def attention_dkv_finish(d) -> None:
+    """Second half of attention_bwd(..., defer_finish=True): fp64 accumulator -> bf16 dK / dV on the CURRENT stream."""
+    check(_abi.load().vn_attention_dkv_finish(C.byref(d), stream()), "attention_dkv_finish")
 
 
 def seq_attention_fwd(q, k, v, o, lse, heads, scale=0.125, causal=True):
